@@ -1,0 +1,102 @@
+// api_float.cu -- pffft_* : the single-precision C-ABI (ref include/pffft/pffft.h:124-250) and the
+// selection of the size-tuned kernels.
+#include "../../include/pffft/pffft_b200.h"
+#include "api_impl.cuh"
+#include "fast_kernels.cuh"
+
+namespace pf {
+
+// ---- tuned-kernel hooks for float -------------------------------------------------------------
+// variant ids for c2c N=1024 (PFFFT_B200_C1024 environment variable, read when the plan is built;
+// a tuning knob for profiling runs, the default is the measured best)
+enum { V_LDG_4x4 = 0, V_LDG_8x2 = 1, V_BULK_8 = 2, V_BULK_12 = 3, V_BULK_4x3 = 4, V_COUNT = 5 };
+static const char* kVariantName[V_COUNT] = {"c1024_warp_ldg_4w", "c1024_warp_ldg_8w", "c1024_warp_bulk_8w",
+                                            "c1024_warp_bulk_12w", "c1024_warp_bulk_4w"};
+
+template <int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
+static int launch_ldg(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+  auto kern = k_c1024_ldg<SIGN, WARPS, MINB, ZIN, ZOUT>;
+  const size_t smem = (1024 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
+  static thread_local bool attr = false;
+  if (!attr) { PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  long long ctas = (batch + WARPS - 1) / WARPS;
+  const long long cap = (long long)s->sm_count * MINB;
+  if (ctas > cap) ctas = cap;
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int SIGN, int WARPS, int MINB, bool ZOUT>
+static int launch_bulk(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+  auto kern = k_c1024_bulk<SIGN, WARPS, MINB, ZOUT>;
+  const size_t smem = (1024 + (size_t)WARPS * 2 * kW1024Tile) * sizeof(cf) + (size_t)WARPS * 2 * sizeof(uint64_t);
+  static thread_local bool attr = false;
+  if (!attr) { PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  long long ctas = (batch + WARPS - 1) / WARPS;
+  const long long cap = (long long)s->sm_count * MINB;
+  if (ctas > cap) ctas = cap;
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int SIGN, bool ZIN, bool ZOUT>
+static int run_c1024(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+  switch (s->fast_variant) {
+    case V_LDG_8x2: return launch_ldg<SIGN, 8, 2, ZIN, ZOUT>(s, in, out, batch, st);
+    case V_BULK_8:  if (!ZIN) return launch_bulk<SIGN, 8, 1, ZOUT>(s, in, out, batch, st); break;
+    case V_BULK_12: if (!ZIN) return launch_bulk<SIGN, 12, 1, ZOUT>(s, in, out, batch, st); break;
+    case V_BULK_4x3: if (!ZIN) return launch_bulk<SIGN, 4, 3, ZOUT>(s, in, out, batch, st); break;
+    default: break;
+  }
+  return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
+}
+
+template <> struct FastHooks<float> {
+  static size_t extra_table_cpx(int N, int transform) { return (transform == XF_COMPLEX && N == 1024) ? 1024 : 0; }
+  // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
+  static void fill_extra_table(int N, int transform, float* dst) {
+    if (!(transform == XF_COMPLEX && N == 1024)) return;
+    for (int k2 = 0; k2 < 32; ++k2)
+      for (int n1 = 0; n1 < 32; ++n1) {
+        long double c, sn;
+        pfplan::unit_root((long long)n1 * k2, 1024, &c, &sn);
+        dst[2 * (k2 * 32 + n1)] = (float)c; dst[2 * (k2 * 32 + n1) + 1] = (float)sn;
+      }
+  }
+  static bool plan(Setup<float>* s) {
+    if (!(s->transform == XF_COMPLEX && s->N == 1024)) return false;
+    int v = V_LDG_4x4;
+    if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
+    s->fast_variant = v;
+    s->kernel_name = kVariantName[v];
+    return true;
+  }
+  static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st) {
+    if (direction == DIR_FORWARD) return ordered ? run_c1024<-1, false, false>(s, in, out, batch, st)
+                                                 : run_c1024<-1, false, true>(s, in, out, batch, st);
+    return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
+                   : run_c1024<+1, true, false>(s, in, out, batch, st);
+  }
+};
+
+}  // namespace pf
+
+PF_API(pffft_, pffftb_, PFFFT_Setup, float, pf::FastHooks<float>, floats_per_transform)
+
+extern "C" PFFFT_EXPORT int pffftb_setup_device(const PFFFT_Setup* s) { return s ? s->device : -1; }
+
+// ---- internal C++ entry points used by fastconv.cu (see internal_api.h)
+#include "internal_api.h"
+namespace pf {
+int float_transform_device(PFFFT_Setup* s, const float* in, float* out, long long batch, int direction, int ordered,
+                           cudaStream_t st, const XformOpts& o) {
+  return engine_transform_device<float, FastHooks<float>>(s, in, out, batch, direction, ordered, st, o);
+}
+int float_zconvolve_device(PFFFT_Setup* s, const float* a, const float* b, float* ab, float scaling, long long batch,
+                           int b_shared, int accumulate, cudaStream_t st) {
+  return engine_zconvolve_device<float>(s, a, b, ab, scaling, batch, b_shared, accumulate, st);
+}
+}  // namespace pf

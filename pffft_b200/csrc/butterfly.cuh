@@ -1,0 +1,157 @@
+// butterfly.cuh -- the arithmetic core: small-radix DFTs and fully-unrolled register FFTs.
+//
+// Replaces (does not translate) the reference's passf2/3/4/5_ps (src/pffft_priv_impl.h:122-321)
+// and, through the N/2 complex packing, radf*/radb* (:323-807).  The reference walks FFTPACK
+// passes over 4-lane SIMD vectors; here a thread owns R points in registers, runs a complete
+// radix-R DIT network on them with compile-time twiddles (FMA-folded butterflies), and exchanges
+// data with other lanes only between such networks.
+//
+// Sign convention (include/pffft/pffft.h:134): SIGN=-1 is PFFFT_FORWARD
+// (e^{-2 pi i jk/N}), SIGN=+1 is PFFFT_BACKWARD; nothing is normalised.
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+namespace pf {
+
+// ---------------------------------------------------------------------------------------------
+// compile-time trigonometry: cos/sin(2*pi*j/n) evaluated exactly-rounded enough for double
+// (quadrant/half-quadrant reduction on the integer fraction, then Taylor on |x| <= pi/4).
+// ---------------------------------------------------------------------------------------------
+namespace ct {
+constexpr double kPi = 3.14159265358979323846264338327950288;
+__host__ __device__ constexpr double taylor_sin(double x) {
+  double x2 = x * x, term = x, sum = x;
+  for (int k = 1; k <= 12; ++k) { term *= -x2 / double((2 * k) * (2 * k + 1)); sum += term; }
+  return sum;
+}
+__host__ __device__ constexpr double taylor_cos(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int k = 1; k <= 12; ++k) { term *= -x2 / double((2 * k - 1) * (2 * k)); sum += term; }
+  return sum;
+}
+struct cs { double c, s; };
+// (cos, sin) of 2*pi*j/n for 0 <= j < n
+__host__ __device__ constexpr cs cossin2pi(long long j, long long n) {
+  j %= n; if (j < 0) j += n;
+  long long q = (4 * j) / n;            // quadrant
+  long long r = 4 * j - q * n;          // position inside the quadrant, angle = (r/n) * pi/2
+  double c0 = 1.0, s0 = 0.0;
+  if (2 * r <= n) { double a = (double(r) / double(n)) * (kPi / 2); c0 = taylor_cos(a); s0 = taylor_sin(a); }
+  else { double a = (double(n - r) / double(n)) * (kPi / 2); c0 = taylor_sin(a); s0 = taylor_cos(a); }
+  if (r == 0) { c0 = 1.0; s0 = 0.0; }
+  if (2 * r == n) { c0 = 0.70710678118654752440; s0 = c0; }
+  switch (q) {
+    case 0: return cs{c0, s0};
+    case 1: return cs{-s0, c0};
+    case 2: return cs{-c0, -s0};
+    default: return cs{s0, -c0};
+  }
+}
+__host__ __device__ constexpr int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+__host__ __device__ constexpr int bitrev(int x, int bits) { int r = 0; for (int i = 0; i < bits; ++i) if (x & (1 << i)) r |= 1 << (bits - 1 - i); return r; }
+}  // namespace ct
+
+// ---------------------------------------------------------------------------------------------
+// radix-R DFT on R values held in an array (generic kernels; runtime-selected radix).
+// c_k = sum_j a_j * exp(SIGN * 2 pi i * j k / R), in place, natural order in and out.
+// Constants as in SURVEY App. B (taur/taui, tr11..ti12) -- they are just cos/sin of 2pi/3, 2pi/5.
+// ---------------------------------------------------------------------------------------------
+template <int SIGN, typename T> PF_HD void dft2(cpx<T>* a) {
+  cpx<T> t = a[0] - a[1]; a[0] = a[0] + a[1]; a[1] = t;
+}
+template <int SIGN, typename T> PF_HD void dft3(cpx<T>* a) {
+  const T hs3 = T(SIGN) * T(0.86602540378443864676372317075294);
+  cpx<T> t1 = a[1] + a[2];
+  cpx<T> m = mk<T>(a[0].x - T(0.5) * t1.x, a[0].y - T(0.5) * t1.y);
+  cpx<T> d = scale(a[1] - a[2], hs3);          // SIGN*sin(2pi/3)*(a1-a2)
+  a[0] = a[0] + t1;
+  a[1] = mk<T>(m.x - d.y, m.y + d.x);          // m + i*d
+  a[2] = mk<T>(m.x + d.y, m.y - d.x);          // m - i*d
+}
+template <int SIGN, typename T> PF_HD void dft4(cpx<T>* a) {
+  cpx<T> t0 = a[0] + a[2], t1 = a[0] - a[2], t2 = a[1] + a[3];
+  cpx<T> t3 = mul_si<SIGN>(a[1] - a[3]);
+  a[0] = t0 + t2; a[2] = t0 - t2; a[1] = t1 + t3; a[3] = t1 - t3;
+}
+template <int SIGN, typename T> PF_HD void dft5(cpx<T>* a) {
+  const T tr11 = T(0.30901699437494742410229341718282), ti11 = T(SIGN) * T(0.95105651629515357211643933337938);
+  const T tr12 = T(-0.80901699437494742410229341718282), ti12 = T(SIGN) * T(0.58778525229247312916870595463907);
+  cpx<T> t1 = a[1] + a[4], t2 = a[2] + a[3], t3 = a[1] - a[4], t4 = a[2] - a[3];
+  cpx<T> m1 = mk<T>(a[0].x + tr11 * t1.x + tr12 * t2.x, a[0].y + tr11 * t1.y + tr12 * t2.y);
+  cpx<T> m2 = mk<T>(a[0].x + tr12 * t1.x + tr11 * t2.x, a[0].y + tr12 * t1.y + tr11 * t2.y);
+  cpx<T> n1 = mk<T>(ti11 * t3.x + ti12 * t4.x, ti11 * t3.y + ti12 * t4.y);
+  cpx<T> n2 = mk<T>(ti12 * t3.x - ti11 * t4.x, ti12 * t3.y - ti11 * t4.y);
+  a[0] = a[0] + t1 + t2;
+  a[1] = mk<T>(m1.x - n1.y, m1.y + n1.x);      // m1 + i n1
+  a[4] = mk<T>(m1.x + n1.y, m1.y - n1.x);
+  a[2] = mk<T>(m2.x - n2.y, m2.y + n2.x);
+  a[3] = mk<T>(m2.x + n2.y, m2.y - n2.x);
+}
+template <int R, int SIGN, typename T> PF_HD void dftR(cpx<T>* a) {
+  if (R == 2) dft2<SIGN>(a);
+  else if (R == 3) dft3<SIGN>(a);
+  else if (R == 4) dft4<SIGN>(a);
+  else dft5<SIGN>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register FFT: N = 2^m points in cpx<T> v[N], decimation in time, all indices compile-time.
+// Input convention: v[p] holds x[bitrev(p)]  (the caller chooses registers at load time, so the
+// bit reversal costs nothing); output v[k] = X[k] in natural order.
+// One butterfly (A,B) <- (A + w B, A - w B), w = exp(SIGN 2 pi i J/G), G = group size:
+//   J=0, G/4      : adds only
+//   G/8, 3G/8     : 2 adds + 4 fma          (w = (+-1 + SIGN i)/sqrt2)
+//   general       : 6 fma                    (A' = A + wB by 2 fma each part, B' = 2A - A')
+// -> 388 instructions for N=32 instead of 456 for the mul-then-add form.
+// ---------------------------------------------------------------------------------------------
+template <int J, int G, int SIGN, typename T> PF_HD void dit_bfly(cpx<T>& A, cpx<T>& B) {
+  const cpx<T> a = A, b = B;
+  if constexpr (J == 0) {
+    A = a + b; B = a - b;
+  } else if constexpr (4 * J == G) {
+    const cpx<T> t = mul_si<SIGN>(b);
+    A = a + t; B = a - t;
+  } else if constexpr (8 * J == G) {
+    const T h = T(0.70710678118654752440084436210485);
+    const T sx = (SIGN < 0) ? (b.x + b.y) : (b.x - b.y);
+    const T sy = (SIGN < 0) ? (b.y - b.x) : (b.y + b.x);
+    A.x = a.x + h * sx; B.x = a.x - h * sx;
+    A.y = a.y + h * sy; B.y = a.y - h * sy;
+  } else if constexpr (8 * J == 3 * G) {
+    const T h = T(0.70710678118654752440084436210485);
+    const T sx = (SIGN < 0) ? (b.x - b.y) : (b.x + b.y);
+    const T sy = (SIGN < 0) ? (b.y + b.x) : (b.y - b.x);
+    A.x = a.x - h * sx; B.x = a.x + h * sx;
+    A.y = a.y - h * sy; B.y = a.y + h * sy;
+  } else {
+    constexpr ct::cs w = ct::cossin2pi(J, G);
+    const T c = T(w.c), s = T(SIGN) * T(w.s);
+    const T px = a.x + b.x * c - b.y * s;      // Re(a + w b)
+    const T py = a.y + b.x * s + b.y * c;      // Im(a + w b)
+    A.x = px; A.y = py;
+    B.x = fma(T(2), a.x, -px); B.y = fma(T(2), a.y, -py);   // explicit: the compiler would rewrite 2*a as a+a and lose the fusion
+  }
+}
+
+// one DIT level: groups of size G over the N-point array (element p -> v[BASE + p*STRIDE])
+template <int N, int G, int SIGN, int BASE, int STRIDE, int P = 0, typename T, int TOTAL>
+PF_HD void dit_level(cpx<T> (&v)[TOTAL]) {
+  if constexpr (P < N / 2) {
+    constexpr int H = G / 2;
+    constexpr int g = P / H, j = P % H;
+    dit_bfly<j, G, SIGN>(v[BASE + (g * G + j) * STRIDE], v[BASE + (g * G + j + H) * STRIDE]);
+    dit_level<N, G, SIGN, BASE, STRIDE, P + 1>(v);
+  }
+}
+template <int N, int SIGN, int BASE, int STRIDE, int G = 2, typename T, int TOTAL>
+PF_HD void dit_fft(cpx<T> (&v)[TOTAL]) {
+  if constexpr (G <= N) {
+    dit_level<N, G, SIGN, BASE, STRIDE>(v);
+    dit_fft<N, SIGN, BASE, STRIDE, 2 * G>(v);
+  }
+}
+// convenience: whole array
+template <int N, int SIGN, typename T> PF_HD void reg_fft(cpx<T> (&v)[N]) { dit_fft<N, SIGN, 0, 1>(v); }
+
+}  // namespace pf

@@ -1,0 +1,404 @@
+// engine.cuh -- host-side engine behind the C-ABI: plan objects, kernel selection and launch,
+// host<->device staging.  Templated on the scalar type; api_float.cu / api_double.cu instantiate it.
+//
+// Plays the role of pffft_new_setup / pffft_transform_internal in the reference
+// (src/pffft_priv_impl.h:1062-1112, :1465-1532) -- validation rules and layouts are the
+// reference's, everything else (plan contents, kernels, batching, streams) is this engine's.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "generic_kernels.cuh"
+#include "plan.h"
+
+namespace pf {
+
+// ---------------------------------------------------------------- process-wide diagnostics (host_common.cu)
+void set_error(const char* where, cudaError_t e);
+void set_error_msg(const char* msg);
+void count_launch(int n = 1);
+bool ptr_is_device(const void* p);   // cudaPointerGetAttributes: device/managed -> true, host/unregistered -> false
+
+#define PF_CUDA_OK(call)                                        \
+  do {                                                          \
+    cudaError_t _e = (call);                                    \
+    if (_e != cudaSuccess) { ::pf::set_error(#call, _e); return (int)_e; } \
+  } while (0)
+
+enum KernelKind { KK_SMEM = 0, KK_GLOBAL = 1, KK_FAST = 2 };
+
+// per-call options beyond the classic API (used by pffastconv: overlapping strided blocks)
+struct XformOpts {
+  long long in_stride = -1;    // elements; -1 -> contiguous
+  long long out_stride = -1;
+  long long in_limit = -1;     // real-time load: readable elements from `in` (zero padding beyond)
+  int out_count = -1;          // real-time store: leading samples stored per transform
+};
+
+struct Slot {                  // one lane of the host-pointer pipeline
+  cudaStream_t stream = nullptr;
+  void* d_in = nullptr;
+  void* d_out = nullptr;
+};
+
+template <typename T> struct Setup {
+  int N = 0, transform = 0, Nc = 0;
+  int device = 0, sm_count = 0;
+  int nfac = 0;
+  int fac[PF_MAX_FACTORS];
+  // device tables: [tw: Nc cpx][twr: N/2 cpx (real only)][fast-kernel tables]
+  void* d_tables = nullptr;
+  size_t table_bytes = 0;
+  const cpx<T>* tw = nullptr;
+  const cpx<T>* twr = nullptr;
+  const cpx<T>* tw_fast = nullptr;
+  cudaStream_t stream = nullptr;          // device-pointer calls are enqueued here (0 = legacy default stream)
+  // kernel choice
+  int kind = KK_SMEM;
+  int fast_variant = 0;
+  int tpc = 1;                            // transforms resident per CTA (shared-memory kernel)
+  size_t smem_bytes = 0;
+  const char* kernel_name = "";
+  // host-pointer pipeline (3 slots: H2D / kernels / D2H overlap across slots)
+  std::mutex mu;
+  Slot slot[3];
+  size_t slot_elems = 0;                  // capacity of each d_in / d_out, in T elements
+  // scratch for the global-memory (large N) path
+  cpx<T>* d_scratch[2] = {nullptr, nullptr};
+  size_t scratch_cpx = 0;
+  std::mutex scratch_mu;                  // enqueue order of scratch users
+  cudaEvent_t scratch_done = nullptr;     // ... and their execution order across streams
+  int occ_cache[64] = {0};                // resident CTAs/SM of each generic-kernel instantiation (0 = not queried yet)
+
+  size_t per() const { return transform == XF_REAL ? (size_t)N : 2 * (size_t)N; }   // elements per transform
+};
+
+template <typename T> struct FastHooks {
+  // implemented by api_float.cu for the sizes that have tuned kernels; default: none
+  static bool plan(Setup<T>*) { return false; }
+  static int run(Setup<T>*, const T*, T*, long long, int, int, cudaStream_t) { return -1; }
+  static size_t extra_table_cpx(int /*N*/, int /*transform*/) { return 0; }
+  static void fill_extra_table(int, int, T*) {}
+};
+
+// ---------------------------------------------------------------- plan creation / destruction
+template <typename T, typename S> void engine_destroy_setup(S* s);
+
+// S = the C-ABI's opaque struct (derives from Setup<T>)
+template <typename T, typename Hooks, typename S>
+S* engine_new_setup(int N, int transform) {
+  if (!pfplan::setup_size_ok(N, transform)) return nullptr;          // ref :1066-1078, :1105-1109
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error_msg("pffft_new_setup: no CUDA device (this engine has no CPU path)"); cudaGetLastError(); return nullptr; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error_msg("pffft_new_setup: cudaGetDeviceProperties failed"); cudaGetLastError(); return nullptr; }
+  if (prop.major < 10) { set_error_msg("pffft_new_setup: device is not sm_100-class; this library contains sm_100a code only"); return nullptr; }
+
+  S* s = new S();
+  s->N = N; s->transform = transform; s->Nc = (transform == XF_REAL) ? N / 2 : N;
+  s->device = dev; s->sm_count = prop.multiProcessorCount;
+  std::vector<int> f = pfplan::factorize(s->Nc);
+  s->nfac = (int)f.size();
+  for (int i = 0; i < s->nfac; ++i) s->fac[i] = f[i];
+
+  // tables
+  const size_t n_tw = (size_t)s->Nc, n_twr = (transform == XF_REAL) ? (size_t)N / 2 : 0;
+  const size_t n_fast = Hooks::extra_table_cpx(N, transform);
+  std::vector<T> host(2 * (n_tw + n_twr + n_fast));
+  pfplan::fill_roots<T>(host.data(), (long long)n_tw, s->Nc);
+  if (n_twr) pfplan::fill_roots<T>(host.data() + 2 * n_tw, (long long)n_twr, N);
+  if (n_fast) Hooks::fill_extra_table(N, transform, host.data() + 2 * (n_tw + n_twr));
+  s->table_bytes = host.size() * sizeof(T);
+  if (cudaMalloc(&s->d_tables, s->table_bytes) != cudaSuccess ||
+      cudaMemcpy(s->d_tables, host.data(), s->table_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("pffft_new_setup: table upload", cudaGetLastError());
+    if (s->d_tables) cudaFree(s->d_tables);
+    delete s; return nullptr;
+  }
+  s->tw = reinterpret_cast<const cpx<T>*>(s->d_tables);
+  s->twr = n_twr ? s->tw + n_tw : nullptr;
+  s->tw_fast = n_fast ? s->tw + n_tw + n_twr : nullptr;
+
+  // kernel family
+  const size_t cbytes = sizeof(cpx<T>);
+  const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;      // 227 KB on sm_100
+  if (2 * (size_t)s->Nc * cbytes + 1024 <= smem_cap) {
+    s->kind = KK_SMEM;
+    int tpc = (int)(2048 / (size_t)s->Nc); if (tpc < 1) tpc = 1;    // ~16-32 KB of transforms per CTA
+    s->tpc = tpc;
+    s->smem_bytes = 2 * (size_t)tpc * s->Nc * cbytes;
+    s->kernel_name = "smem_stockham";
+  } else {
+    s->kind = KK_GLOBAL;
+    s->kernel_name = "global_stockham";
+  }
+  if (Hooks::plan(s)) s->kind = KK_FAST;
+
+  // one transform's worth of staging so single host-pointer calls never allocate (README.md:269-271 of the reference)
+  for (int i = 0; i < 3; ++i) {
+    if (cudaStreamCreateWithFlags(&s->slot[i].stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create", cudaGetLastError()); }
+  }
+  s->slot_elems = s->per();
+  bool ok = true;
+  for (int i = 0; i < 3 && ok; ++i) {
+    ok = cudaMalloc(&s->slot[i].d_in, s->slot_elems * sizeof(T)) == cudaSuccess &&
+         cudaMalloc(&s->slot[i].d_out, s->slot_elems * sizeof(T)) == cudaSuccess;
+  }
+  if (ok && s->kind == KK_GLOBAL) {
+    s->scratch_cpx = (size_t)s->Nc;
+    ok = cudaMalloc((void**)&s->d_scratch[0], s->scratch_cpx * cbytes) == cudaSuccess &&
+         cudaMalloc((void**)&s->d_scratch[1], s->scratch_cpx * cbytes) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->scratch_done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) { set_error("pffft_new_setup: device allocation", cudaGetLastError()); engine_destroy_setup<T, S>(s); return nullptr; }
+  return s;
+}
+
+template <typename T, typename S> void engine_destroy_setup(S* s) {
+  if (!s) return;
+  int cur = 0; cudaGetDevice(&cur);
+  if (cur != s->device) cudaSetDevice(s->device);
+  for (int i = 0; i < 3; ++i) {
+    if (s->slot[i].stream) { cudaStreamSynchronize(s->slot[i].stream); cudaStreamDestroy(s->slot[i].stream); }
+    if (s->slot[i].d_in) cudaFree(s->slot[i].d_in);
+    if (s->slot[i].d_out) cudaFree(s->slot[i].d_out);
+  }
+  for (int i = 0; i < 2; ++i) if (s->d_scratch[i]) cudaFree(s->d_scratch[i]);
+  if (s->scratch_done) cudaEventDestroy(s->scratch_done);
+  if (s->d_tables) cudaFree(s->d_tables);
+  if (cur != s->device) cudaSetDevice(cur);
+  delete s;
+}
+
+// ---------------------------------------------------------------- launches (device pointers)
+template <typename T, int LM, int SM, int SIGN>
+int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
+  if (s->kind == KK_GLOBAL) {
+    // the ping-pong scratch is shared by every stream using this plan: serialise its users
+    std::lock_guard<std::mutex> lock(s->scratch_mu);
+    PF_CUDA_OK(cudaStreamWaitEvent(st, s->scratch_done, 0));
+    // grow scratch to the batch (large-N path only; the batch of such sizes is small)
+    const size_t need = (size_t)p.batch * s->Nc;
+    if (need > s->scratch_cpx) {
+      PF_CUDA_OK(cudaDeviceSynchronize());
+      for (int i = 0; i < 2; ++i) { if (s->d_scratch[i]) cudaFree(s->d_scratch[i]); s->d_scratch[i] = nullptr; }
+      PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[0], need * sizeof(cpx<T>)));
+      PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[1], need * sizeof(cpx<T>)));
+      s->scratch_cpx = need;
+    }
+    const long long total = p.batch * (long long)s->Nc;
+    const int thr = 256;
+    auto grid_for = [&](long long work) { long long g = (work + thr - 1) / thr; long long cap = (long long)s->sm_count * 32; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); };
+    k_glob_load<T, LM><<<grid_for(total), thr, 0, st>>>(p, s->d_scratch[0]);
+    count_launch();
+    int cur = 0, stride = 1;
+    for (int f = 0; f < s->nfac; ++f) {
+      const int r = s->fac[f];
+      k_glob_stage<T, SIGN><<<grid_for(total / r), thr, 0, st>>>(s->d_scratch[cur], s->d_scratch[cur ^ 1], p.batch, s->Nc, r, stride, s->tw);
+      count_launch();
+      cur ^= 1; stride *= r;
+    }
+    k_glob_store<T, SM><<<grid_for(total), thr, 0, st>>>(p, s->d_scratch[cur]);
+    count_launch();
+    PF_CUDA_OK(cudaGetLastError());
+    PF_CUDA_OK(cudaEventRecord(s->scratch_done, st));
+    return 0;
+  }
+  // shared-memory kernel
+  auto kern = k_smem_fft<T, LM, SM, SIGN>;
+  static thread_local size_t attr_set_for = 0;   // opt-in dynamic shared memory once per instantiation and size
+  if (s->smem_bytes > 48 * 1024 && attr_set_for < s->smem_bytes) {
+    PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    attr_set_for = s->smem_bytes;
+  }
+  constexpr int combo = (LM * 5 + SM) * 2 + (SIGN > 0 ? 1 : 0);
+  int per_sm = s->occ_cache[combo];
+  if (per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, s->smem_bytes);
+    if (per_sm < 1) per_sm = 1;
+    s->occ_cache[combo] = per_sm;
+  }
+  long long ctas = (p.batch + s->tpc - 1) / s->tpc;
+  const long long cap = (long long)s->sm_count * per_sm;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  kern<<<(int)ctas, 256, s->smem_bytes, st>>>(p, s->tpc);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T> XformParams<T> make_params(Setup<T>* s, const T* in, T* out, long long batch, const XformOpts& o) {
+  XformParams<T> p;
+  p.in = in; p.out = out;
+  p.in_stride = o.in_stride >= 0 ? o.in_stride : (long long)s->per();
+  p.out_stride = o.out_stride >= 0 ? o.out_stride : (long long)s->per();
+  p.in_limit = o.in_limit;
+  p.out_count = o.out_count >= 0 ? o.out_count : s->N;
+  p.batch = batch; p.N = s->N; p.Nc = s->Nc; p.nfac = s->nfac;
+  for (int i = 0; i < PF_MAX_FACTORS; ++i) p.fac[i] = i < s->nfac ? s->fac[i] : 1;
+  p.tw = s->tw; p.twr = s->twr;
+  return p;
+}
+
+// transform `batch` vectors resident on the device
+template <typename T, typename Hooks>
+int engine_transform_device(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered,
+                            cudaStream_t st, const XformOpts& o = XformOpts()) {
+  if (batch <= 0) return 0;
+  const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+  if (s->kind == KK_FAST && plain) {
+    const int rc = Hooks::run(s, in, out, batch, direction, ordered, st);
+    if (rc >= 0) return rc;                       // -1: this (direction, layout) has no tuned kernel -> generic
+  }
+  const XformParams<T> p = make_params(s, in, out, batch, o);
+  const bool fwd = direction == DIR_FORWARD;
+  if (s->transform == XF_COMPLEX) {
+    if (fwd) return ordered ? launch_generic<T, L_C_ORD, S_C_ORD, -1>(s, p, st) : launch_generic<T, L_C_ORD, S_C_Z, -1>(s, p, st);
+    return ordered ? launch_generic<T, L_C_ORD, S_C_ORD, +1>(s, p, st) : launch_generic<T, L_C_Z, S_C_ORD, +1>(s, p, st);
+  }
+  if (fwd) return ordered ? launch_generic<T, L_R_TIME, S_R_ORD, -1>(s, p, st) : launch_generic<T, L_R_TIME, S_R_Z, -1>(s, p, st);
+  return ordered ? launch_generic<T, L_R_ORD, S_R_TIME, +1>(s, p, st) : launch_generic<T, L_R_Z, S_R_TIME, +1>(s, p, st);
+}
+
+// ---------------------------------------------------------------- host-pointer pipeline
+// Streams the batch through three slots (H2D -> kernels -> D2H in slot order on the slot's
+// stream); consecutive chunks use different slots so copies in both directions overlap compute.
+template <typename T> int ensure_slots(Setup<T>* s, size_t elems) {
+  if (elems <= s->slot_elems) return 0;
+  for (int i = 0; i < 3; ++i) {
+    PF_CUDA_OK(cudaStreamSynchronize(s->slot[i].stream));
+    if (s->slot[i].d_in) cudaFree(s->slot[i].d_in);
+    if (s->slot[i].d_out) cudaFree(s->slot[i].d_out);
+    s->slot[i].d_in = s->slot[i].d_out = nullptr;
+    PF_CUDA_OK(cudaMalloc(&s->slot[i].d_in, elems * sizeof(T)));
+    PF_CUDA_OK(cudaMalloc(&s->slot[i].d_out, elems * sizeof(T)));
+  }
+  s->slot_elems = elems;
+  return 0;
+}
+
+template <typename T, typename Fn>
+int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device_op) {
+  std::lock_guard<std::mutex> lock(s->mu);
+  int cur = 0; cudaGetDevice(&cur);
+  if (cur != s->device) PF_CUDA_OK(cudaSetDevice(s->device));
+  const size_t per = s->per();
+  long long chunk = (long long)((size_t)(32u << 20) / (per * sizeof(T)));     // ~32 MiB per direction per chunk
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  int rc = ensure_slots(s, (size_t)chunk * per);
+  if (rc) return rc;
+  int i = 0;
+  for (long long b0 = 0; b0 < batch; b0 += chunk, i = (i + 1) % 3) {
+    const long long nb = (batch - b0 < chunk) ? (batch - b0) : chunk;
+    Slot& sl = s->slot[i];
+    PF_CUDA_OK(cudaMemcpyAsync(sl.d_in, in + (size_t)b0 * per, (size_t)nb * per * sizeof(T), cudaMemcpyHostToDevice, sl.stream));
+    rc = device_op((const T*)sl.d_in, (T*)sl.d_out, nb, sl.stream);
+    if (rc) return rc;
+    PF_CUDA_OK(cudaMemcpyAsync(out + (size_t)b0 * per, sl.d_out, (size_t)nb * per * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+  }
+  for (int k = 0; k < 3; ++k) PF_CUDA_OK(cudaStreamSynchronize(s->slot[k].stream));
+  if (cur != s->device) cudaSetDevice(cur);
+  return 0;
+}
+
+// the public transform: host or device pointers
+template <typename T, typename Hooks>
+int engine_transform(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered) {
+  if (!s || !in || !out) { set_error_msg("pffft transform: NULL argument"); return (int)cudaErrorInvalidValue; }
+  if (direction != DIR_FORWARD && direction != DIR_BACKWARD) { set_error_msg("pffft transform: bad direction"); return (int)cudaErrorInvalidValue; }
+  const bool din = ptr_is_device(in), dout = ptr_is_device(out);
+  if (din != dout) { set_error_msg("pffft transform: input and output must both be host or both be device pointers"); return (int)cudaErrorInvalidValue; }
+  if (din) return engine_transform_device<T, Hooks>(s, in, out, batch, direction, ordered, s->stream);
+  return host_pipeline<T>(s, in, out, batch, [&](const T* di, T* dst_, long long nb, cudaStream_t st) {
+    return engine_transform_device<T, Hooks>(s, di, dst_, nb, direction, ordered, st);
+  });
+}
+
+// ---------------------------------------------------------------- zreorder / zconvolve
+template <typename T> int engine_zreorder_device(Setup<T>* s, const T* in, T* out, long long batch, int direction, cudaStream_t st) {
+  const long long slots = batch * (s->transform == XF_REAL ? s->N / 2 : s->N);
+  long long g = (slots + 255) / 256; const long long cap = (long long)s->sm_count * 32;
+  if (g > cap) g = cap; if (g < 1) g = 1;
+  const bool toz = direction == DIR_BACKWARD;
+  if (s->transform == XF_REAL) {
+    if (toz) k_zreorder<T, true, true><<<(int)g, 256, 0, st>>>(in, out, batch, s->N);
+    else     k_zreorder<T, true, false><<<(int)g, 256, 0, st>>>(in, out, batch, s->N);
+  } else {
+    if (toz) k_zreorder<T, false, true><<<(int)g, 256, 0, st>>>(in, out, batch, s->N);
+    else     k_zreorder<T, false, false><<<(int)g, 256, 0, st>>>(in, out, batch, s->N);
+  }
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <typename T> int engine_zreorder(Setup<T>* s, const T* in, T* out, long long batch, int direction) {
+  if (!s || !in || !out) { set_error_msg("pffft_zreorder: NULL argument"); return (int)cudaErrorInvalidValue; }
+  if (in == out) { set_error_msg("pffft_zreorder: input and output must not alias (ref pffft_priv_impl.h:1162)"); return (int)cudaErrorInvalidValue; }
+  const bool din = ptr_is_device(in), dout = ptr_is_device(out);
+  if (din != dout) { set_error_msg("pffft_zreorder: mixed host/device pointers"); return (int)cudaErrorInvalidValue; }
+  if (din) return engine_zreorder_device<T>(s, in, out, batch, direction, s->stream);
+  return host_pipeline<T>(s, in, out, batch, [&](const T* di, T* dst_, long long nb, cudaStream_t st) {
+    return engine_zreorder_device<T>(s, di, dst_, nb, direction, st);
+  });
+}
+
+template <typename T> int engine_zconvolve_device(Setup<T>* s, const T* a, const T* b, T* ab, T scaling, long long batch,
+                                                  int b_shared, int accumulate, cudaStream_t st) {
+  const int per = (int)s->per();
+  const long long groups = batch * (per / 8);
+  long long g = (groups + 255) / 256; const long long cap = (long long)s->sm_count * 32;
+  if (g > cap) g = cap; if (g < 1) g = 1;
+  const bool real = s->transform == XF_REAL;
+  if (real) {
+    if (accumulate) k_zconvolve<T, true, true><<<(int)g, 256, 0, st>>>(a, b, ab, scaling, batch, per, b_shared);
+    else            k_zconvolve<T, true, false><<<(int)g, 256, 0, st>>>(a, b, ab, scaling, batch, per, b_shared);
+  } else {
+    if (accumulate) k_zconvolve<T, false, true><<<(int)g, 256, 0, st>>>(a, b, ab, scaling, batch, per, b_shared);
+    else            k_zconvolve<T, false, false><<<(int)g, 256, 0, st>>>(a, b, ab, scaling, batch, per, b_shared);
+  }
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// host or device pointers; host path stages a, b (and ab when accumulating) through slot memory
+template <typename T> int engine_zconvolve(Setup<T>* s, const T* a, const T* b, T* ab, T scaling, long long batch,
+                                           int b_shared, int accumulate) {
+  if (!s || !a || !b || !ab) { set_error_msg("pffft_zconvolve: NULL argument"); return (int)cudaErrorInvalidValue; }
+  if (batch <= 0) return 0;
+  const bool da = ptr_is_device(a), db = ptr_is_device(b), dab = ptr_is_device(ab);
+  if (da != db || da != dab) { set_error_msg("pffft_zconvolve: mixed host/device pointers"); return (int)cudaErrorInvalidValue; }
+  if (da) return engine_zconvolve_device<T>(s, a, b, ab, scaling, batch, b_shared, accumulate, s->stream);
+  // host: simple synchronous staging (this entry point is bandwidth-trivial next to the PCIe copies)
+  std::lock_guard<std::mutex> lock(s->mu);
+  int cur = 0; cudaGetDevice(&cur);
+  if (cur != s->device) PF_CUDA_OK(cudaSetDevice(s->device));
+  const size_t per = s->per();
+  const size_t nb_b = b_shared ? 1 : (size_t)batch;
+  T *d_a = nullptr, *d_b = nullptr, *d_ab = nullptr;
+  cudaStream_t st = s->slot[0].stream;
+  int rc = 0;
+  do {
+    if ((rc = (int)cudaMalloc((void**)&d_a, (size_t)batch * per * sizeof(T)))) break;
+    if ((rc = (int)cudaMalloc((void**)&d_b, nb_b * per * sizeof(T)))) break;
+    if ((rc = (int)cudaMalloc((void**)&d_ab, (size_t)batch * per * sizeof(T)))) break;
+    if ((rc = (int)cudaMemcpyAsync(d_a, a, (size_t)batch * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
+    if ((rc = (int)cudaMemcpyAsync(d_b, b, nb_b * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
+    if (accumulate && (rc = (int)cudaMemcpyAsync(d_ab, ab, (size_t)batch * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
+    if ((rc = engine_zconvolve_device<T>(s, d_a, d_b, d_ab, scaling, batch, b_shared, accumulate, st))) break;
+    if ((rc = (int)cudaMemcpyAsync(ab, d_ab, (size_t)batch * per * sizeof(T), cudaMemcpyDeviceToHost, st))) break;
+    rc = (int)cudaStreamSynchronize(st);
+  } while (0);
+  if (rc) set_error("pffft_zconvolve (host staging)", (cudaError_t)rc);
+  if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b); if (d_ab) cudaFree(d_ab);
+  if (cur != s->device) cudaSetDevice(cur);
+  return rc;
+}
+
+}  // namespace pf

@@ -1,0 +1,176 @@
+// fast_kernels.cuh -- size-tuned sm_100a kernels for the headline sizes.
+//
+// c2c N=1024 fp32 (BASELINE configs C2/C5): ONE TRANSFORM PER WARP.
+//   1024 = 32 x 32.  Lane n1 owns the 32 points x[n1 + 32*n2] (64 registers), runs a complete
+//   radix-32 register FFT over n2, multiplies by W_1024^{n1*k2}, the warp transposes the 32x32
+//   tile through a padded shared-memory tile (conflict-free 64-bit accesses, __syncwarp only --
+//   no CTA barrier in the steady state), lane k2 runs a second radix-32 FFT over n1 and owns
+//   X[k2 + 32*k1]: every global access of the warp is a fully coalesced 256-byte row.
+//   HBM traffic: one 8 KiB read and one 8 KiB write per transform (the algorithmic minimum).
+//   This replaces the reference's 7 sweeps (uninterleave, 4x passf4_ps, cplx_finalize,
+//   zreorder; src/pffft_priv_impl.h:1465-1532).
+//
+//   Two feeding schemes share the arithmetic:
+//     k_c1024_ldg  : lanes load their points straight into registers (LDG.64), latency hidden by
+//                    occupancy (16 warps/SM).
+//     k_c1024_bulk : each warp owns a 2-deep ring of 8 KiB shared-memory stages filled by the TMA
+//                    engine with 1-D bulk-async copies (cp.async.bulk ... mbarrier::complete_tx,
+//                    SASS UBLKCP) issued two transforms ahead; the consumed stage doubles as the
+//                    transpose tile.  Loads cost no registers and no issue slots.
+#pragma once
+#include "butterfly.cuh"
+#include "layout.cuh"
+
+namespace pf {
+
+constexpr int kW1024Tile = 32 * 33;   // padded 32x32 tile, in complex elements (8448 bytes)
+
+PF_HD constexpr int brev5(int p) { return ct::bitrev(p, 5); }
+
+// phase A: v[p] = x[lane + 32*brev5(p)] on entry.  Row FFT over n2, twiddle, write tile row `lane`.
+//   tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
+template <int SIGN>
+PF_HD void w1024_rows(cf (&v)[32], int lane, const cf* tw, cf* tile) {
+  reg_fft<32, SIGN>(v);                       // v[k2] = sum_n2 x[lane + 32 n2] w32^(n2 k2)
+  tile[lane * 33] = v[0];
+#pragma unroll
+  for (int k2 = 1; k2 < 32; ++k2) tile[lane * 33 + k2] = cmul_dir<SIGN>(v[k2], tw[k2 * 32 + lane]);
+}
+// phase B: gather column `lane` (= k2) in bit-reversed register order, column FFT over n1.
+//   on exit v[k1] = X[lane + 32*k1]
+template <int SIGN>
+PF_HD void w1024_cols(cf (&v)[32], int lane, const cf* tile) {
+#pragma unroll
+  for (int p = 0; p < 32; ++p) v[p] = tile[brev5(p) * 33 + lane];
+  reg_fft<32, SIGN>(v);
+}
+
+#ifdef __CUDACC__
+PF_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PF_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+PF_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PF_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+PF_D void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+PF_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PF_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+PF_D cf ld_stream(const cf* p) { float2 t = __ldcs(reinterpret_cast<const float2*>(p)); return mk<float>(t.x, t.y); }
+PF_D void st_stream(cf* p, cf v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
+
+// store the finished transform: lane owns X[lane + 32*k1].  ZOUT selects the reference's
+// z-domain layout (4-lane groups: bins lane..lane+3 contiguous, re|im split) for pffft_transform.
+template <bool ZOUT>
+PF_D void w1024_store(const cf (&v)[32], int lane, cf* dst) {
+  if (!ZOUT) {
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) st_stream(dst + lane + 32 * k1, v[k1]);
+  } else {
+    float* d = reinterpret_cast<float*>(dst);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const int p = zpos_complex(lane + 32 * k1, 1024);
+      d[p] = v[k1].x; d[p + 4] = v[k1].y;
+    }
+  }
+}
+// element loader for the first phase; ZIN gathers from the z-domain layout (backward unordered)
+template <bool ZIN>
+PF_D cf w1024_ld(const cf* src, int idx) {
+  if (!ZIN) return ld_stream(src + idx);
+  const float* s = reinterpret_cast<const float*>(src);
+  const int p = zpos_complex(idx, 1024);
+  return mk<float>(s[p], s[p + 4]);
+}
+
+// ---------------------------------------------------------------- register-fed variant
+template <int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_c1024_ldg(const cf* __restrict__ in, cf* __restrict__ out, long long batch, const cf* __restrict__ tw_g) {
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cf* tw = reinterpret_cast<cf*>(pf_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf* tile = tw + 1024 + warp * kW1024Tile;
+  for (int i = threadIdx.x; i < 1024; i += WARPS * 32) tw[i] = tw_g[i];
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * WARPS;
+  for (long long t = (long long)blockIdx.x * WARPS + warp; t < batch; t += stride) {
+    const cf* src = in + t * 1024;
+    cf v[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) v[p] = w1024_ld<ZIN>(src, lane + 32 * brev5(p));
+    w1024_rows<SIGN>(v, lane, tw, tile);
+    __syncwarp();
+    w1024_cols<SIGN>(v, lane, tile);
+    __syncwarp();                               // tile is rewritten by the next iteration
+    w1024_store<ZOUT>(v, lane, out + t * 1024);
+  }
+}
+
+// ---------------------------------------------------------------- TMA bulk-copy fed variant
+// shared memory: [tw 8 KiB][per warp: 2 stages x 8448 B][mbarriers: WARPS x 2 x 8 B]
+template <int SIGN, int WARPS, int MINB, bool ZOUT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_c1024_bulk(const cf* __restrict__ in, cf* __restrict__ out, long long batch, const cf* __restrict__ tw_g) {
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cf* tw = reinterpret_cast<cf*>(pf_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf* stage0 = tw + 1024 + warp * (2 * kW1024Tile);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tw + 1024 + WARPS * (2 * kW1024Tile)) + warp * 2;
+  for (int i = threadIdx.x; i < 1024; i += WARPS * 32) tw[i] = tw_g[i];
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); fence_proxy_async(); }
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * WARPS;
+  const long long first = (long long)blockIdx.x * WARPS + warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const long long t = first + s * stride;
+      if (t < batch) { mbar_expect_tx(&bars[s], 8192); bulk_g2s(stage0 + s * kW1024Tile, in + t * 1024, 8192, &bars[s]); }
+    }
+  }
+  int it = 0;
+  for (long long t = first; t < batch; t += stride, ++it) {
+    const int s = it & 1;
+    cf* buf = stage0 + s * kW1024Tile;
+    mbar_wait(&bars[s], (it >> 1) & 1);
+    cf v[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) v[p] = buf[lane + 32 * brev5(p)];
+    __syncwarp();                               // every lane has its points: the stage becomes the tile
+    w1024_rows<SIGN>(v, lane, tw, buf);
+    __syncwarp();
+    w1024_cols<SIGN>(v, lane, buf);
+    __syncwarp();                               // tile consumed: hand the stage back to the TMA engine
+    if (lane == 0) {
+      const long long tn = t + 2 * stride;
+      if (tn < batch) {
+        fence_proxy_async();                    // order our generic-proxy accesses before the async-proxy write
+        mbar_expect_tx(&bars[s], 8192);
+        bulk_g2s(buf, in + tn * 1024, 8192, &bars[s]);
+      }
+    }
+    w1024_store<ZOUT>(v, lane, out + t * 1024);
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace pf

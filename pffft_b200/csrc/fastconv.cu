@@ -1,0 +1,221 @@
+// fastconv.cu -- pffastconv_* : overlap-save FIR convolution (ref src/pffastconv.c:58-263,
+// include/pffft/pffastconv.h:83-180).
+//
+// Same block algebra and results as the reference's per-block loop
+//   memcpy -> pffft_transform(FWD) -> pffft_zconvolve_no_accu(Hf, 1/Nfft) -> pffft_transform(BWD) -> memcpy
+// but every block of one pffastconv_apply call is an independent unit of work, so the call becomes
+// three batched launches over all blocks at once: the forward kernel reads the overlapping input
+// windows straight from the stream (batch stride = outputs per block, zero padding past the end),
+// the inverse kernel stores only the valid samples of each block straight into the output.
+#include <cuda_runtime.h>
+#include <vector>
+#include <string.h>
+#include "../../include/pffft/pffft_b200.h"
+#include "internal_api.h"
+
+using pf::XformOpts;
+
+struct PFFASTCONV_Setup {
+  PFFFT_Setup* st = nullptr;     // real plan of Nfft points
+  int filterLen = 0;             // effective taps (2F-1 in single-FFT complex mode, ref pffastconv.c:91-94)
+  int Nfft = 0;
+  int flags = 0;
+  float scale = 0.f;
+  int device = 0;
+  cudaStream_t stream = nullptr; // device-pointer calls
+  float* d_Hf = nullptr;         // z-domain spectrum of the arranged filter
+  // scratch, grown on demand (a PFFASTCONV_Setup is single-threaded by contract, pffastconv.h:77-81)
+  float* d_spec = nullptr; size_t spec_elems = 0;
+  float* d_x = nullptr;    size_t x_elems = 0;     // host input staging / planar split
+  float* d_y = nullptr;    size_t y_elems = 0;     // host output staging / planar split
+};
+
+namespace {
+
+int grow(float** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) { cudaDeviceSynchronize(); cudaFree(*p); *p = nullptr; *cap = 0; }
+  cudaError_t e = cudaMalloc((void**)p, need * sizeof(float));
+  if (e != cudaSuccess) { pf::set_error("pffastconv: scratch allocation", e); return (int)e; }
+  *cap = need;
+  return 0;
+}
+
+// interleaved complex stream <-> two planar real streams (CPLX_INP_OUT without SINGLE_FFT runs the
+// real convolution on the real and on the imaginary part, ref pffastconv.c:212-247)
+__global__ void k_split(const float* __restrict__ x, float* __restrict__ re, float* __restrict__ im, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    re[i] = v.x; im[i] = v.y;
+  }
+}
+__global__ void k_merge(const float* __restrict__ re, const float* __restrict__ im, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float2*>(y)[i] = make_float2(re[i], im[i]);
+}
+// split/merge for streams whose base is only 4-byte aligned
+__global__ void k_split_u(const float* __restrict__ x, float* __restrict__ re, float* __restrict__ im, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    re[i] = x[2 * i]; im[i] = x[2 * i + 1];
+  }
+}
+__global__ void k_merge_u(const float* __restrict__ re, const float* __restrict__ im, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    y[2 * i] = re[i]; y[2 * i + 1] = im[i];
+  }
+}
+
+using pfplan::BlockPlan;
+using pfplan::plan_blocks;
+
+// one real stream already on the device: x[0..inputLen) -> y[0..produced)
+int conv_stream(PFFASTCONV_Setup* s, const float* x, long long inputLen, float* y, const BlockPlan& bp, cudaStream_t st) {
+  const int Nfft = s->Nfft;
+  const long long max_blocks = (long long)((size_t)(256u << 20) / ((size_t)Nfft * sizeof(float)));   // <= 256 MiB of spectra in flight
+  const long long chunk = max_blocks < 1 ? 1 : max_blocks;
+  auto run = [&](long long first_off, long long nblk, int out_count) -> int {
+    for (long long b0 = 0; b0 < nblk; b0 += chunk) {
+      const long long nb = (nblk - b0 < chunk) ? (nblk - b0) : chunk;
+      int rc = grow(&s->d_spec, &s->spec_elems, (size_t)nb * Nfft);
+      if (rc) return rc;
+      const long long off = first_off + b0 * bp.stride;
+      XformOpts fo; fo.in_stride = bp.stride; fo.out_stride = Nfft; fo.in_limit = inputLen - off;
+      rc = pf::float_transform_device(s->st, x + off, s->d_spec, nb, pf::DIR_FORWARD, 0, st, fo);
+      if (rc) return rc;
+      rc = pf::float_zconvolve_device(s->st, s->d_spec, s->d_Hf, s->d_spec, s->scale, nb, 1, 0, st);
+      if (rc) return rc;
+      XformOpts bo; bo.in_stride = Nfft; bo.out_stride = bp.stride; bo.out_count = out_count;
+      rc = pf::float_transform_device(s->st, s->d_spec, y + off, nb, pf::DIR_BACKWARD, 0, st, bo);
+      if (rc) return rc;
+    }
+    return 0;
+  };
+  int rc = 0;
+  if (bp.n_full > 0) rc = run(0, bp.n_full, bp.stride);
+  if (!rc && bp.tail_off >= 0) rc = run(bp.tail_off, 1, bp.tail_out);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+PFFASTCONV_EXPORT PFFASTCONV_Setup* pffastconv_new_setup(const float* filterCoeffs, int filterLen, int* blockLen, int flags) {
+  if (!filterCoeffs || !blockLen || filterLen <= 0) return nullptr;
+  const int cplxFactor = ((flags & PFFASTCONV_CPLX_INP_OUT) && (flags & PFFASTCONV_CPLX_SINGLE_FFT)) ? 2 : 1;
+  const int minFftLen = 2 * pffft_simd_size() * pffft_simd_size();
+  int Nfft = 2 * pffft_next_power_of_two(filterLen - 1);        // ref pffastconv.c:62
+  if (Nfft < minFftLen) Nfft = minFftLen;
+  if (flags & PFFASTCONV_CPLX_FILTER) return nullptr;           // ref :71-72
+  if (*blockLen > Nfft) Nfft = pffft_next_power_of_two(*blockLen);
+  *blockLen = Nfft;                                             // in (complex) samples, ref :80
+  Nfft *= cplxFactor;
+
+  PFFASTCONV_Setup* s = new PFFASTCONV_Setup();
+  s->st = pffft_new_setup(Nfft, PFFFT_REAL);
+  if (!s->st) { delete s; return nullptr; }
+  s->device = pffftb_setup_device(s->st);
+  s->filterLen = (cplxFactor == 2) ? 2 * filterLen - 1 : filterLen;
+  s->Nfft = Nfft; s->flags = flags; s->scale = (float)(1.0 / Nfft);
+
+  // time-reversed taps placed circularly (ref :99-106); zero-stuffed by 2 in single-FFT complex mode
+  std::vector<float> ht((size_t)Nfft, 0.f);
+  for (int i = 0; i < filterLen; ++i) {
+    const float c = (flags & PFFASTCONV_CORRELATION) ? filterCoeffs[i] : filterCoeffs[filterLen - 1 - i];
+    ht[(size_t)((Nfft - cplxFactor * i) & (Nfft - 1))] = c;
+  }
+  bool ok = cudaMalloc((void**)&s->d_Hf, (size_t)Nfft * sizeof(float)) == cudaSuccess;
+  float* d_tmp = nullptr;
+  ok = ok && cudaMalloc((void**)&d_tmp, (size_t)Nfft * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMemcpy(d_tmp, ht.data(), (size_t)Nfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    ok = pf::float_transform_device(s->st, d_tmp, s->d_Hf, 1, pf::DIR_FORWARD, 0, nullptr, XformOpts()) == 0;   // ref :108
+    ok = ok && cudaStreamSynchronize(nullptr) == cudaSuccess;
+  }
+  if (d_tmp) cudaFree(d_tmp);
+  if (!ok) { pf::set_error("pffastconv_new_setup", cudaGetLastError()); pffastconv_destroy_setup(s); return nullptr; }
+  return s;
+}
+
+PFFASTCONV_EXPORT void pffastconv_destroy_setup(PFFASTCONV_Setup* s) {
+  if (!s) return;
+  cudaDeviceSynchronize();
+  if (s->d_Hf) cudaFree(s->d_Hf);
+  if (s->d_spec) cudaFree(s->d_spec);
+  if (s->d_x) cudaFree(s->d_x);
+  if (s->d_y) cudaFree(s->d_y);
+  pffft_destroy_setup(s->st);
+  delete s;
+}
+
+PFFASTCONV_EXPORT int pffastconv_apply(PFFASTCONV_Setup* s, const float* input, int cplxInputLen, float* output, int applyFlush) {
+  if (!s || !input || !output || cplxInputLen <= 0) return 0;
+  const int flags = s->flags;
+  const bool cplx = (flags & PFFASTCONV_CPLX_INP_OUT) != 0;
+  const int cplxFactor = (cplx && (flags & PFFASTCONV_CPLX_SINGLE_FFT)) ? 2 : 1;
+  const long long inputLen = (long long)cplxFactor * cplxInputLen;           // length of the real stream(s)
+  const BlockPlan bp = plan_blocks(inputLen, s->Nfft, s->filterLen, applyFlush, cplxFactor == 2);
+  if (bp.produced <= 0) return 0;
+
+  const bool din = pf::ptr_is_device(input), dout = pf::ptr_is_device(output);
+  if (din != dout) { pf::set_error_msg("pffastconv_apply: input and output must both be host or both be device pointers"); return 0; }
+  cudaStream_t st = s->stream;
+  const size_t in_floats = (size_t)(cplx ? 2 : 1) * (size_t)cplxInputLen;   // floats in `input`
+  const size_t out_floats = (size_t)(cplx && cplxFactor == 1 ? 2 : 1) * (size_t)bp.produced;   // floats written to `output`
+
+  const float* dx = input;
+  float* dy = output;
+  const bool two_planes = cplx && cplxFactor == 1;
+  int rc = 0;
+  // staging: host pointers need a device copy; the two-FFT complex mode needs planar streams
+  size_t need_x = 0, need_y = 0;
+  if (!din) { need_x += in_floats; need_y += out_floats; }
+  if (two_planes) { need_x += 2 * (size_t)cplxInputLen; need_y += 2 * (size_t)bp.produced; }
+  if ((rc = grow(&s->d_x, &s->x_elems, need_x + 8))) return 0;
+  if ((rc = grow(&s->d_y, &s->y_elems, need_y + 8))) return 0;
+  float* x_planes = s->d_x;
+  float* y_planes = s->d_y;
+  if (!din) {
+    float* hx = s->d_x + (two_planes ? 2 * (size_t)cplxInputLen : 0);
+    float* hy = s->d_y + (two_planes ? 2 * (size_t)bp.produced : 0);
+    hx += (4 - ((uintptr_t)hx / sizeof(float)) % 4) % 4;      // keep 16-byte alignment of the staged streams
+    hy += (4 - ((uintptr_t)hy / sizeof(float)) % 4) % 4;
+    if (cudaMemcpyAsync(hx, input, in_floats * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) { pf::set_error("pffastconv_apply: H2D", cudaGetLastError()); return 0; }
+    dx = hx; dy = hy;
+  }
+
+  if (!two_planes) {
+    rc = conv_stream(s, dx, inputLen, dy, bp, st);
+  } else {
+    const long long n = cplxInputLen;
+    const int thr = 256; long long g = (n + thr - 1) / thr; if (g > 148 * 16) g = 148 * 16;
+    float* xr = x_planes; float* xi = x_planes + n;
+    float* yr = y_planes; float* yi = y_planes + bp.produced;
+    if (((uintptr_t)dx & 7) == 0) k_split<<<(int)g, thr, 0, st>>>(dx, xr, xi, n); else k_split_u<<<(int)g, thr, 0, st>>>(dx, xr, xi, n);
+    pf::count_launch();
+    rc = conv_stream(s, xr, inputLen, yr, bp, st);
+    if (!rc) rc = conv_stream(s, xi, inputLen, yi, bp, st);
+    if (!rc) {
+      const long long m = bp.produced; long long g2 = (m + thr - 1) / thr; if (g2 > 148 * 16) g2 = 148 * 16;
+      if (((uintptr_t)dy & 7) == 0) k_merge<<<(int)g2, thr, 0, st>>>(yr, yi, dy, m); else k_merge_u<<<(int)g2, thr, 0, st>>>(yr, yi, dy, m);
+      pf::count_launch();
+    }
+  }
+  if (rc) return 0;
+  if (!din) {
+    if (cudaMemcpyAsync(output, dy, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { pf::set_error("pffastconv_apply: D2H", cudaGetLastError()); return 0; }
+  }
+  if (cudaGetLastError() != cudaSuccess) return 0;
+  return (int)(bp.produced / cplxFactor);                      // ref :201, :262
+}
+
+PFFASTCONV_EXPORT void* pffastconv_malloc(size_t nb) { return pffft_aligned_malloc(nb); }
+PFFASTCONV_EXPORT void pffastconv_free(void* p) { pffft_aligned_free(p); }
+PFFASTCONV_EXPORT int pffastconv_simd_size(void) { return pffft_simd_size(); }
+PFFFT_EXPORT int pffastconvb_set_stream(PFFASTCONV_Setup* s, void* st) {
+  if (!s) return (int)cudaErrorInvalidValue;
+  s->stream = (cudaStream_t)st; return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// generic_kernels.cuh -- kernels that work for EVERY size the API admits
+// (N = 16*2^a*3^b*5^c complex, 32*... real; ref pffft_priv_impl.h:91-98), both precisions.
+//
+//   k_smem_fft   : one CTA keeps whole transforms in shared memory: load+pre-rotation,
+//                  all Stockham radix-{2,3,4,5} stages, post-rotation+store.  One HBM read and
+//                  one HBM write per transform.  Used when 2 buffers of Nc complex fit in SMEM.
+//   k_glob_*     : the same stages with the ping-pong buffers in global memory, one launch per
+//                  stage, for sizes beyond shared memory (up to the reference's 2^26 limit,
+//                  pffft_priv_impl.h:1069).
+//   k_zreorder   : pffft_zreorder            (pffft_priv_impl.h:1158-1193)
+//   k_zconvolve  : pffft_zconvolve_accumulate/_no_accu (pffft_priv_impl.h:1534-1684)
+//
+// Real transforms are an Nc = N/2 point complex FFT on packed pairs plus a rotation
+// (SURVEY App. F); this replaces the reference's rfftf1/rfftb1 + real_finalize/preprocess
+// (pffft_priv_impl.h:809-901, :1273-1462) while producing the same canonical / z-domain layouts.
+//
+// Size-tuned kernels for the headline sizes live in fast_kernels.cuh; these are the complete,
+// always-available path and the semantic definition the fast kernels are tested against.
+#pragma once
+#include "butterfly.cuh"
+#include "layout.cuh"
+
+namespace pf {
+
+enum LoadMode  { L_C_ORD = 0, L_C_Z = 1, L_R_TIME = 2, L_R_ORD = 3, L_R_Z = 4 };
+enum StoreMode { S_C_ORD = 0, S_C_Z = 1, S_R_TIME = 2, S_R_ORD = 3, S_R_Z = 4 };
+
+#define PF_MAX_FACTORS 28
+
+template <typename T> struct XformParams {
+  const T* in;
+  T* out;
+  long long in_stride;    // elements between consecutive transforms of the batch (input side)
+  long long out_stride;   // same, output side
+  long long in_limit;     // L_R_TIME only: number of readable elements starting at `in` (<0: no limit);
+                          // samples beyond it read as zero (overlap-save tail padding, ref pffastconv.c:231-233)
+  int out_count;          // S_R_TIME only: leading real samples stored per transform (ref pffastconv.c:255)
+  long long batch;
+  int N;                  // transform length as the API sees it
+  int Nc;                 // complex core length: N (complex) or N/2 (real)
+  int nfac;
+  int fac[PF_MAX_FACTORS];
+  const cpx<T>* tw;       // exp(-2 pi i k / Nc), k < Nc
+  const cpx<T>* twr;      // exp(-2 pi i k / N),  k < N/2   (real transforms)
+};
+
+// ------------------------------------------------------------------ element-wise load / store
+template <bool ZLAYOUT, bool REAL, typename T> PF_HD cpx<T> spec_get(const T* base, int k, int N) {
+  if (!ZLAYOUT) return reinterpret_cast<const cpx<T>*>(base)[k];
+  const int p = zpos<REAL>(k, N);
+  return mk<T>(base[p], base[p + 4]);
+}
+template <bool ZLAYOUT, bool REAL, typename T> PF_HD void spec_put(T* base, int k, int N, cpx<T> v) {
+  if (!ZLAYOUT) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
+  const int p = zpos<REAL>(k, N);
+  base[p] = v.x; base[p + 4] = v.y;
+}
+
+// element i of the complex core's INPUT for this transform
+template <int LM, typename T>
+PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, long long avail, bool vec_ok) {
+  if (LM == L_C_ORD) return spec_get<false, false>(base, i, N);
+  if (LM == L_C_Z)   return spec_get<true, false>(base, i, N);
+  if (LM == L_R_TIME) {
+    const long long e = 2LL * i;
+    if (vec_ok && (avail < 0 || e + 1 < avail)) return reinterpret_cast<const cpx<T>*>(base)[i];
+    const T x = (avail < 0 || e < avail) ? base[e] : T(0);
+    const T y = (avail < 0 || e + 1 < avail) ? base[e + 1] : T(0);
+    return mk<T>(x, y);
+  }
+  // backward real: rebuild the packed half-length spectrum Z' = 2*(E + i O) from X (SURVEY App. F;
+  // the factor 2 keeps BACKWARD(FORWARD(x)) = N x, ref pffft.h:134)
+  constexpr bool Z = (LM == L_R_Z);
+  if (i == 0) {
+    const cpx<T> s0 = spec_get<Z, true>(base, 0, N);      // (X[0], X[N/2])
+    return mk<T>(s0.x + s0.y, s0.x - s0.y);
+  }
+  const cpx<T> a = spec_get<Z, true>(base, i, N);
+  const cpx<T> b = conj(spec_get<Z, true>(base, Nc - i, N));
+  const cpx<T> s = a + b, d = a - b;
+  const cpx<T> u = cmul_dir<+1>(d, twr[i]);               // d * exp(+2 pi i k/N)
+  return mk<T>(s.x - u.y, s.y + u.x);                     // s + i u
+}
+
+// store element k of the transform's OUTPUT given the complex core's natural-order result z[0..Nc)
+template <int SM, typename T>
+PF_HD void store_core(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<T>* twr, int out_count, bool vec_ok) {
+  if (SM == S_C_ORD) { spec_put<false, false>(base, k, N, z[k]); return; }
+  if (SM == S_C_Z)   { spec_put<true, false>(base, k, N, z[k]); return; }
+  if (SM == S_R_TIME) {
+    const cpx<T> v = z[k];
+    const int e = 2 * k;
+    if (vec_ok && e + 1 < out_count) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
+    if (e < out_count) base[e] = v.x;
+    if (e + 1 < out_count) base[e + 1] = v.y;
+    return;
+  }
+  // forward real: X[k] = (Z[k] + conj Z[M-k])/2 - (i/2) W^k (Z[k] - conj Z[M-k])
+  constexpr bool Z = (SM == S_R_Z);
+  if (k == 0) {
+    const cpx<T> z0 = z[0];
+    spec_put<Z, true>(base, 0, N, mk<T>(z0.x + z0.y, z0.x - z0.y));
+    return;
+  }
+  const cpx<T> a = z[k];
+  const cpx<T> b = conj(z[Nc - k]);
+  const cpx<T> s = a + b, d = a - b;
+  const cpx<T> u = cmul(d, twr[k]);
+  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+}
+
+// ------------------------------------------------------------------ one Stockham butterfly
+// Autosort DIF stage: butterfly b of Nc/R; `s` = product of the radices already applied.
+// Reads x[b + j*Nc/R] (unit stride in b -> conflict-free / coalesced), writes
+// y[q + s*(R*p + k)] * W_Nc^{s*p*k} with p = b/s, q = b%s.
+template <int R, int SIGN, typename T>
+PF_HD void stockham_bfly(const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, const cpx<T>* tw) {
+  const int m = Nc / R;
+  const int q = b % s;
+  const int sp = b - q;
+  cpx<T> a[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) a[j] = x[b + j * m];
+  dftR<R, SIGN>(a);
+  const int o = q + sp * R;
+  y[o] = a[0];
+  if (sp == 0) {
+#pragma unroll
+    for (int k = 1; k < R; ++k) y[o + s * k] = a[k];
+  } else {
+#pragma unroll
+    for (int k = 1; k < R; ++k) y[o + s * k] = cmul_dir<SIGN>(a[k], tw[sp * k]);
+  }
+}
+template <int SIGN, typename T>
+PF_HD void stockham_any(int r, const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, const cpx<T>* tw) {
+  switch (r) {
+    case 2: stockham_bfly<2, SIGN>(x, y, b, Nc, s, tw); break;
+    case 3: stockham_bfly<3, SIGN>(x, y, b, Nc, s, tw); break;
+    case 4: stockham_bfly<4, SIGN>(x, y, b, Nc, s, tw); break;
+    default: stockham_bfly<5, SIGN>(x, y, b, Nc, s, tw); break;
+  }
+}
+
+template <typename T> PF_HD bool vec_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0; }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ shared-memory kernel
+// `tpc` transforms are resident per CTA iteration (many for small N, one for large N).
+template <typename T, int LM, int SM, int SIGN>
+__global__ void __launch_bounds__(256) k_smem_fft(const XformParams<T> p, const int tpc) {
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* bufA = reinterpret_cast<cpx<T>*>(pf_smem_raw);
+  cpx<T>* bufB = bufA + (size_t)tpc * p.Nc;
+  const int Nc = p.Nc, N = p.N;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  for (long long t0 = (long long)blockIdx.x * tpc; t0 < p.batch; t0 += (long long)gridDim.x * tpc) {
+    const int nt = (int)((p.batch - t0 < tpc) ? (p.batch - t0) : tpc);
+    // ---- load (+ z-domain gather / backward-real pre-rotation)
+    for (int idx = tid; idx < nt * Nc; idx += nthr) {
+      const int tl = idx / Nc, i = idx - tl * Nc;
+      const T* base = p.in + (t0 + tl) * p.in_stride;
+      const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - (t0 + tl) * p.in_stride);
+      bufA[idx] = load_core<LM, T>(base, i, N, Nc, p.twr, avail, vec_aligned<T>(base));
+    }
+    __syncthreads();
+    // ---- Stockham stages, ping-pong A <-> B
+    cpx<T>* src = bufA;
+    cpx<T>* dst = bufB;
+    int s = 1;
+    for (int f = 0; f < p.nfac; ++f) {
+      const int r = p.fac[f];
+      const int m = Nc / r;
+      for (int idx = tid; idx < nt * m; idx += nthr) {
+        const int tl = idx / m, b = idx - tl * m;
+        stockham_any<SIGN, T>(r, src + (size_t)tl * Nc, dst + (size_t)tl * Nc, b, Nc, s, p.tw);
+      }
+      __syncthreads();
+      cpx<T>* t = src; src = dst; dst = t;
+      s *= r;
+    }
+    // ---- store (+ forward-real post-rotation / z-domain scatter)
+    for (int idx = tid; idx < nt * Nc; idx += nthr) {
+      const int tl = idx / Nc, k = idx - tl * Nc;
+      T* base = p.out + (t0 + tl) * p.out_stride;
+      store_core<SM, T>(base, src + (size_t)tl * Nc, k, N, Nc, p.twr, p.out_count, vec_aligned<T>(base));
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ global-memory passes (large N)
+template <typename T, int LM>
+__global__ void __launch_bounds__(256) k_glob_load(const XformParams<T> p, cpx<T>* __restrict__ dst) {
+  const long long total = p.batch * p.Nc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / p.Nc;
+    const int i = (int)(idx - t * p.Nc);
+    const T* base = p.in + t * p.in_stride;
+    const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - t * p.in_stride);
+    dst[idx] = load_core<LM, T>(base, i, p.N, p.Nc, p.twr, avail, vec_aligned<T>(base));
+  }
+}
+template <typename T, int SIGN>
+__global__ void __launch_bounds__(256) k_glob_stage(const cpx<T>* __restrict__ src, cpx<T>* __restrict__ dst,
+                                                    long long batch, int Nc, int r, int s, const cpx<T>* __restrict__ tw) {
+  const int m = Nc / r;
+  const long long total = batch * m;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / m;
+    const int b = (int)(idx - t * m);
+    stockham_any<SIGN, T>(r, src + t * Nc, dst + t * Nc, b, Nc, s, tw);
+  }
+}
+template <typename T, int SM>
+__global__ void __launch_bounds__(256) k_glob_store(const XformParams<T> p, const cpx<T>* __restrict__ src) {
+  const long long total = p.batch * p.Nc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / p.Nc;
+    const int k = (int)(idx - t * p.Nc);
+    T* base = p.out + t * p.out_stride;
+    store_core<SM, T>(base, src + t * p.Nc, k, p.N, p.Nc, p.twr, p.out_count, vec_aligned<T>(base));
+  }
+}
+
+// ------------------------------------------------------------------ zreorder (pure permutation)
+// one thread per canonical complex slot; TOZ=false: z-domain -> canonical (PFFFT_FORWARD),
+// TOZ=true: canonical -> z-domain (PFFFT_BACKWARD).  ref pffft_priv_impl.h:1158-1193
+template <typename T, bool REAL, bool TOZ>
+__global__ void __launch_bounds__(256) k_zreorder(const T* __restrict__ in, T* __restrict__ out, long long batch, int N) {
+  const int nslots = REAL ? N / 2 : N;
+  const long long per = REAL ? N : 2LL * N;
+  const long long total = batch * nslots;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / nslots;
+    const int k = (int)(idx - t * nslots);
+    const T* ib = in + t * per;
+    T* ob = out + t * per;
+    if (TOZ) spec_put<true, REAL>(ob, k, N, spec_get<false, REAL>(ib, k, N));
+    else     spec_put<false, REAL>(ob, k, N, spec_get<true, REAL>(ib, k, N));
+  }
+}
+
+// ------------------------------------------------------------------ zconvolve
+// z-domain spectra are groups of 8 elements (4 re, 4 im).  One thread per group: 2x 4-wide
+// loads of a, b (and ab when accumulating).  Arithmetic is done with explicitly un-fused
+// mul/add in the reference's operation order (VCPLXMUL then VMADD, src/simd/pf_float.h:76,
+// pf_sse1_float.h:61) so results are bit-identical to the CPU library; the kernel is
+// bandwidth-bound, the extra instructions are free.  Real setups multiply element 0 (DC) and
+// element 4 (Nyquist) as independent reals (pffft_priv_impl.h:1626-1629, :1680-1683).
+template <typename T> struct vec4 { T v[4]; };
+template <typename T> PF_D vec4<T> ld4(const T* p);
+template <> PF_D vec4<float> ld4<float>(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return {{t.x, t.y, t.z, t.w}}; }
+template <> PF_D vec4<double> ld4<double>(const double* p) {
+  double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  return {{a.x, a.y, b.x, b.y}};
+}
+template <typename T> PF_D void st4(T* p, const vec4<T>& v);
+template <> PF_D void st4<float>(float* p, const vec4<float>& v) { *reinterpret_cast<float4*>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]); }
+template <> PF_D void st4<double>(double* p, const vec4<double>& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.v[0], v.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v.v[2], v.v[3]);
+}
+PF_D float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
+PF_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+PF_D float  add_rn(float a, float b)   { return __fadd_rn(a, b); }
+PF_D double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T, bool REAL, bool ACC>
+__global__ void __launch_bounds__(256) k_zconvolve(const T* a, const T* b, T* ab,  /* may alias (ref pffft.h:194,208) */
+                                                   T scaling, long long batch, int per /*elements per spectrum*/, int b_shared) {
+  const int groups = per / 8;
+  const long long total = batch * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / groups;
+    const int g = (int)(idx - t * groups);
+    const long long off = t * per + 8LL * g;
+    const long long boff = (b_shared ? 0 : t * (long long)per) + 8LL * g;
+    const vec4<T> ar = ld4(a + off), ai = ld4(a + off + 4);
+    const vec4<T> br = ld4(b + boff), bi = ld4(b + boff + 4);
+    vec4<T> cr, ci;
+    if (ACC) { cr = ld4(ab + off); ci = ld4(ab + off + 4); }
+    vec4<T> orr, oi;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const T re = add_rn(mul_rn(ar.v[l], br.v[l]), -mul_rn(ai.v[l], bi.v[l]));
+      const T im = add_rn(mul_rn(ai.v[l], br.v[l]), mul_rn(ar.v[l], bi.v[l]));
+      if (ACC) { orr.v[l] = add_rn(mul_rn(re, scaling), cr.v[l]); oi.v[l] = add_rn(mul_rn(im, scaling), ci.v[l]); }
+      else     { orr.v[l] = mul_rn(re, scaling);                   oi.v[l] = mul_rn(im, scaling); }
+    }
+    if (REAL && g == 0) {
+      const T dc = mul_rn(mul_rn(ar.v[0], br.v[0]), scaling);
+      const T ny = mul_rn(mul_rn(ai.v[0], bi.v[0]), scaling);
+      orr.v[0] = ACC ? add_rn(cr.v[0], dc) : dc;
+      oi.v[0]  = ACC ? add_rn(ci.v[0], ny) : ny;
+    }
+    st4(ab + off, orr);
+    st4(ab + off + 4, oi);
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace pf

@@ -1,0 +1,109 @@
+"""CPU-side checks of logic shared with the device code.  tests/emu/libemu.so (built by
+__graft_entry__.build()) steps the PF_HD functions of pffft_b200/csrc -- index maps, Stockham stages,
+real pre/post rotations, the warp kernel's two phases -- one lane at a time on the host, so the algebra
+is verified against the reference before any GPU time is spent.  It is a test harness: the product
+library never executes these on the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, uniform
+
+EMU = os.path.join(ROOT, "tests", "emu", "libemu.so")
+L_C_ORD, L_C_Z, L_R_TIME, L_R_ORD, L_R_Z = range(5)
+S_C_ORD, S_C_Z, S_R_TIME, S_R_ORD, S_R_Z = range(5)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(EMU):
+        pytest.skip("tests/emu/libemu.so not built (python __graft_entry__.py)")
+    e = C.CDLL(EMU)
+    e.emu_generic.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p] + [C.c_longlong] * 4 + [C.c_int]
+    e.emu_w1024.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    e.emu_fastconv_produced.restype = C.c_longlong
+    e.emu_fastconv_produced.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
+    return e
+
+
+def test_zdomain_index_maps_equal_reference_zreorder(emu, ref):
+    for tr in (0, 1):
+        for N in [32, 64, 96, 128, 160, 192, 256, 288, 384, 480, 512, 640, 800, 1024, 2592, 4000, 4096, 12000]:
+            if not ref.lib.pffft_is_valid_size(N, tr):
+                continue
+            per = N if tr == 0 else 2 * N
+            canon = ref.zreorder(N, tr, np.arange(per, dtype=np.float32), 0)   # canon[i] = z-domain index feeding slot i
+            slots = N // 2 if tr == 0 else N
+            pos = np.array([emu.emu_zpos(1 if tr == 0 else 0, k, N) for k in range(slots)])
+            assert np.array_equal(canon[0::2], pos) and np.array_equal(canon[1::2], pos + 4), (N, tr)
+
+
+def _emu_run(emu, prec, N, tr, d, lm, sm, x):
+    dt = np.float32 if prec == 0 else np.float64
+    n = N if tr == 0 else 2 * N
+    x = np.ascontiguousarray(x, dtype=dt); o = np.zeros(n, dt)
+    assert emu.emu_generic(prec, N, tr, d, lm, sm, x.ctypes.data, o.ctypes.data, 1, n, n, -1, n) == 0
+    return o
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_generic_kernel_algebra(emu, ref, R, prec):
+    dt = np.float32 if prec == 0 else np.float64
+    rng = np.random.default_rng(1)
+    for N in [16, 32, 48, 64, 96, 160, 240, 256, 480, 800, 1024, 2592, 4096]:
+        for tr in (0, 1):
+            if not ref.lib.pffft_is_valid_size(N, tr):
+                continue
+            tol = 2e-6 if prec == 0 else (1e-13 if (N & (N - 1)) == 0 else 2e-7)
+            x = uniform(rng, N if tr == 0 else 2 * N, dt)
+            want = ref.transform(N, tr, x, 0, True, dt); wantz = ref.transform(N, tr, x, 0, False, dt)
+            fo = _emu_run(emu, prec, N, tr, 0, L_R_TIME if tr == 0 else L_C_ORD, S_R_ORD if tr == 0 else S_C_ORD, x)
+            fz = _emu_run(emu, prec, N, tr, 0, L_R_TIME if tr == 0 else L_C_ORD, S_R_Z if tr == 0 else S_C_Z, x)
+            bo = _emu_run(emu, prec, N, tr, 1, L_R_ORD if tr == 0 else L_C_ORD, S_R_TIME if tr == 0 else S_C_ORD, want)
+            bz = _emu_run(emu, prec, N, tr, 1, L_R_Z if tr == 0 else L_C_Z, S_R_TIME if tr == 0 else S_C_ORD, wantz)
+            assert R.relmax(fo, want) <= tol and R.relmax(fz, wantz) <= tol, (N, tr)
+            assert R.relmax(bo, ref.transform(N, tr, want, 1, True, dt)) <= tol, (N, tr)
+            assert R.relmax(bz, ref.transform(N, tr, wantz, 1, False, dt)) <= tol, (N, tr)
+
+
+def test_register_fft_networks(emu):
+    rng = np.random.default_rng(2)
+    for N in (2, 4, 8, 16, 32, 64):
+        for d in (0, 1):
+            x = uniform(rng, 2 * N); o = np.zeros(2 * N, np.float32)
+            assert emu.emu_regfft(N, d, x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)) == 0
+            z = x[0::2].astype(np.float64) + 1j * x[1::2]
+            w = np.fft.fft(z) if d == 0 else np.fft.ifft(z) * N
+            assert np.max(np.abs((o[0::2] + 1j * o[1::2]) - w)) / np.max(np.abs(w)) <= 5e-7
+
+
+def test_warp_kernel_phases_c1024(emu, ref, R):
+    rng = np.random.default_rng(3)
+    x = uniform(rng, 3 * 2048).reshape(3, 2048)
+    for d in (0, 1):
+        o = np.zeros_like(x)
+        emu.emu_w1024(d, x.ctypes.data, o.ctypes.data, 3)
+        w = ref.transform_batch(1024, 1, x, d, True)
+        assert max(R.relmax(o[i], w[i]) for i in range(3)) <= 2e-6
+
+
+def test_overlap_save_block_algebra_matches_reference_lengths(emu, ref):
+    """the closed-form block plan used by pffastconv_apply yields exactly the reference loop's output count
+    (tests/test_pffastconv.c:810-820 treats length mismatches as the hard failure)"""
+    h = np.ones(200, np.float32)
+    for taps in (1, 2, 31, 124, 131, 144, 200):
+        for flags in (0, 1, 17):
+            for bl in (0, 64, 512, 4096):
+                for length in (taps - 1, taps, taps + 1, 300, 1000, 4097, 10000):
+                    if length <= 0:
+                        continue
+                    cf = 2 if flags == 17 else 1
+                    x = np.zeros(length * (2 if flags & 1 else 1) , np.float32)
+                    for flush in (0, 1):
+                        _, n_ref, bl_ref = ref.fastconv(h[:taps], x, bl, flags, flush)
+                        nfft = bl_ref * cf
+                        flen = 2 * taps - 1 if cf == 2 else taps
+                        got = emu.emu_fastconv_produced(cf * length, nfft, flen, flush, 1 if cf == 2 else 0) // cf
+                        assert got == n_ref, (taps, flags, bl, length, flush, got, n_ref)

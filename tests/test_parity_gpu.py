@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the unmodified reference
+(oracle/_ref) and the committed golden fixtures.
+
+Tolerance (north_star): relmax = max|got-ref| / max|ref| <= 1e-5 (float), 1e-12 (double) on the
+ordered output; permutations (zreorder) and zconvolve are bit-exact.
+Properties restated from the reference's own tests are cited inline."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, uniform
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+# bench_pffft.c:445 validation sizes + the power-of-two ladder of tests/test_pffft.c:333
+POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864]
+
+
+def torch_mod():
+    import torch
+    return torch
+
+
+def gpu_transform(pf, N, tr, x, direction, ordered, dtype, device_ptrs):
+    """one call of pffft_transform(_ordered) on a (batch, per) array"""
+    with pf.Setup(N, tr, dtype) as s:
+        if device_ptrs:
+            torch = torch_mod()
+            xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            yd = s.transform_batch(xd, direction, ordered)
+            torch.cuda.synchronize()
+            return yd.cpu().numpy()
+        return s.transform_batch(np.ascontiguousarray(x), direction, ordered)
+
+
+def valid(pf, N, tr):
+    return pf.pffft_is_valid_size(N, tr) == 1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("N", POW2 + NONPOW2)
+def test_ordered_parity_vs_reference(pf, ref, R, N, tr, dtype):
+    if not valid(pf, N, tr):
+        pytest.skip("size not valid for this transform type")
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(N * 2 + tr)
+    per = N if tr == 0 else 2 * N
+    batch = 3
+    x = uniform(rng, batch * per, dtype).reshape(batch, per)
+    want_f = ref.transform_batch(N, tr, x, 0, True, dtype)
+    got_f = gpu_transform(pf, N, tr, x, 0, True, dtype, device_ptrs=True)
+    pow2 = (N & (N - 1)) == 0
+    # the reference's double path carries float-precision radix-3/5 constants (pffft_priv_impl.h:154,259-262:
+    # literals with an 'f' suffix), so for non-power-of-two doubles the ORACLE is only ~1e-8 accurate;
+    # there the 1e-12 contract is checked against numpy's float64 FFT instead (see test below).
+    tol = TOL[dtype] if (pow2 or dtype == np.float32) else 5e-7
+    for b in range(batch):
+        assert R.relmax(got_f[b], want_f[b]) <= tol, ("forward", N, tr, dtype, b)
+    want_b = ref.transform_batch(N, tr, want_f, 1, True, dtype)
+    got_b = gpu_transform(pf, N, tr, want_f, 1, True, dtype, device_ptrs=True)
+    for b in range(batch):
+        assert R.relmax(got_b[b], want_b[b]) <= tol, ("backward", N, tr, dtype, b)
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("N", [96, 160, 480, 4000, 12000, 1024, 65536])
+def test_double_vs_numpy_1e12(pf, R, N, tr):
+    if not valid(pf, N, tr):
+        pytest.skip("size")
+    rng = np.random.default_rng(N + tr)
+    per = N if tr == 0 else 2 * N
+    x = uniform(rng, per, np.float64)
+    got = gpu_transform(pf, N, tr, x[None, :], 0, True, np.float64, True)[0]
+    if tr == 1:
+        want = np.fft.fft(x[0::2] + 1j * x[1::2])
+        want = np.stack([want.real, want.imag], -1).ravel()
+    else:
+        X = np.fft.rfft(x)
+        want = np.stack([X.real[:-1], X.imag[:-1]], -1).ravel()
+        want[1] = X.real[-1]                       # slot 0 = (DC, Nyquist), include/pffft/pffft.h:144-155
+    assert R.relmax(got, want) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("N", [16, 32, 64, 96, 160, 256, 1024, 2048, 4000, 4096, 8192, 16384, 36864])
+def test_unordered_layout_and_zreorder(pf, ref, R, N, tr, dtype):
+    """pffft_transform's z-domain output has the reference's internal layout: comparable element-wise,
+    zreorder is the same permutation (bit-exact), ordered == zreorder(unordered) bit-exact
+    (bench_pffft.c:343-366)."""
+    if not valid(pf, N, tr):
+        pytest.skip("size")
+    torch = torch_mod()
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(7 * N + tr)
+    per = N if tr == 0 else 2 * N
+    x = uniform(rng, 2 * per, dtype).reshape(2, per)
+    tol = TOL[dtype] if (N & (N - 1)) == 0 or dtype == np.float32 else 5e-7
+    want_z = ref.transform_batch(N, tr, x, 0, False, dtype)
+    with pf.Setup(N, tr, dtype) as s:
+        xd = torch.from_numpy(x).cuda()
+        zd = s.transform_batch(xd, 0, ordered=False)
+        od = s.transform_batch(xd, 0, ordered=True)
+        rd = s.zreorder_batch(zd, 0)                       # z -> canonical
+        zz = s.zreorder_batch(rd, 1)                       # canonical -> z
+        bd = s.transform_batch(zd, 1, ordered=False)       # backward from the z-domain
+        torch.cuda.synchronize()
+        z, o, r_, zz, b = [t.cpu().numpy() for t in (zd, od, rd, zz, bd)]
+    for i in range(2):
+        assert R.relmax(z[i], want_z[i]) <= tol
+        # permutation identical to the reference's, on the reference's own data: bit-exact
+        assert np.array_equal(ref.zreorder(N, tr, want_z[i], 0, dtype), gpu_zreorder_host(pf, N, tr, want_z[i], 0, dtype))
+        assert R.relmax(b[i], x[i] * N) <= 10 * tol       # BACKWARD(FORWARD(x)) = N x  (pffft.h:134)
+    assert np.array_equal(o, r_), "ordered != zreorder(unordered)"
+    assert np.array_equal(zz, z), "zreorder(BACKWARD) o zreorder(FORWARD) != identity"
+
+
+def gpu_zreorder_host(pf, N, tr, v, direction, dtype):
+    with pf.Setup(N, tr, dtype) as s:
+        out = np.empty_like(v)
+        pf.pffft_zreorder(s.handle, np.ascontiguousarray(v), out, direction)   # classic entry point, host pointers
+        return out
+
+
+@pytest.mark.parametrize("N,tr", [(64, 1), (1024, 1), (4096, 0), (96, 1), (160, 0)])
+def test_classic_entry_points_host_pointers_and_inplace(pf, ref, R, N, tr):
+    """C1 plumbing: pffft_transform_ordered with HOST pointers (the reference's only mode), work=NULL,
+    in-place == out-of-place bit-exact (bench_pffft.c:343-349)."""
+    rng = np.random.default_rng(1)
+    per = N if tr == 0 else 2 * N
+    x = uniform(rng, per)
+    want = ref.transform(N, tr, x, 0, True)
+    s = pf.pffft_new_setup(N, tr)
+    assert s
+    try:
+        out = np.zeros(per + 16, np.float32)
+        out[per:] = 777.0                                   # canary (bench_pffft.c:552)
+        pf.pffft_transform_ordered(s, x, out, None, pf.PFFFT_FORWARD)
+        assert R.relmax(out[:per], want) <= 1e-5
+        assert np.all(out[per:] == 777.0)
+        inpl = x.copy()
+        pf.pffft_transform_ordered(s, inpl, inpl, None, pf.PFFFT_FORWARD)
+        assert np.array_equal(inpl, out[:per])
+        back = np.empty(per, np.float32)
+        pf.pffft_transform_ordered(s, out[:per].copy(), back, None, pf.PFFFT_BACKWARD)
+        assert R.relmax(back, x * N) <= 1e-5
+        # unordered pair through the classic calls
+        z = np.empty(per, np.float32); c = np.empty(per, np.float32)
+        pf.pffft_transform(s, x, z, None, pf.PFFFT_FORWARD)
+        pf.pffft_zreorder(s, z, c, pf.PFFFT_FORWARD)
+        assert np.array_equal(c, out[:per])
+    finally:
+        pf.pffft_destroy_setup(s)
+
+
+def test_batch_element_equals_single_launch(pf):
+    """batch element b of a batched launch == the same transform launched alone, bit-exact."""
+    torch = torch_mod()
+    for N, tr in [(1024, 1), (256, 1), (4096, 0), (96, 1)]:
+        per = N if tr == 0 else 2 * N
+        rng = np.random.default_rng(5)
+        x = torch.from_numpy(uniform(rng, 37 * per).reshape(37, per)).cuda()
+        with pf.Setup(N, tr) as s:
+            yb = s.transform_batch(x, 0, True)
+            for b in (0, 17, 36):
+                y1 = s.transform_batch(x[b].contiguous(), 0, True)
+                assert torch.equal(y1, yb[b])
+
+
+def test_host_batch_pipeline_matches_device_path(pf):
+    """host-pointer batches are chunked through 3 streams; result must equal the device-pointer path bit-exactly
+    (enough transforms for several chunks)."""
+    torch = torch_mod()
+    N, tr = 1024, 1
+    per = 2 * N
+    batch = 3 * 4096 + 5                                    # > 3 chunks of 32 MiB
+    rng = np.random.default_rng(9)
+    x = uniform(rng, batch * per).reshape(batch, per)
+    with pf.Setup(N, tr) as s:
+        yh = s.transform_batch(x, 0, True)
+        yd = s.transform_batch(torch.from_numpy(x).cuda(), 0, True).cpu().numpy()
+    assert np.array_equal(yh, yd)
+
+
+def test_golden_fixtures(pf, R):
+    """committed outputs of the unmodified reference (tests/golden/make_golden.py)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pffft_golden.npz"))
+    keys = sorted(k[:-2] for k in g.files if k.endswith("_x") and k.startswith("N"))
+    assert len(keys) >= 13
+    for key in keys:
+        N = int(key[1:].split("_")[0]); tr = 0 if "_r_" in key else 1
+        dtype = np.dtype(np.float32 if key.endswith("f4") else np.float64)
+        tol = TOL[dtype] if (N & (N - 1)) == 0 or dtype == np.float32 else 5e-7
+        x = g[key + "_x"]
+        assert R.relmax(gpu_transform(pf, N, tr, x[None], 0, True, dtype, True)[0], g[key + "_fwd_ordered"]) <= tol, key
+        assert R.relmax(gpu_transform(pf, N, tr, x[None], 0, False, dtype, True)[0], g[key + "_fwd_z"]) <= tol, key
+        assert R.relmax(gpu_transform(pf, N, tr, g[key + "_fwd_ordered"][None], 1, True, dtype, False)[0],
+                        g[key + "_bwd_ordered"]) <= tol, key
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+def test_zconvolve_bit_exact(pf, ref, tr):
+    """pffft_zconvolve_accumulate / _no_accu reproduce the reference's unfused arithmetic exactly, including the
+    real-transform DC/Nyquist rule (pffft_priv_impl.h:1626-1629, :1680-1683); aliasing ab==a allowed."""
+    torch = torch_mod()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pffft_golden.npz"))
+    key = "zconv_%s" % ("r" if tr == 0 else "c")
+    a, b, ab = g[key + "_a"], g[key + "_b"], g[key + "_ab"]
+    N = 256
+    with pf.Setup(N, tr) as s:
+        for acc, want in ((True, g[key + "_acc"]), (False, g[key + "_noacc"])):
+            out = ab.copy()
+            (pf.pffft_zconvolve_accumulate if acc else pf.pffft_zconvolve_no_accu)(s.handle, a, b, out, 0.37)   # host pointers
+            assert np.array_equal(out, want), ("host", acc)
+            ad, bd, od = [torch.from_numpy(v.copy()).cuda() for v in (a, b, ab)]
+            (pf.pffft_zconvolve_accumulate if acc else pf.pffft_zconvolve_no_accu)(s.handle, ad, bd, od, 0.37)   # device pointers
+            assert np.array_equal(od.cpu().numpy(), want), ("device", acc)
+        # aliasing: ab == a
+        ad = torch.from_numpy(a.copy()).cuda(); bd = torch.from_numpy(b).cuda()
+        pf.pffft_zconvolve_no_accu(s.handle, ad, bd, ad, 0.37)
+        assert np.array_equal(ad.cpu().numpy(), ref.zconvolve(N, tr, a, b, a, 0.37, False))
+    # other sizes / double against the live reference
+    for N2, dt in ((1024, np.float32), (96, np.float32), (512, np.float64)):
+        if not pf.pffft_is_valid_size(N2, tr):
+            continue
+        per = N2 if tr == 0 else 2 * N2
+        rng = np.random.default_rng(N2)
+        a2, b2, c2 = [uniform(rng, per, dt) for _ in range(3)]
+        with pf.Setup(N2, tr, dt) as s2:
+            out = c2.copy()
+            pf.pffft_zconvolve_accumulate(s2.handle, a2, b2, out, 0.25)
+            assert np.array_equal(out, ref.zconvolve(N2, tr, a2, b2, c2, 0.25, True, dt))
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+def test_zconvolve_is_circular_convolution(pf, R, tr):
+    """BACKWARD(zconvolve(FWD_z(x), FWD_z(h), 1/N)) == circular convolution (bench_pffft.c:396-425)."""
+    torch = torch_mod()
+    N = 512
+    per = N if tr == 0 else 2 * N
+    rng = np.random.default_rng(3)
+    x, h = uniform(rng, per), uniform(rng, per)
+    with pf.Setup(N, tr) as s:
+        xd, hd = torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda()
+        X = s.transform_batch(xd, 0, ordered=False); H = s.transform_batch(hd, 0, ordered=False)
+        acc = torch.zeros_like(X)
+        s.zconvolve_batch(X, H, acc, 1.0 / N, accumulate=True)
+        s.zconvolve_batch(X, H, acc, 1.0 / N, accumulate=True)        # twice -> doubled
+        y = s.transform_batch(acc, 1, ordered=False).cpu().numpy()
+    if tr == 0:
+        want = np.fft.irfft(np.fft.rfft(x.astype(np.float64)) * np.fft.rfft(h.astype(np.float64)), N)
+    else:
+        cx = x[0::2].astype(np.float64) + 1j * x[1::2]; ch = h[0::2].astype(np.float64) + 1j * h[1::2]
+        w = np.fft.ifft(np.fft.fft(cx) * np.fft.fft(ch))
+        want = np.stack([w.real, w.imag], -1).ravel()
+    assert R.relmax(y, 2 * want) <= 1e-5
+
+
+def _carrier_case(pf, N, tr, dtype, dyn_db_min):
+    """one (N, real|complex) sweep of tests/test_pffft.c:109-243: carrier at every 16th bin, amplitude 1.0/1.1,
+    start phase m*pi/8; limits from :52-67 (140 dB float / 215 dB double, 1e-4 degree, 1e-6 magnitude,
+    round trip sum err^2 <= N*1e-7)."""
+    torch = torch_mod()
+    cplx = tr == 1
+    with pf.Setup(N, tr, dtype) as s:
+        m = 0
+        for k in range(0, N if cplx else N // 2 + 1, N // 16):
+            amp = 1.0 if m % 3 == 0 else 1.1
+            freq = k / N if k < N / 2 else (k - N) / N
+            dphi = 2 * np.pi * freq
+            if dphi < 0:
+                dphi += 2 * np.pi
+            phi0 = (m % 4) * 0.125 * np.pi
+            ph = np.empty(N)
+            phi = phi0
+            for j in range(N):                              # same normalised phase accumulation as the reference
+                ph[j] = phi
+                phi += dphi
+                if phi >= np.pi:
+                    phi -= 2 * np.pi
+            if cplx:
+                x = np.stack([amp * np.cos(ph).astype(dtype), amp * np.sin(ph).astype(dtype)], -1).ravel().astype(dtype)
+            else:
+                x = (amp * np.cos(ph).astype(dtype)).astype(dtype)
+            xd = torch.from_numpy(x).cuda()
+            yd = s.transform_batch(xd, 0, True)
+            y = yd.cpu().numpy().astype(np.float64)
+            nb = N if cplx else N // 2 + 1
+            pwr = np.empty(nb)
+            for j in range(nb):
+                if not cplx and j == 0:
+                    pwr[j] = y[0] * y[0]
+                elif not cplx and j == N // 2:
+                    pwr[j] = y[1] * y[1]
+                else:
+                    pwr[j] = y[2 * j] ** 2 + y[2 * j + 1] ** 2
+            car = pwr[k]
+            other = np.delete(pwr, k).max()
+            dyn = 10 * np.log10(car) - 10 * np.log10(max(other, 1e-300))
+            assert dyn >= dyn_db_min, (N, tr, k, dyn)
+            if k > 0 and k != N // 2:
+                got_phi = np.arctan2(y[2 * k + 1], y[2 * k])
+                assert abs(got_phi - phi0) <= 1e-4 * np.pi / 180, (N, tr, k, got_phi, phi0)
+            expected = amp if cplx else (amp if (k == 0 or k == N // 2) else amp / 2)
+            assert abs(np.sqrt(car) / N - expected) <= 1e-6, (N, tr, k)
+            z = s.transform_batch(yd, 1, True).cpu().numpy().astype(np.float64) / N
+            assert np.sum((x - z) ** 2) <= N * 1e-7, (N, tr, k)
+            m += 1
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("N", [32, 64, 256, 1024, 4096, 16384, 65536])
+def test_carrier_properties_float(pf, N, tr):
+    _carrier_case(pf, N, tr, np.float32, 140.0)
+
+
+@pytest.mark.parametrize("tr", [0, 1])
+@pytest.mark.parametrize("N", [32, 1024, 8192, 65536])
+def test_carrier_properties_double(pf, N, tr):
+    _carrier_case(pf, N, tr, np.float64, 215.0)
+
+
+def test_full_size_round_trip_c2(pf):
+    """BASELINE C2 shape at reduced batch for memory: N=1024 complex, 2^17 transforms, ifft(fft(x))/N == x and
+    Parseval per transform -- size-independent properties at scale, on device-resident data."""
+    torch = torch_mod()
+    N, batch = 1024, 1 << 17
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    x = torch.rand((batch, 2 * N), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    with pf.Setup(N, 1) as s:
+        y = s.transform_batch(x, 0, True)
+        z = s.transform_batch(y, 1, True)
+    err = ((z / N - x) ** 2).sum(dim=1).max().item()
+    assert err <= N * 1e-7
+    ex = (x.double() ** 2).sum(dim=1); ey = (y.double() ** 2).sum(dim=1) / N
+    assert torch.max(torch.abs(ey / ex - 1)).item() <= 1e-5
+    # linearity: F(a x1 + x2) = a F(x1) + F(x2)
+    x2 = torch.rand((256, 2 * N), generator=g, device="cuda") * 2 - 1
+    with pf.Setup(N, 1) as s:
+        lhs = s.transform_batch(0.5 * x[:256] + x2, 0, True)
+        rhs = 0.5 * y[:256] + s.transform_batch(x2, 0, True)
+    assert (lhs - rhs).abs().max().item() <= 1e-5 * rhs.abs().max().item()
+
+
+def test_kernel_selection_reports_tuned_kernel(pf):
+    with pf.Setup(1024, 1) as s:
+        assert "c1024" in s.kernel
+    with pf.Setup(96, 1) as s:
+        assert s.kernel == "smem_stockham"
+    with pf.Setup(65536, 1) as s:
+        assert s.kernel == "global_stockham"
+    n0 = pf.launch_count()
+    torch = torch_mod()
+    with pf.Setup(1024, 1) as s:
+        s.transform_batch(torch.zeros(4, 2048, device="cuda"), 0, True)
+    assert pf.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_every_c1024_variant_is_correct(pf, ref, R, variant, monkeypatch):
+    torch = torch_mod()
+    monkeypatch.setenv("PFFFT_B200_C1024", str(variant))
+    rng = np.random.default_rng(variant)
+    batch = 1500                                            # more transforms than resident warps: exercises the ring
+    x = uniform(rng, batch * 2048).reshape(batch, 2048)
+    with pf.Setup(1024, 1) as s:
+        xd = torch.from_numpy(x).cuda()
+        f = s.transform_batch(xd, 0, True)
+        z = s.transform_batch(xd, 0, False)
+        b = s.transform_batch(f, 1, True)
+        bz = s.transform_batch(z, 1, False)
+        inpl = xd.clone(); s.transform_batch(inpl, 0, True, out=inpl)
+        torch.cuda.synchronize()
+        f_, z_, b_, bz_ = [t.cpu().numpy() for t in (f, z, b, bz)]
+        assert torch.equal(inpl, f)
+    idx = [0, 1, 2, 747, 1498, 1499]
+    wf = ref.transform_batch(1024, 1, x[idx], 0, True)
+    wz = ref.transform_batch(1024, 1, x[idx], 0, False)
+    for j, i in enumerate(idx):
+        assert R.relmax(f_[i], wf[j]) <= 1e-5
+        assert R.relmax(z_[i], wz[j]) <= 1e-5
+        assert R.relmax(b_[i], x[i] * 1024) <= 1e-5
+        assert R.relmax(bz_[i], x[i] * 1024) <= 1e-5
+    # all transforms: against numpy in double
+    cx = x[:, 0::2].astype(np.float64) + 1j * x[:, 1::2]
+    W = np.fft.fft(cx, axis=1)
+    got = f_[:, 0::2] + 1j * f_[:, 1::2]
+    assert np.max(np.abs(got - W)) / np.max(np.abs(W)) <= 1e-5
