@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""bench_configs.py -- secondary measurements: every BASELINE.json config (C1..C4) plus a size sweep,
+one JSON line each (bench.py stays the single-line headline the driver reads).  Device-resident data,
+CUDA-event timing, inputs larger than L2 where the config allows."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def ev_time(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    import torch
+    import pffft_b200 as pf
+    peak = 6573.2
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    out = []
+
+    def emit(d):
+        print(json.dumps(d), flush=True)
+        out.append(d)
+
+    # C1: N=64 complex forward, batch 1, host pointers through the classic entry point (latency)
+    x = (np.random.default_rng(1).random(128) * 2 - 1).astype(np.float32)
+    y = np.empty_like(x)
+    s = pf.pffft_new_setup(64, 1)
+    for _ in range(20):
+        pf.pffft_transform_ordered(s, x, y, None, 0)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        pf.pffft_transform_ordered(s, x, y, None, 0)
+    dt = (time.perf_counter() - t0) / 200
+    pf.pffft_destroy_setup(s)
+    emit({"config": "C1 N=64 cplx fwd batch=1 host pointers (pffft_transform_ordered)", "us_per_call": dt * 1e6})
+
+    def xform_case(name, N, tr, batch, direction, ordered, dtype=torch.float32):
+        per = N if tr == 0 else 2 * N
+        es = 4 if dtype == torch.float32 else 8
+        g = torch.Generator(device="cuda"); g.manual_seed(1235)
+        xin = torch.rand((batch, per), generator=g, device="cuda", dtype=dtype) * 2 - 1
+        yout = torch.empty_like(xin)
+        st = pf.Setup(N, tr, np.float32 if dtype == torch.float32 else np.float64)
+        t = ev_time(lambda: pf.pffftb_transform_batch(st.handle, xin, yout, batch, direction, 1 if ordered else 0), args.iters)
+        nbytes = 2 * batch * per * es
+        flops = (5 if tr == 1 else 2.5) * N * np.log2(N) * batch
+        emit({"config": name, "N": N, "transform": "real" if tr == 0 else "complex", "batch": batch, "kernel": st.kernel,
+              "ms": t * 1e3, "ffts_per_s": batch / t, "gbs_algorithmic": nbytes / t / 1e9, "frac_of_hbm_peak": nbytes / t / 1e9 / peak,
+              "gflops": flops / t / 1e9, "dtype": "f32" if dtype == torch.float32 else "f64",
+              "direction": "fwd" if direction == 0 else "bwd", "ordered": bool(ordered)})
+        st.close()
+        del xin, yout
+        torch.cuda.empty_cache()
+
+    xform_case("C2 N=1024 cplx fwd batch=2^20", 1024, 1, 1 << 20, 0, True)
+    xform_case("C2 N=1024 cplx bwd batch=2^20", 1024, 1, 1 << 20, 1, True)
+    xform_case("C3 N=4096 real fwd batch=2^18", 4096, 0, 1 << 18, 0, True)
+    xform_case("C3' N=4096 real bwd batch=2^18", 4096, 0, 1 << 18, 1, True)
+
+    # C4: pffastconv 2^24-sample real stream, 4097 taps, device resident, one apply(flush=1) call
+    n, taps = 1 << 24, 4097
+    xs = torch.from_numpy((np.arange(n) % 4093).astype(np.float32)).cuda()
+    ys = torch.empty(n, device="cuda")
+    h = np.array([(-1.0, 1.0, 0.5)[j % 3] for j in range(taps)], np.float32)
+    fc = pf.FastConv(h, 0, 0)
+    produced = fc.apply(xs, ys, n, 1)
+    t = ev_time(lambda: fc.apply(xs, ys, n, 1), args.iters)
+    emit({"config": "C4 pffastconv 2^24 samples, 4097 taps, device resident", "Nfft": fc.block_len, "produced": produced,
+          "ms": t * 1e3, "msamples_per_s": produced / t / 1e6, "gbs_algorithmic": 8.0 * produced / t / 1e9,
+          "frac_of_hbm_peak": 8.0 * produced / t / 1e9 / peak})
+    xh = xs.cpu().numpy(); yh = np.empty(n, np.float32)
+    fc.apply(xh, yh, n, 1)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        fc.apply(xh, yh, n, 1)
+    th = (time.perf_counter() - t0) / 3
+    emit({"config": "C4 pffastconv, host pointers (pageable numpy buffers)", "ms": th * 1e3, "msamples_per_s": produced / th / 1e6})
+    fc.close()
+
+    if args.sweep:
+        for N in (64, 256, 512, 2048, 4096, 8192, 16384, 65536, 96, 960, 4000):
+            batch = max(1, (1 << 28) // (8 * N))
+            xform_case("sweep cplx fwd", N, 1, batch, 0, True)
+        for N in (1024, 8192, 65536):
+            batch = max(1, (1 << 28) // (4 * N))
+            xform_case("sweep real fwd", N, 0, batch, 0, True)
+        xform_case("sweep cplx fwd f64", 1024, 1, 1 << 17, 0, True, torch.float64)
+        xform_case("sweep cplx fwd z-domain", 1024, 1, 1 << 18, 0, False)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

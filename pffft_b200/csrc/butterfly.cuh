@@ -102,8 +102,8 @@ template <int R, int SIGN, typename T> PF_HD void dftR(cpx<T>* a) {
 // One butterfly (A,B) <- (A + w B, A - w B), w = exp(SIGN 2 pi i J/G), G = group size:
 //   J=0, G/4      : adds only
 //   G/8, 3G/8     : 2 adds + 4 fma          (w = (+-1 + SIGN i)/sqrt2)
-//   general       : 6 fma                    (A' = A + wB by 2 fma each part, B' = 2A - A')
-// -> 388 instructions for N=32 instead of 456 for the mul-then-add form.
+//   general       : 8 fma                    (each output its own 2-fma chain)
+// -> 428 instructions for N=32 (456 for the mul-then-add form), every product fused.
 // ---------------------------------------------------------------------------------------------
 template <int J, int G, int SIGN, typename T> PF_HD void dit_bfly(cpx<T>& A, cpx<T>& B) {
   const cpx<T> a = A, b = B;
@@ -116,21 +116,24 @@ template <int J, int G, int SIGN, typename T> PF_HD void dit_bfly(cpx<T>& A, cpx
     const T h = T(0.70710678118654752440084436210485);
     const T sx = (SIGN < 0) ? (b.x + b.y) : (b.x - b.y);
     const T sy = (SIGN < 0) ? (b.y - b.x) : (b.y + b.x);
-    A.x = a.x + h * sx; B.x = a.x - h * sx;
-    A.y = a.y + h * sy; B.y = a.y - h * sy;
+    A.x = fma(h, sx, a.x); B.x = fma(-h, sx, a.x);
+    A.y = fma(h, sy, a.y); B.y = fma(-h, sy, a.y);
   } else if constexpr (8 * J == 3 * G) {
     const T h = T(0.70710678118654752440084436210485);
     const T sx = (SIGN < 0) ? (b.x - b.y) : (b.x + b.y);
     const T sy = (SIGN < 0) ? (b.y + b.x) : (b.y - b.x);
-    A.x = a.x - h * sx; B.x = a.x + h * sx;
-    A.y = a.y - h * sy; B.y = a.y + h * sy;
+    A.x = fma(-h, sx, a.x); B.x = fma(h, sx, a.x);
+    A.y = fma(-h, sy, a.y); B.y = fma(h, sy, a.y);
   } else {
     constexpr ct::cs w = ct::cossin2pi(J, G);
     const T c = T(w.c), s = T(SIGN) * T(w.s);
-    const T px = a.x + b.x * c - b.y * s;      // Re(a + w b)
-    const T py = a.y + b.x * s + b.y * c;      // Im(a + w b)
-    A.x = px; A.y = py;
-    B.x = fma(T(2), a.x, -px); B.y = fma(T(2), a.y, -py);   // explicit: the compiler would rewrite 2*a as a+a and lose the fusion
+    // both outputs as their own 2-fma chains (8 fma per butterfly).  The 6-fma variant B = 2a - A
+    // re-injects A's rounding error into B, which costs ~4 dB of spur-free range on pure tones
+    // (tests/test_pffft.c wants >= 140 dB); the kernel is HBM-bound, the 2 extra fma are free.
+    A.x = fma(-b.y, s, fma(b.x, c, a.x));      // Re(a + w b)
+    A.y = fma(b.y, c, fma(b.x, s, a.y));       // Im(a + w b)
+    B.x = fma(b.y, s, fma(-b.x, c, a.x));      // Re(a - w b)
+    B.y = fma(-b.y, c, fma(-b.x, s, a.y));     // Im(a - w b)
   }
 }
 

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 
 #define PF_HD __host__ __device__ __forceinline__
 #define PF_D  __device__ __forceinline__
@@ -24,12 +25,12 @@ template <typename T> PF_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
 template <typename T> PF_HD cpx<T> scale(cpx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
 // a * b (contraction to FMA allowed: 2 mul + 2 fma)
 template <typename T> PF_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
-  return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return mk<T>(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 // a * (b.x + i*SIGNFLIP*b.y): SIGN=-1 keeps the table's forward sign, SIGN=+1 conjugates it
 template <int SIGN, typename T> PF_HD cpx<T> cmul_dir(cpx<T> a, cpx<T> w) {
   if (SIGN < 0) return cmul(a, w);
-  return mk<T>(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+  return mk<T>(fma(a.x, w.x, a.y * w.y), fma(a.y, w.x, -(a.x * w.y)));
 }
 // multiply by SIGN*i  (SIGN=-1 : *(-i) ; SIGN=+1 : *(+i))
 template <int SIGN, typename T> PF_HD cpx<T> mul_si(cpx<T> a) {

@@ -67,7 +67,7 @@ def test_lengths_and_values_vs_reference(pf, ref, flags_name):
 def test_values_vs_direct_convolution(pf):
     x, h = inputs(20000, 131)
     y, n, bl = gpu_conv(pf, h, x, 0, 0, 1)
-    assert n == 20000 - 131 + 1 and bl == 256
+    assert n == 20000 - 131 + 1 and bl == 512     # 2*nextpow2(130)
     want = direct(x, h, n)
     assert np.max(np.abs(y - want)) <= (want.max() - want.min()) / 1e5
     # correlation flag: taps used as given (ref pffastconv.c:100-101)
@@ -123,8 +123,14 @@ def test_c4_config_sampled(pf):
     rng = np.random.default_rng(0)
     pos = np.concatenate([[0, 1, 4095, 4096, produced - 1], rng.integers(0, produced, 40)])
     hr = h[::-1].astype(np.float64)
-    lim = None
+    # The reference test's limit (max-min)/1e5 (:685) is meant for its short filters; with 4097 taps on the
+    # 0..4092 ramp the outputs sit near 1.4e6 (one float ulp = 0.125) while their range is only ~7e3, so that
+    # limit is below float resolution for ANY implementation, the reference included.  Use the north-star
+    # metric instead: |err| <= 1e-5 * max|y|  (observed: ~1e-7, i.e. 1 ulp).
+    lim = 1e-5 * float(np.abs(y).max())
+    worst = 0.0
     for p in pos:
         want = float(np.dot(x[p:p + taps].astype(np.float64), hr))
-        lim = lim or (y.max() - y.min()) / 1e5
-        assert abs(y[p] - want) <= lim, (p, y[p], want)
+        worst = max(worst, abs(float(y[p]) - want))
+    assert worst <= lim, (worst, lim)
+    assert worst <= 4 * float(np.spacing(np.float32(np.abs(y).max()))), worst   # and in fact within a few ulp
