@@ -48,6 +48,14 @@
     if (!s) return (int)cudaErrorInvalidValue;                                                                 \
     s->stream = (cudaStream_t)st; return 0;                                                                    \
   }                                                                                                            \
+  /* self-test hooks the reference's tests link against (tests/test_pffft.c:269-272; ref impl            \
+     pffft_priv_impl.h:1830,1889 validates its SIMD macros).  Here: known-answer transforms on the device. */ \
+  PFFFT_EXPORT int PF_CAT(PF_CAT(validate_, PFX), simd_ex)(FILE* dbg) {                                        \
+    return pf::engine_selftest<T, HOOKS, SETUP_T>(dbg);                                                        \
+  }                                                                                                            \
+  PFFFT_EXPORT void PF_CAT(PF_CAT(validate_, PFX), simd)(void) {                                               \
+    pf::engine_selftest<T, HOOKS, SETUP_T>(stdout);                                                            \
+  }                                                                                                            \
   PFFFT_EXPORT int PF_CAT(BPFX, setup_tables)(SETUP_T* s, void** p, size_t* n) {                               \
     if (!s || !p || !n) return (int)cudaErrorInvalidValue;                                                     \
     *p = s->d_tables; *n = s->table_bytes; return 0;                                                           \

@@ -321,6 +321,35 @@ int engine_transform(Setup<T>* s, const T* in, T* out, long long batch, int dire
   });
 }
 
+// ---------------------------------------------------------------- device self-test (validate_pffft_simd_ex)
+// known answers: delta -> all ones, constant -> N*delta, for one size per kernel family; returns #failures
+template <typename T, typename Hooks, typename S> int engine_selftest(FILE* dbg) {
+  int errs = 0;
+  const int sizes[4] = {64, 1024, 96, 32768};
+  for (int tr = 0; tr < 2; ++tr)
+    for (int si = 0; si < 4; ++si) {
+      const int N = sizes[si];
+      if (!pfplan::setup_size_ok(N, tr)) continue;
+      S* s = engine_new_setup<T, Hooks, S>(N, tr);
+      if (!s) { ++errs; if (dbg) fprintf(dbg, "selftest: no plan for N=%d\n", N); continue; }
+      const size_t per = s->per();
+      std::vector<T> x(per, T(0)), y(per, T(-1));
+      x[0] = T(1);                                               // unit impulse
+      engine_transform<T, Hooks>(s, x.data(), y.data(), 1, DIR_FORWARD, 1);
+      double worst = 0;
+      if (tr == XF_COMPLEX) { for (int k = 0; k < N; ++k) { worst = fmax(worst, fabs((double)y[2 * k] - 1)); worst = fmax(worst, fabs((double)y[2 * k + 1])); } }
+      else { worst = fmax(fabs((double)y[0] - 1), fabs((double)y[1] - 1)); for (int k = 1; k < N / 2; ++k) { worst = fmax(worst, fabs((double)y[2 * k] - 1)); worst = fmax(worst, fabs((double)y[2 * k + 1])); } }
+      engine_transform<T, Hooks>(s, y.data(), x.data(), 1, DIR_BACKWARD, 1);   // back: N * impulse
+      worst = fmax(worst, fabs((double)x[0] / N - 1));
+      for (size_t i = 1; i < per; ++i) worst = fmax(worst, fabs((double)x[i]) / N);
+      const double tol = sizeof(T) == 4 ? 1e-5 : 1e-12;
+      if (!(worst <= tol)) { ++errs; if (dbg) fprintf(dbg, "selftest FAILED: N=%d %s kernel=%s err=%g\n", N, tr ? "complex" : "real", s->kernel_name, worst); }
+      else if (dbg) fprintf(dbg, "selftest ok: N=%d %s kernel=%s err=%g\n", N, tr ? "complex" : "real", s->kernel_name, worst);
+      engine_destroy_setup<T, S>(s);
+    }
+  return errs;
+}
+
 // ---------------------------------------------------------------- zreorder / zconvolve
 template <typename T> int engine_zreorder_device(Setup<T>* s, const T* in, T* out, long long batch, int direction, cudaStream_t st) {
   const long long slots = batch * (s->transform == XF_REAL ? s->N / 2 : s->N);
