@@ -3,6 +3,7 @@
 #include "../../include/pffft/pffft_b200.h"
 #include "api_impl.cuh"
 #include "fast_kernels.cuh"
+#include "cta_kernels.cuh"
 
 namespace pf {
 
@@ -54,31 +55,107 @@ static int run_c1024(Setup<float>* s, const float* in, float* out, long long bat
   return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
 }
 
+// ---- CTA-per-transform kernels (cta_kernels.cuh): complex cores of 512 / 1024 / 2048 / 4096 points
+template <int C, int LM, int SM, int SIGN>
+static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
+  constexpr int MINB = 48 / C;                              // 768 threads/SM -> 85-register budget (64 spills)
+  auto kern = k_cta_fft<C, LM, SM, SIGN, MINB>;
+  const size_t smem = (size_t)K2<C>::NC * sizeof(cf);
+  static thread_local int per_sm = 0;
+  if (per_sm == 0) {
+    if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * C, smem);
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long ctas = p.batch;
+  const long long cap = (long long)s->sm_count * per_sm;
+  if (ctas > cap) ctas = cap;
+  const cf* tw1 = s->tw_fast;
+  const cf* tw2 = s->tw_fast + K2<C>::NC;
+  kern<<<(int)ctas, 16 * C, smem, st>>>(p, tw1, tw2);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int C>
+static int run_cta(Setup<float>* s, const XformParams<float>& p, int direction, int ordered, cudaStream_t st) {
+  const bool fwd = direction == DIR_FORWARD;
+  if (s->transform == XF_COMPLEX) {
+    if (fwd) return ordered ? launch_cta<C, L_C_ORD, S_C_ORD, -1>(s, p, st) : launch_cta<C, L_C_ORD, S_C_Z, -1>(s, p, st);
+    return ordered ? launch_cta<C, L_C_ORD, S_C_ORD, +1>(s, p, st) : launch_cta<C, L_C_Z, S_C_ORD, +1>(s, p, st);
+  }
+  if (fwd) return ordered ? launch_cta<C, L_R_TIME, S_R_ORD, -1>(s, p, st) : launch_cta<C, L_R_TIME, S_R_Z, -1>(s, p, st);
+  return ordered ? launch_cta<C, L_R_ORD, S_R_TIME, +1>(s, p, st) : launch_cta<C, L_R_Z, S_R_TIME, +1>(s, p, st);
+}
+static int cta_C_for(int Nc) { return Nc == 512 ? 2 : Nc == 1024 ? 4 : Nc == 2048 ? 8 : Nc == 4096 ? 16 : 0; }
+
 template <> struct FastHooks<float> {
-  static size_t extra_table_cpx(int N, int transform) { return (transform == XF_COMPLEX && N == 1024) ? 1024 : 0; }
-  // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
+  static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
+  static size_t extra_table_cpx(int N, int transform) {
+    if (is_warp1024(N, transform)) return 1024;
+    const int Nc = transform == XF_REAL ? N / 2 : N;
+    const int C = cta_C_for(Nc);
+    return C ? (size_t)Nc + 16 * (size_t)C : 0;
+  }
   static void fill_extra_table(int N, int transform, float* dst) {
-    if (!(transform == XF_COMPLEX && N == 1024)) return;
-    for (int k2 = 0; k2 < 32; ++k2)
-      for (int n1 = 0; n1 < 32; ++n1) {
+    if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
+      for (int k2 = 0; k2 < 32; ++k2)
+        for (int n1 = 0; n1 < 32; ++n1) {
+          long double c, sn;
+          pfplan::unit_root((long long)n1 * k2, 1024, &c, &sn);
+          dst[2 * (k2 * 32 + n1)] = (float)c; dst[2 * (k2 * 32 + n1) + 1] = (float)sn;
+        }
+      return;
+    }
+    const int Nc = transform == XF_REAL ? N / 2 : N;
+    const int C = cta_C_for(Nc);
+    if (!C) return;
+    const int BC = 16 * C;
+    for (int ka = 0; ka < 16; ++ka)                         // tw1[ka*BC + m] = exp(-2 pi i m ka / Nc)
+      for (int m = 0; m < BC; ++m) {
         long double c, sn;
-        pfplan::unit_root((long long)n1 * k2, 1024, &c, &sn);
-        dst[2 * (k2 * 32 + n1)] = (float)c; dst[2 * (k2 * 32 + n1) + 1] = (float)sn;
+        pfplan::unit_root((long long)m * ka, Nc, &c, &sn);
+        dst[2 * (ka * BC + m)] = (float)c; dst[2 * (ka * BC + m) + 1] = (float)sn;
+      }
+    float* t2 = dst + 2 * (size_t)Nc;
+    for (int kb = 0; kb < 16; ++kb)                         // tw2[kb*C + nc] = exp(-2 pi i nc kb / BC)
+      for (int nc = 0; nc < C; ++nc) {
+        long double c, sn;
+        pfplan::unit_root((long long)nc * kb, BC, &c, &sn);
+        t2[2 * (kb * C + nc)] = (float)c; t2[2 * (kb * C + nc) + 1] = (float)sn;
       }
   }
   static bool plan(Setup<float>* s) {
-    if (!(s->transform == XF_COMPLEX && s->N == 1024)) return false;
-    int v = V_LDG_4x4;
-    if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
-    s->fast_variant = v;
-    s->kernel_name = kVariantName[v];
+    if (is_warp1024(s->N, s->transform)) {
+      int v = V_LDG_4x4;
+      if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
+      s->fast_variant = v;
+      s->kernel_name = kVariantName[v];
+      return true;
+    }
+    const int C = cta_C_for(s->Nc);
+    if (!C || getenv("PFFFT_B200_NO_CTA")) return false;
+    s->fast_variant = 100 + C;
+    s->kernel_name = C == 2 ? "cta_16x16x2" : C == 4 ? "cta_16x16x4" : C == 8 ? "cta_16x16x8" : "cta_16x16x16";
     return true;
   }
-  static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st) {
-    if (direction == DIR_FORWARD) return ordered ? run_c1024<-1, false, false>(s, in, out, batch, st)
-                                                 : run_c1024<-1, false, true>(s, in, out, batch, st);
-    return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
-                   : run_c1024<+1, true, false>(s, in, out, batch, st);
+  static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
+                 const XformOpts& o) {
+    if (s->fast_variant < 100) {                            // warp-per-transform N=1024 complex: contiguous batches only
+      const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+      if (!plain) return -1;
+      if (direction == DIR_FORWARD) return ordered ? run_c1024<-1, false, false>(s, in, out, batch, st)
+                                                   : run_c1024<-1, false, true>(s, in, out, batch, st);
+      return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
+                     : run_c1024<+1, true, false>(s, in, out, batch, st);
+    }
+    const XformParams<float> p = make_params(s, in, out, batch, o);
+    switch (s->fast_variant - 100) {
+      case 2: return run_cta<2>(s, p, direction, ordered, st);
+      case 4: return run_cta<4>(s, p, direction, ordered, st);
+      case 8: return run_cta<8>(s, p, direction, ordered, st);
+      default: return run_cta<16>(s, p, direction, ordered, st);
+    }
   }
 };
 

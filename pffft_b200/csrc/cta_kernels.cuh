@@ -1,0 +1,137 @@
+// cta_kernels.cuh -- one transform per CTA for complex cores of 512..4096 points (real N up to 8192).
+//
+// Nc = 16 x 16 x C (C = 2,4,8,16), T = Nc/16 threads, every thread owns 16 points in registers.
+// Three register-FFT passes (radix 16, 16, C) over the three index digits
+//      n = n_c + C*n_b + 16*C*n_a        k = k_a + 16*k_b + 256*k_c
+//   pass 1: thread m=(n_b,n_c): FFT over n_a of x[m + 16C*n_a] (coalesced global loads), * W_Nc^{m k_a}
+//   pass 2: thread (k_a,n_c)  : FFT over n_b, * W_{16C}^{n_c k_b}           (in place in shared memory)
+//   pass 3: thread (k_a,k_b)  : FFT over n_c -> X[k_a + 16 k_b + 256 k_c]   (coalesced global stores)
+// The exchange tile is exactly Nc complex words with an XOR swizzle of the low 4 address bits by
+// rotr4(k_a, log2(16/C)); every 64-bit shared access of every pass is bank-conflict free for all C
+// (derivation in DESIGN.md section 4).  One HBM read + one HBM write per transform.
+//
+// Load/store reuse the element functions of generic_kernels.cuh, so the same kernel serves complex
+// and real transforms (N/2-point packing + rotation), canonical and z-domain layouts, and the strided /
+// zero-padded / truncated accesses of pffastconv.  Replaces, for these sizes, cfftf1/rfftf1/rfftb1 +
+// finalize/preprocess + zreorder of the reference (src/pffft_priv_impl.h:809-1048, :1195-1462, :1158-1193).
+#pragma once
+#include "butterfly.cuh"
+#include "generic_kernels.cuh"
+
+namespace pf {
+
+template <int C> struct K2 {
+  static constexpr int NC = 256 * C;          // complex core length
+  static constexpr int T = 16 * C;            // threads per transform
+  static constexpr int BC = 16 * C;           // stride of the first digit
+  static constexpr int SH = (C == 16) ? 0 : (C == 8) ? 1 : (C == 4) ? 2 : 3;   // log2(16/C)
+  PF_HD static int swz(int k_a) { return ((k_a >> SH) | (k_a << (4 - SH))) & 15; }
+  PF_HD static int idx(int k_a, int j_b, int j_c) { return k_a * (16 * C) + ((j_b * C + j_c) ^ swz(k_a)); }
+};
+
+PF_HD constexpr int brev4(int p) { return ct::bitrev(p, 4); }
+template <int C> PF_HD constexpr int brevC(int p) { return ct::bitrev(p, ct::ilog2(C)); }
+
+// direct store of output element k from a register (modes that need no partner element)
+template <int SM, typename T>
+PF_HD void store_elem(T* base, int k, cpx<T> v, int N, int out_count, bool vec_ok) {
+  if (SM == S_C_ORD) { spec_put<false, false>(base, k, N, v); return; }
+  if (SM == S_C_Z)   { spec_put<true, false>(base, k, N, v); return; }
+  // S_R_TIME: two real samples, truncated to out_count (pffastconv keeps only the valid ones)
+  const int e = 2 * k;
+  if (vec_ok && e + 1 < out_count) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
+  if (e < out_count) base[e] = v.x;
+  if (e + 1 < out_count) base[e + 1] = v.y;
+}
+
+// ---- pass 1: thread m in [0, 16C)
+template <int C, int LM, int SIGN, typename T>
+PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long avail, bool vec_ok,
+                    const cpx<T>* tw1, cpx<T>* tile) {
+  using K = K2<C>;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok);
+  reg_fft<16, SIGN>(v);
+  const int jb = m / C, jc = m % C;
+  tile[K::idx(0, jb, jc)] = v[0];
+#pragma unroll
+  for (int ka = 1; ka < 16; ++ka) tile[K::idx(ka, jb, jc)] = cmul_dir<SIGN>(v[ka], tw1[ka * K::BC + m]);
+}
+// ---- pass 2: thread t -> (k_a = t / C, n_c = t % C), in place
+template <int C, int SIGN, typename T>
+PF_HD void k2_pass2(int t, const cpx<T>* tw2, cpx<T>* tile) {
+  using K = K2<C>;
+  const int ka = t / C, nc = t % C;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = tile[K::idx(ka, brev4(p), nc)];
+  reg_fft<16, SIGN>(v);
+  tile[K::idx(ka, 0, nc)] = v[0];
+#pragma unroll
+  for (int kb = 1; kb < 16; ++kb) tile[K::idx(ka, kb, nc)] = cmul_dir<SIGN>(v[kb], tw2[kb * C + nc]);
+}
+// ---- pass 3: thread t -> k_a = t % 16, k_b = t / 16 + C*r (r < 16/C); u[r*C + k_c] = X[k_a + 16 k_b + 256 k_c]
+template <int C, int SIGN, typename T>
+PF_HD void k2_pass3(int t, const cpx<T>* tile, cpx<T> (&u)[16]) {
+  using K = K2<C>;
+  const int ka = t & 15, kb0 = t >> 4;
+#pragma unroll
+  for (int r = 0; r < 16 / C; ++r) {
+#pragma unroll
+    for (int p = 0; p < C; ++p) u[r * C + p] = tile[K::idx(ka, kb0 + C * r, brevC<C>(p))];
+  }
+  if (C == 16) dit_fft<16, SIGN, 0, 1>(u);
+  if (C == 8) { dit_fft<8, SIGN, 0, 1>(u); dit_fft<8, SIGN, 8, 1>(u); }
+  if (C == 4) { dit_fft<4, SIGN, 0, 1>(u); dit_fft<4, SIGN, 4, 1>(u); dit_fft<4, SIGN, 8, 1>(u); dit_fft<4, SIGN, 12, 1>(u); }
+  if (C == 2) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { const cpx<T> a = u[2 * r], b = u[2 * r + 1]; u[2 * r] = a + b; u[2 * r + 1] = a - b; }
+  }
+}
+// natural index of u[r*C + kc] held by thread t after pass 3
+template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) + 16 * ((t >> 4) + C * r) + 256 * kc; }
+
+#ifdef __CUDACC__
+// One CTA = one transform at a time, persistent over the batch.  blockDim.x == 16*C.
+template <int C, int LM, int SM, int SIGN, int MINB>
+__global__ void __launch_bounds__(16 * C, MINB)
+k_cta_fft(const XformParams<float> p, const cpx<float>* __restrict__ tw1, const cpx<float>* __restrict__ tw2) {
+  using K = K2<C>;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<float>* tile = reinterpret_cast<cpx<float>*>(pf_smem_raw);
+  const int t = threadIdx.x;
+  constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);   // forward real: X[k] needs Z[k] and Z[Nc-k]
+  for (long long tr = blockIdx.x; tr < p.batch; tr += gridDim.x) {
+    const float* ibase = p.in + tr * p.in_stride;
+    float* obase = p.out + tr * p.out_stride;
+    const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
+    k2_pass1<C, LM, SIGN, float>(t, ibase, p.N, p.twr, avail, vec_aligned<float>(ibase), tw1, tile);
+    __syncthreads();
+    k2_pass2<C, SIGN, float>(t, tw2, tile);
+    __syncthreads();
+    cpx<float> u[16];
+    k2_pass3<C, SIGN, float>(t, tile, u);
+    if (!kNeedsPartner) {
+      const bool vok = vec_aligned<float>(obase);
+#pragma unroll
+      for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+        for (int kc = 0; kc < C; ++kc) store_elem<SM, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
+      __syncthreads();                          // tile is rewritten by the next transform's pass 1
+    } else {
+      __syncthreads();                          // everyone has read the tile: reuse it as the natural-order buffer
+#pragma unroll
+      for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+        for (int kc = 0; kc < C; ++kc) tile[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) store_core<SM, float>(obase, tile, t + K::T * j, p.N, K::NC, p.twr, p.out_count, true);
+      __syncthreads();
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace pf

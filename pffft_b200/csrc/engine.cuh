@@ -78,10 +78,12 @@ template <typename T> struct Setup {
   size_t per() const { return transform == XF_REAL ? (size_t)N : 2 * (size_t)N; }   // elements per transform
 };
 
+template <typename T> XformParams<T> make_params(Setup<T>* s, const T* in, T* out, long long batch, const XformOpts& o);
+
 template <typename T> struct FastHooks {
   // implemented by api_float.cu for the sizes that have tuned kernels; default: none
   static bool plan(Setup<T>*) { return false; }
-  static int run(Setup<T>*, const T*, T*, long long, int, int, cudaStream_t) { return -1; }
+  static int run(Setup<T>*, const T*, T*, long long, int, int, cudaStream_t, const XformOpts&) { return -1; }
   static size_t extra_table_cpx(int /*N*/, int /*transform*/) { return 0; }
   static void fill_extra_table(int, int, T*) {}
 };
@@ -251,10 +253,9 @@ template <typename T, typename Hooks>
 int engine_transform_device(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered,
                             cudaStream_t st, const XformOpts& o = XformOpts()) {
   if (batch <= 0) return 0;
-  const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
-  if (s->kind == KK_FAST && plain) {
-    const int rc = Hooks::run(s, in, out, batch, direction, ordered, st);
-    if (rc >= 0) return rc;                       // -1: this (direction, layout) has no tuned kernel -> generic
+  if (s->kind == KK_FAST) {
+    const int rc = Hooks::run(s, in, out, batch, direction, ordered, st, o);
+    if (rc >= 0) return rc;                       // -1: this (direction, layout, options) has no tuned kernel -> generic
   }
   const XformParams<T> p = make_params(s, in, out, batch, o);
   const bool fwd = direction == DIR_FORWARD;

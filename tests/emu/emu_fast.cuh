@@ -31,3 +31,83 @@ extern "C" int emu_w1024(int dir, const float* in, float* out, long long batch) 
   if (dir == 0) emu_w1024_run<-1>(in, out, batch); else emu_w1024_run<+1>(in, out, batch);
   return 0;
 }
+
+// ---- CTA kernel (cta_kernels.cuh): phases stepped thread by thread
+#include "../../pffft_b200/csrc/cta_kernels.cuh"
+template <int C, int LM, int SM, int SIGN>
+static void emu_k2_run(const float* in, float* out, int N, long long in_limit, int out_count) {
+  using namespace pf;
+  using K = K2<C>;
+  const int Nc = K::NC;
+  std::vector<float> tw1(2 * (size_t)Nc), tw2(2 * 16 * C), twr(2 * (size_t)(N / 2 > 0 ? N / 2 : 1));
+  for (int ka = 0; ka < 16; ++ka) for (int m = 0; m < K::BC; ++m) {
+    long double c, s; pfplan::unit_root((long long)m * ka, Nc, &c, &s);
+    tw1[2 * (ka * K::BC + m)] = (float)c; tw1[2 * (ka * K::BC + m) + 1] = (float)s;
+  }
+  for (int kb = 0; kb < 16; ++kb) for (int nc = 0; nc < C; ++nc) {
+    long double c, s; pfplan::unit_root((long long)nc * kb, K::BC, &c, &s);
+    tw2[2 * (kb * C + nc)] = (float)c; tw2[2 * (kb * C + nc) + 1] = (float)s;
+  }
+  pfplan::fill_roots<float>(twr.data(), N / 2, N);
+  const cf* ptw1 = reinterpret_cast<const cf*>(tw1.data());
+  const cf* ptw2 = reinterpret_cast<const cf*>(tw2.data());
+  const cf* ptwr = reinterpret_cast<const cf*>(twr.data());
+  std::vector<cf> tile(Nc), nat(Nc);
+  for (int t = 0; t < K::T; ++t) k2_pass1<C, LM, SIGN, float>(t, in, N, ptwr, in_limit, vec_aligned<float>(in), ptw1, tile.data());
+  for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, ptw2, tile.data());
+  constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  for (int t = 0; t < K::T; ++t) {
+    cf u[16];
+    k2_pass3<C, SIGN, float>(t, tile.data(), u);
+    for (int r = 0; r < 16 / C; ++r) for (int kc = 0; kc < C; ++kc) {
+      const int k = k2_out_index<C>(t, r, kc);
+      if (partner) nat[k] = u[r * C + kc];
+      else store_elem<SM, float>(out, k, u[r * C + kc], N, out_count, vec_aligned<float>(out));
+    }
+  }
+  if (partner)
+    for (int t = 0; t < K::T; ++t) for (int j = 0; j < 16; ++j)
+      store_core<SM, float>(out, nat.data(), t + K::T * j, N, Nc, ptwr, out_count, true);
+}
+template <int C>
+static int emu_k2_c(int N, int lm, int sm, int dir, const float* in, float* out, long long in_limit, int out_count) {
+  using namespace pf;
+#define K2CASE(L, S, SG) if (lm == L && sm == S && dir == (SG > 0 ? 1 : 0)) { emu_k2_run<C, L, S, SG>(in, out, N, in_limit, out_count); return 0; }
+  K2CASE(L_C_ORD, S_C_ORD, -1) K2CASE(L_C_ORD, S_C_Z, -1) K2CASE(L_C_ORD, S_C_ORD, +1) K2CASE(L_C_Z, S_C_ORD, +1)
+  K2CASE(L_R_TIME, S_R_ORD, -1) K2CASE(L_R_TIME, S_R_Z, -1) K2CASE(L_R_ORD, S_R_TIME, +1) K2CASE(L_R_Z, S_R_TIME, +1)
+#undef K2CASE
+  return -2;
+}
+// Nc = complex core length (512..4096), N = API length (Nc complex, 2*Nc real)
+extern "C" int emu_k2(int Nc, int N, int lm, int sm, int dir, const float* in, float* out, long long in_limit, int out_count) {
+  switch (Nc) {
+    case 512: return emu_k2_c<2>(N, lm, sm, dir, in, out, in_limit, out_count);
+    case 1024: return emu_k2_c<4>(N, lm, sm, dir, in, out, in_limit, out_count);
+    case 2048: return emu_k2_c<8>(N, lm, sm, dir, in, out, in_limit, out_count);
+    case 4096: return emu_k2_c<16>(N, lm, sm, dir, in, out, in_limit, out_count);
+  }
+  return -1;
+}
+// bank-conflict audit of the swizzled tile: worst number of distinct-address hits per bank-pair over all
+// half-warps of the three passes (1 = conflict free)
+template <int C> static int emu_k2_conflicts_c() {
+  using K = pf::K2<C>;
+  int worst = 1;
+  auto audit = [&](auto addr_of_thread, int nthreads) {
+    for (int h = 0; h < nthreads; h += 16) {
+      int cnt[16] = {0};
+      for (int l = 0; l < 16 && h + l < nthreads; ++l) cnt[addr_of_thread(h + l) & 15]++;
+      for (int b = 0; b < 16; ++b) if (cnt[b] > worst) worst = cnt[b];
+    }
+  };
+  for (int ka = 0; ka < 16; ++ka) audit([&](int m) { return K::idx(ka, m / C, m % C); }, K::T);                 // pass 1 writes
+  for (int jb = 0; jb < 16; ++jb) audit([&](int t) { return K::idx(t / C, jb, t % C); }, K::T);                  // pass 2 r/w
+  for (int r = 0; r < 16 / C; ++r) for (int jc = 0; jc < C; ++jc)
+    audit([&](int t) { return K::idx(t & 15, (t >> 4) + C * r, jc); }, K::T);                                    // pass 3 reads
+  return worst;
+}
+extern "C" int emu_k2_conflicts(int C) {
+  switch (C) { case 2: return emu_k2_conflicts_c<2>(); case 4: return emu_k2_conflicts_c<4>();
+               case 8: return emu_k2_conflicts_c<8>(); case 16: return emu_k2_conflicts_c<16>(); }
+  return -1;
+}
