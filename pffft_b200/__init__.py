@@ -248,11 +248,15 @@ class Setup:
         self.per = self.N if transform == PFFFT_REAL else 2 * self.N
 
     def close(self):
-        if self.handle:
-            pffft_destroy_setup(self.handle, self.dtype)
+        if getattr(self, "handle", None):
+            try:
+                pffft_destroy_setup(self.handle, self.dtype)
+            except Exception:              # interpreter shutdown: module globals may already be gone
+                pass
             self.handle = None
 
-    __del__ = close
+    def __del__(self):
+        self.close()
 
     def __enter__(self):
         return self
@@ -307,10 +311,14 @@ class FastConv:
 
     def close(self):
         if getattr(self, "handle", None):
-            lib.pffastconv_destroy_setup(self.handle)
+            try:
+                lib.pffastconv_destroy_setup(self.handle)
+            except Exception:
+                pass
             self.handle = None
 
-    __del__ = close
+    def __del__(self):
+        self.close()
 
     def apply(self, x, y, length, flush):
         """x, y: numpy arrays or torch CUDA tensors; length in (complex) samples; returns samples produced"""

@@ -55,10 +55,13 @@ static int run_c1024(Setup<float>* s, const float* in, float* out, long long bat
   return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
 }
 
+#ifndef PF_CTA_TPSM
+#define PF_CTA_TPSM 1024
+#endif
 // ---- CTA-per-transform kernels (cta_kernels.cuh): complex cores of 512 / 1024 / 2048 / 4096 points
 template <int C, int LM, int SM, int SIGN>
 static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
-  constexpr int MINB = 48 / C;                              // 768 threads/SM -> 85-register budget (64 spills)
+  constexpr int MINB = PF_CTA_TPSM / (16 * C);              // threads per SM the register budget is sized for
   auto kern = k_cta_fft<C, LM, SM, SIGN, MINB>;
   const size_t smem = (size_t)K2<C>::NC * sizeof(cf);
   static thread_local int per_sm = 0;
@@ -171,6 +174,18 @@ namespace pf {
 int float_transform_device(PFFFT_Setup* s, const float* in, float* out, long long batch, int direction, int ordered,
                            cudaStream_t st, const XformOpts& o) {
   return engine_transform_device<float, FastHooks<float>>(s, in, out, batch, direction, ordered, st, o);
+}
+FloatPlanTables float_plan_tables(PFFFT_Setup* s) {
+  FloatPlanTables t{0, s->sm_count, nullptr, nullptr, s->twr};
+  if (s->kind == KK_FAST && s->fast_variant >= 100) {
+    t.C = s->fast_variant - 100;
+    t.tw1 = s->tw_fast;
+    t.tw2 = s->tw_fast + s->Nc;
+  }
+  return t;
+}
+int float_zreorder_device(PFFFT_Setup* s, const float* in, float* out, long long batch, int direction, cudaStream_t st) {
+  return engine_zreorder_device<float>(s, in, out, batch, direction, st);
 }
 int float_zconvolve_device(PFFFT_Setup* s, const float* a, const float* b, float* ab, float scaling, long long batch,
                            int b_shared, int accumulate, cudaStream_t st) {

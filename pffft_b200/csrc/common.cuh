@@ -23,6 +23,7 @@ template <typename T> PF_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return mk<T>(
 template <typename T> PF_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
 template <typename T> PF_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
 template <typename T> PF_HD cpx<T> scale(cpx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+template <typename T> PF_HD cpx<T> scale2(cpx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }   // same, for scopes where `scale` is a variable
 // a * b (contraction to FMA allowed: 2 mul + 2 fma)
 template <typename T> PF_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
   return mk<T>(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));

@@ -30,6 +30,16 @@ template <int C> struct K2 {
 };
 
 PF_HD constexpr int brev4(int p) { return ct::bitrev(p, 4); }
+
+// table read through the read-only path (ld.global.nc) on the device
+template <typename T> PF_HD cpx<T> ldtab(const cpx<T>* p) {
+#ifdef __CUDA_ARCH__
+  if constexpr (sizeof(T) == 4) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
+  else { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
+#else
+  return *p;
+#endif
+}
 template <int C> PF_HD constexpr int brevC(int p) { return ct::bitrev(p, ct::ilog2(C)); }
 
 // direct store of output element k from a register (modes that need no partner element)
@@ -45,18 +55,24 @@ PF_HD void store_elem(T* base, int k, cpx<T> v, int N, int out_count, bool vec_o
 }
 
 // ---- pass 1: thread m in [0, 16C)
-template <int C, int LM, int SIGN, typename T>
+template <int C, int LM, int SIGN, bool FAST, typename T>
 PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long avail, bool vec_ok,
                     const cpx<T>* tw1, cpx<T>* tile) {
   using K = K2<C>;
   cpx<T> v[16];
+  if (FAST && (LM == L_R_TIME || LM == L_C_ORD)) {      // contiguous, aligned, fully in range: plain 64-bit loads
+    const cpx<T>* src = reinterpret_cast<const cpx<T>*>(base) + m;
 #pragma unroll
-  for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok);
+    for (int p = 0; p < 16; ++p) v[p] = src[K::BC * brev4(p)];
+  } else {
+#pragma unroll
+    for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok);
+  }
   reg_fft<16, SIGN>(v);
   const int jb = m / C, jc = m % C;
   tile[K::idx(0, jb, jc)] = v[0];
 #pragma unroll
-  for (int ka = 1; ka < 16; ++ka) tile[K::idx(ka, jb, jc)] = cmul_dir<SIGN>(v[ka], tw1[ka * K::BC + m]);
+  for (int ka = 1; ka < 16; ++ka) tile[K::idx(ka, jb, jc)] = cmul_dir<SIGN>(v[ka], ldtab(tw1 + ka * K::BC + m));
 }
 // ---- pass 2: thread t -> (k_a = t / C, n_c = t % C), in place
 template <int C, int SIGN, typename T>
@@ -69,7 +85,7 @@ PF_HD void k2_pass2(int t, const cpx<T>* tw2, cpx<T>* tile) {
   reg_fft<16, SIGN>(v);
   tile[K::idx(ka, 0, nc)] = v[0];
 #pragma unroll
-  for (int kb = 1; kb < 16; ++kb) tile[K::idx(ka, kb, nc)] = cmul_dir<SIGN>(v[kb], tw2[kb * C + nc]);
+  for (int kb = 1; kb < 16; ++kb) tile[K::idx(ka, kb, nc)] = cmul_dir<SIGN>(v[kb], ldtab(tw2 + kb * C + nc));
 }
 // ---- pass 3: thread t -> k_a = t % 16, k_b = t / 16 + C*r (r < 16/C); u[r*C + k_c] = X[k_a + 16 k_b + 256 k_c]
 template <int C, int SIGN, typename T>
@@ -89,6 +105,25 @@ PF_HD void k2_pass3(int t, const cpx<T>* tile, cpx<T> (&u)[16]) {
     for (int r = 0; r < 8; ++r) { const cpx<T> a = u[2 * r], b = u[2 * r + 1]; u[2 * r] = a + b; u[2 * r + 1] = a - b; }
   }
 }
+// forward-real epilogue on PAIRS: X[k] and X[Nc-k] share s = Z[k] + conj Z[Nc-k] and u = W^k (Z[k] - conj Z[Nc-k])
+//   X[k] = ((s.x + u.y), (s.y - u.x))/2      X[Nc-k] = ((s.x - u.y), (-s.y - u.x))/2
+// k = 0 also emits the self-paired middle bin: slot 0 = (Z0.x + Z0.y, Z0.x - Z0.y), X[Nc/2] = conj Z[Nc/2].
+template <int SM, typename T>
+PF_HD void real_post_pair(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<T>* twr) {
+  constexpr bool Z = (SM == S_R_Z);
+  if (k == 0) {
+    const cpx<T> z0 = z[0], zm = z[Nc / 2];
+    spec_put<Z, true>(base, 0, N, mk<T>(z0.x + z0.y, z0.x - z0.y));
+    spec_put<Z, true>(base, Nc / 2, N, mk<T>(zm.x, -zm.y));
+    return;
+  }
+  const cpx<T> a = z[k], b = conj(z[Nc - k]);
+  const cpx<T> s = a + b, d = a - b;
+  const cpx<T> u = cmul(d, ldtab(twr + k));
+  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+  spec_put<Z, true>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+}
+
 // natural index of u[r*C + kc] held by thread t after pass 3
 template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) + 16 * ((t >> 4) + C * r) + 256 * kc; }
 
@@ -96,17 +131,25 @@ template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) 
 // One CTA = one transform at a time, persistent over the batch.  blockDim.x == 16*C.
 template <int C, int LM, int SM, int SIGN, int MINB>
 __global__ void __launch_bounds__(16 * C, MINB)
-k_cta_fft(const XformParams<float> p, const cpx<float>* __restrict__ tw1, const cpx<float>* __restrict__ tw2) {
+k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* tw2) {
   using K = K2<C>;
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<float>* tile = reinterpret_cast<cpx<float>*>(pf_smem_raw);
   const int t = threadIdx.x;
   constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);   // forward real: X[k] needs Z[k] and Z[Nc-k]
   for (long long tr = blockIdx.x; tr < p.batch; tr += gridDim.x) {
+    // keep the twiddle loads inside the loop: hoisted, the 30 per-thread twiddles are loop invariants the
+    // compiler spills to local memory (measured: +2 GB of L2 traffic per 4 GB launch); re-read from L1 instead
+    const cpx<float>* twr = p.twr;
+    asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twr));
     const float* ibase = p.in + tr * p.in_stride;
     float* obase = p.out + tr * p.out_stride;
     const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
-    k2_pass1<C, LM, SIGN, float>(t, ibase, p.N, p.twr, avail, vec_aligned<float>(ibase), tw1, tile);
+    const bool vin = vec_aligned<float>(ibase);
+    if (vin && (avail < 0 || avail >= (long long)(2 * K::NC)))
+      k2_pass1<C, LM, SIGN, true, float>(t, ibase, p.N, twr, avail, true, tw1, tile);
+    else
+      k2_pass1<C, LM, SIGN, false, float>(t, ibase, p.N, twr, avail, vin, tw1, tile);
     __syncthreads();
     k2_pass2<C, SIGN, float>(t, tw2, tile);
     __syncthreads();
@@ -114,10 +157,18 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* __restrict__ tw1, const 
     k2_pass3<C, SIGN, float>(t, tile, u);
     if (!kNeedsPartner) {
       const bool vok = vec_aligned<float>(obase);
+      if (SM == S_C_ORD || (SM == S_R_TIME && vok && p.out_count >= 2 * K::NC)) {   // whole transform stored: no per-element checks
+        cpx<float>* dst = reinterpret_cast<cpx<float>*>(obase);
 #pragma unroll
-      for (int r = 0; r < 16 / C; ++r)
+        for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
-        for (int kc = 0; kc < C; ++kc) store_elem<SM, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
+          for (int kc = 0; kc < C; ++kc) dst[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+          for (int kc = 0; kc < C; ++kc) store_elem<SM, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
+      }
       __syncthreads();                          // tile is rewritten by the next transform's pass 1
     } else {
       __syncthreads();                          // everyone has read the tile: reuse it as the natural-order buffer
@@ -126,8 +177,8 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* __restrict__ tw1, const 
 #pragma unroll
         for (int kc = 0; kc < C; ++kc) tile[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
       __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) store_core<SM, float>(obase, tile, t + K::T * j, p.N, K::NC, p.twr, p.out_count, true);
+#pragma unroll 4
+      for (int j = 0; j < 8; ++j) real_post_pair<SM, float>(obase, tile, t + K::T * j, p.N, K::NC, twr);   // k in [0, Nc/2)
       __syncthreads();
     }
   }

@@ -10,8 +10,10 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/pffft/pffft_b200.h"
 #include "internal_api.h"
+#include "fastconv_kernels.cuh"
 
 using pf::XformOpts;
 
@@ -24,6 +26,9 @@ struct PFFASTCONV_Setup {
   int device = 0;
   cudaStream_t stream = nullptr; // device-pointer calls
   float* d_Hf = nullptr;         // z-domain spectrum of the arranged filter
+  float* d_Hc = nullptr;         // the same spectrum in canonical order (fused kernel)
+  pf::FloatPlanTables tabs{0, 0, nullptr, nullptr, nullptr};
+  int fused_ctas_per_sm = 0;
   // scratch, grown on demand (a PFFASTCONV_Setup is single-threaded by contract, pffastconv.h:77-81)
   float* d_spec = nullptr; size_t spec_elems = 0;
   float* d_x = nullptr;    size_t x_elems = 0;     // host input staging / planar split
@@ -68,9 +73,48 @@ __global__ void k_merge_u(const float* __restrict__ re, const float* __restrict_
 using pfplan::BlockPlan;
 using pfplan::plan_blocks;
 
+// fused path: one launch for every block of the stream (Nfft = 512*C, C in {2,4,8,16})
+template <int C>
+int launch_fused(PFFASTCONV_Setup* s, const float* x, long long inputLen, float* y, const BlockPlan& bp, cudaStream_t st) {
+  constexpr int MINB = (C == 16) ? 3 : 1024 / (16 * C);
+  auto kern = pf::k_fastconv_fused<C, MINB>;
+  const size_t smem = 2 * (size_t)pf::K2<C>::NC * sizeof(pf::cf);
+  if (s->fused_ctas_per_sm == 0) {
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      pf::set_error("pffastconv: cudaFuncSetAttribute", cudaGetLastError()); return -1;
+    }
+    int per = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, 16 * C, smem);
+    s->fused_ctas_per_sm = per < 1 ? 1 : per;
+  }
+  pf::FastconvParams p;
+  p.x = x; p.y = y; p.input_len = inputLen; p.n_full = bp.n_full; p.stride = bp.stride;
+  p.tail_out = bp.tail_off >= 0 ? bp.tail_out : 0;
+  p.scale = s->scale; p.twr = s->tabs.twr; p.Hc = reinterpret_cast<const pf::cf*>(s->d_Hc);
+  p.tw1 = s->tabs.tw1; p.tw2 = s->tabs.tw2;
+  long long nblk = bp.n_full + (p.tail_out > 0 ? 1 : 0);
+  long long ctas = nblk;
+  const long long cap = (long long)s->tabs.sm_count * s->fused_ctas_per_sm;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) return 0;
+  kern<<<(int)ctas, 16 * C, smem, st>>>(p);
+  pf::count_launch();
+  if (cudaGetLastError() != cudaSuccess) { pf::set_error("pffastconv: fused launch", cudaGetLastError()); return -1; }
+  return 0;
+}
+
 // one real stream already on the device: x[0..inputLen) -> y[0..produced)
 int conv_stream(PFFASTCONV_Setup* s, const float* x, long long inputLen, float* y, const BlockPlan& bp, cudaStream_t st) {
   const int Nfft = s->Nfft;
+  if (s->d_Hc && s->tabs.C) {
+    // the tail block follows the full ones at the same stride, so one grid covers both
+    switch (s->tabs.C) {
+      case 2: return launch_fused<2>(s, x, inputLen, y, bp, st);
+      case 4: return launch_fused<4>(s, x, inputLen, y, bp, st);
+      case 8: return launch_fused<8>(s, x, inputLen, y, bp, st);
+      case 16: return launch_fused<16>(s, x, inputLen, y, bp, st);
+    }
+  }
   const long long max_blocks = (long long)((size_t)(256u << 20) / ((size_t)Nfft * sizeof(float)));   // <= 256 MiB of spectra in flight
   const long long chunk = max_blocks < 1 ? 1 : max_blocks;
   auto run = [&](long long first_off, long long nblk, int out_count) -> int {
@@ -132,6 +176,13 @@ PFFASTCONV_EXPORT PFFASTCONV_Setup* pffastconv_new_setup(const float* filterCoef
     ok = pf::float_transform_device(s->st, d_tmp, s->d_Hf, 1, pf::DIR_FORWARD, 0, nullptr, XformOpts()) == 0;   // ref :108
     ok = ok && cudaStreamSynchronize(nullptr) == cudaSuccess;
   }
+  // canonical copy of the spectrum for the fused single-kernel path
+  s->tabs = pf::float_plan_tables(s->st);
+  if (ok && s->tabs.C && getenv("PFFFT_B200_NO_FUSED_CONV") == nullptr) {
+    ok = cudaMalloc((void**)&s->d_Hc, (size_t)Nfft * sizeof(float)) == cudaSuccess &&
+         pf::float_zreorder_device(s->st, s->d_Hf, s->d_Hc, 1, pf::DIR_FORWARD, nullptr) == 0 &&
+         cudaStreamSynchronize(nullptr) == cudaSuccess;
+  }
   if (d_tmp) cudaFree(d_tmp);
   if (!ok) { pf::set_error("pffastconv_new_setup", cudaGetLastError()); pffastconv_destroy_setup(s); return nullptr; }
   return s;
@@ -141,6 +192,7 @@ PFFASTCONV_EXPORT void pffastconv_destroy_setup(PFFASTCONV_Setup* s) {
   if (!s) return;
   cudaDeviceSynchronize();
   if (s->d_Hf) cudaFree(s->d_Hf);
+  if (s->d_Hc) cudaFree(s->d_Hc);
   if (s->d_spec) cudaFree(s->d_spec);
   if (s->d_x) cudaFree(s->d_x);
   if (s->d_y) cudaFree(s->d_y);

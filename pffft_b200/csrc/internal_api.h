@@ -11,4 +11,8 @@ int float_transform_device(PFFFT_Setup* s, const float* in, float* out, long lon
                            cudaStream_t st, const XformOpts& o);
 int float_zconvolve_device(PFFFT_Setup* s, const float* a, const float* b, float* ab, float scaling, long long batch,
                            int b_shared, int accumulate, cudaStream_t st);
+// tables of a float plan that runs on the 16x16xC CTA kernels (C = 0 when it does not)
+struct FloatPlanTables { int C; int sm_count; const cpx<float>* tw1; const cpx<float>* tw2; const cpx<float>* twr; };
+FloatPlanTables float_plan_tables(PFFFT_Setup* s);
+int float_zreorder_device(PFFFT_Setup* s, const float* in, float* out, long long batch, int direction, cudaStream_t st);
 }  // namespace pf

@@ -53,7 +53,7 @@ static void emu_k2_run(const float* in, float* out, int N, long long in_limit, i
   const cf* ptw2 = reinterpret_cast<const cf*>(tw2.data());
   const cf* ptwr = reinterpret_cast<const cf*>(twr.data());
   std::vector<cf> tile(Nc), nat(Nc);
-  for (int t = 0; t < K::T; ++t) k2_pass1<C, LM, SIGN, float>(t, in, N, ptwr, in_limit, vec_aligned<float>(in), ptw1, tile.data());
+  for (int t = 0; t < K::T; ++t) k2_pass1<C, LM, SIGN, false, float>(t, in, N, ptwr, in_limit, vec_aligned<float>(in), ptw1, tile.data());
   for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, ptw2, tile.data());
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
   for (int t = 0; t < K::T; ++t) {
@@ -66,8 +66,8 @@ static void emu_k2_run(const float* in, float* out, int N, long long in_limit, i
     }
   }
   if (partner)
-    for (int t = 0; t < K::T; ++t) for (int j = 0; j < 16; ++j)
-      store_core<SM, float>(out, nat.data(), t + K::T * j, N, Nc, ptwr, out_count, true);
+    for (int t = 0; t < K::T; ++t) for (int j = 0; j < 8; ++j)
+      real_post_pair<SM, float>(out, nat.data(), t + K::T * j, N, Nc, ptwr);
 }
 template <int C>
 static int emu_k2_c(int N, int lm, int sm, int dir, const float* in, float* out, long long in_limit, int out_count) {
@@ -109,5 +109,61 @@ template <int C> static int emu_k2_conflicts_c() {
 extern "C" int emu_k2_conflicts(int C) {
   switch (C) { case 2: return emu_k2_conflicts_c<2>(); case 4: return emu_k2_conflicts_c<4>();
                case 8: return emu_k2_conflicts_c<8>(); case 16: return emu_k2_conflicts_c<16>(); }
+  return -1;
+}
+
+// ---- fused overlap-save kernel (fastconv_kernels.cuh), stepped block by block
+#include "../../pffft_b200/csrc/fastconv_kernels.cuh"
+template <int C>
+static long long emu_fastconv_c(const float* x, long long len, const float* h, int taps, int flush, float* y) {
+  using namespace pf;
+  using K = K2<C>;
+  const int Nc = K::NC, Nfft = 2 * Nc;
+  std::vector<float> tw1(2 * (size_t)Nc), tw2(2 * 16 * C), twr(2 * (size_t)Nc);
+  for (int ka = 0; ka < 16; ++ka) for (int m = 0; m < K::BC; ++m) {
+    long double c, s; pfplan::unit_root((long long)m * ka, Nc, &c, &s);
+    tw1[2 * (ka * K::BC + m)] = (float)c; tw1[2 * (ka * K::BC + m) + 1] = (float)s;
+  }
+  for (int kb = 0; kb < 16; ++kb) for (int nc = 0; nc < C; ++nc) {
+    long double c, s; pfplan::unit_root((long long)nc * kb, K::BC, &c, &s);
+    tw2[2 * (kb * C + nc)] = (float)c; tw2[2 * (kb * C + nc) + 1] = (float)s;
+  }
+  pfplan::fill_roots<float>(twr.data(), Nc, Nfft);
+  const cf* ptw1 = reinterpret_cast<const cf*>(tw1.data());
+  const cf* ptw2 = reinterpret_cast<const cf*>(tw2.data());
+  const cf* ptwr = reinterpret_cast<const cf*>(twr.data());
+  // filter spectrum, canonical layout (time-reversed taps placed circularly, ref pffastconv.c:99-106)
+  std::vector<float> ht(Nfft, 0.f), Hc(Nfft, 0.f);
+  for (int i = 0; i < taps; ++i) ht[(Nfft - i) & (Nfft - 1)] = h[taps - 1 - i];
+  emu_k2_run<C, L_R_TIME, S_R_ORD, -1>(ht.data(), Hc.data(), Nfft, -1, Nfft);
+  const pfplan::BlockPlan bp = pfplan::plan_blocks(len, Nfft, taps, flush, false);
+  const long long nblk = bp.n_full + (bp.tail_off >= 0 ? 1 : 0);
+  std::vector<cf> tile(Nc), nat(Nc);
+  const float scale = (float)(1.0 / Nfft);
+  for (long long b = 0; b < nblk; ++b) {
+    const long long off = b * bp.stride;
+    const int out_count = b < bp.n_full ? bp.stride : bp.tail_out;
+    const float* ibase = x + off; float* obase = y + off;
+    for (int t = 0; t < K::T; ++t) k2_pass1<C, L_R_TIME, -1, false, float>(t, ibase, Nfft, ptwr, len - off, vec_aligned<float>(ibase), ptw1, tile.data());
+    for (int t = 0; t < K::T; ++t) k2_pass2<C, -1, float>(t, ptw2, tile.data());
+    for (int t = 0; t < K::T; ++t) { cf u[16]; k2_pass3<C, -1, float>(t, tile.data(), u);
+      for (int r = 0; r < 16 / C; ++r) for (int kc = 0; kc < C; ++kc) nat[k2_out_index<C>(t, r, kc)] = u[r * C + kc]; }
+    for (int t = 0; t < K::T; ++t) for (int j = 0; j < 8; ++j)
+      fastconv_pair<float>(nat.data(), t + K::T * j, Nc, ptwr, reinterpret_cast<const cf*>(Hc.data()), scale);
+    for (int t = 0; t < K::T; ++t) k2_pass1_smem<C, +1, float>(t, nat.data(), ptw1, tile.data());
+    for (int t = 0; t < K::T; ++t) k2_pass2<C, +1, float>(t, ptw2, tile.data());
+    for (int t = 0; t < K::T; ++t) { cf u[16]; k2_pass3<C, +1, float>(t, tile.data(), u);
+      for (int r = 0; r < 16 / C; ++r) for (int kc = 0; kc < C; ++kc)
+        store_elem<S_R_TIME, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], Nfft, out_count, vec_aligned<float>(obase)); }
+  }
+  return bp.produced;
+}
+extern "C" long long emu_fastconv(int Nfft, const float* x, long long len, const float* h, int taps, int flush, float* y) {
+  switch (Nfft) {
+    case 1024: return emu_fastconv_c<2>(x, len, h, taps, flush, y);
+    case 2048: return emu_fastconv_c<4>(x, len, h, taps, flush, y);
+    case 4096: return emu_fastconv_c<8>(x, len, h, taps, flush, y);
+    case 8192: return emu_fastconv_c<16>(x, len, h, taps, flush, y);
+  }
   return -1;
 }

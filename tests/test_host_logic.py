@@ -107,3 +107,29 @@ def test_overlap_save_block_algebra_matches_reference_lengths(emu, ref):
                         flen = 2 * taps - 1 if cf == 2 else taps
                         got = emu.emu_fastconv_produced(cf * length, nfft, flen, flush, 1 if cf == 2 else 0) // cf
                         assert got == n_ref, (taps, flags, bl, length, flush, got, n_ref)
+
+
+def test_cta_kernel_phases_and_swizzle(emu, ref, R):
+    """cta_kernels.cuh stepped on the CPU: all four sizes, complex and real (N/2 packing + pair rotation),
+    canonical and z-domain; and the XOR-swizzled exchange tile audited bank-conflict free for every pass."""
+    emu.emu_k2.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
+    for c in (2, 4, 8, 16):
+        assert emu.emu_k2_conflicts(c) == 1
+    rng = np.random.default_rng(0)
+
+    def run(Nc, N, lm, sm, d, x):
+        x = np.ascontiguousarray(x); o = np.zeros_like(x)
+        assert emu.emu_k2(Nc, N, lm, sm, d, x.ctypes.data, o.ctypes.data, -1, N) == 0
+        return o
+    for Nc in (512, 1024, 2048, 4096):
+        N = Nc; x = uniform(rng, 2 * N)
+        wf = ref.transform(N, 1, x, 0, True); wz = ref.transform(N, 1, x, 0, False)
+        errs = [R.relmax(run(Nc, N, L_C_ORD, S_C_ORD, 0, x), wf), R.relmax(run(Nc, N, L_C_ORD, S_C_Z, 0, x), wz),
+                R.relmax(run(Nc, N, L_C_ORD, S_C_ORD, 1, wf), ref.transform(N, 1, wf, 1, True)),
+                R.relmax(run(Nc, N, L_C_Z, S_C_ORD, 1, wz), ref.transform(N, 1, wz, 1, False))]
+        N = 2 * Nc; x = uniform(rng, N)
+        wf = ref.transform(N, 0, x, 0, True); wz = ref.transform(N, 0, x, 0, False)
+        errs += [R.relmax(run(Nc, N, L_R_TIME, S_R_ORD, 0, x), wf), R.relmax(run(Nc, N, L_R_TIME, S_R_Z, 0, x), wz),
+                 R.relmax(run(Nc, N, L_R_ORD, S_R_TIME, 1, wf), ref.transform(N, 0, wf, 1, True)),
+                 R.relmax(run(Nc, N, L_R_Z, S_R_TIME, 1, wz), ref.transform(N, 0, wz, 1, False))]
+        assert max(errs) <= 2e-6, (Nc, errs)
