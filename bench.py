@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -64,9 +64,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,7 +75,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 - 0.03 <= ts <= t1 + 0.03)]
+        window = "timed region"
+        if not inside:                       # sampler slower than the region: fall back to every sample of the run
+            inside, window = [ln for _, ln in self.lines], "whole run (no sample landed inside the timed region)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -87,7 +91,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -218,6 +222,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
@@ -225,13 +232,11 @@ def main():
     err = ((z[:64] / N - x[:64]) ** 2).sum(dim=1).max().item()
     assert err <= N * 1e-7, "bench self-check failed: round trip error %g" % err
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = pf.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    wall0 = time.time()
     ev0.record()
     for i in range(args.steps):
         fwd_ev[i][0].record()
@@ -240,8 +245,9 @@ def main():
         pf.pffftb_transform_batch(setup.handle, y, z, batch, pf.PFFFT_BACKWARD, 1)
     ev1.record()
     barrier()
+    wall1 = time.time()
     launches = pf.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in fwd_ev]))
     if world > 1:

@@ -25,11 +25,23 @@ typedef void (*afree_fn)(void*);
 
 typedef struct {
   xform_fn xform; void* setup;
-  const float* in; float* out; float* work;
-  size_t per; long first, count; int fwd_inv; int iters;
+  float* in; float* out; float* work;
+  size_t per; long first, count; int fwd_inv; int iters; unsigned seed;
 } job_t;
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+/* first touch by the thread that will use the slice (NUMA placement), uniform(-1,1) from a per-thread xorshift */
+static void* filler(void* p) {
+  job_t* j = (job_t*)p;
+  uint32_t st = j->seed * 2654435761u + (uint32_t)j->first * 40503u + 1u;
+  for (size_t i = (size_t)j->first * j->per; i < (size_t)(j->first + j->count) * j->per; ++i) {
+    st ^= st << 13; st ^= st >> 17; st ^= st << 5;
+    j->in[i] = (float)((st >> 8) * (1.0 / 8388608.0) - 1.0);
+    j->out[i] = 0.f;
+  }
+  return NULL;
+}
 
 static void* worker(void* p) {
   job_t* j = (job_t*)p;
@@ -59,21 +71,20 @@ double cpu_bench_transform(const char* libpath, int N, int transform, long batch
   float* in = (float*)amalloc(per * batch * sizeof(float));
   float* out = (float*)amalloc(per * batch * sizeof(float));
   if (!in || !out) return -4.0;
-  uint32_t st = seed ? seed : 1u;
-  for (size_t i = 0; i < per * (size_t)batch; ++i) {            /* uniform(-1,1), xorshift */
-    st ^= st << 13; st ^= st >> 17; st ^= st << 5;
-    in[i] = (float)((st >> 8) * (1.0 / 8388608.0) - 1.0);
-  }
-  memset(out, 0, per * batch * sizeof(float));
   if (nthreads < 1) nthreads = 1;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
   job_t* jobs = (job_t*)malloc(sizeof(job_t) * nthreads);
   for (int t = 0; t < nthreads; ++t) {
     long lo = batch * t / nthreads, hi = batch * (t + 1) / nthreads;
-    jobs[t] = (job_t){xform, s, in, out, (float*)amalloc(per * sizeof(float)), per, lo, hi - lo, fwd_inv, iters};
+    jobs[t] = (job_t){xform, s, in, out, (float*)amalloc(per * sizeof(float)), per, lo, hi - lo, fwd_inv, iters, seed ? seed : 1u};
   }
+  for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, filler, &jobs[t]);
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
   /* warm-up pass (page faults, caches), then the timed passes */
-  for (int t = 0; t < nthreads; ++t) { job_t w = jobs[t]; w.iters = 1; worker(&w); }
+  { job_t* warm = (job_t*)malloc(sizeof(job_t) * nthreads);
+    for (int t = 0; t < nthreads; ++t) { warm[t] = jobs[t]; warm[t].iters = 1; pthread_create(&th[t], NULL, worker, &warm[t]); }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(warm); }
   const double t0 = now_s();
   for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, &jobs[t]);
   for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);

@@ -59,11 +59,11 @@ static int run_c1024(Setup<float>* s, const float* in, float* out, long long bat
 #define PF_CTA_TPSM 1024
 #endif
 // ---- CTA-per-transform kernels (cta_kernels.cuh): complex cores of 512 / 1024 / 2048 / 4096 points
-template <int C, int LM, int SM, int SIGN>
-static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
+template <int C, int LM, int SM, int SIGN, bool STAGED>
+static int launch_cta_v(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
   constexpr int MINB = PF_CTA_TPSM / (16 * C);              // threads per SM the register budget is sized for
-  auto kern = k_cta_fft<C, LM, SM, SIGN, MINB>;
-  const size_t smem = (size_t)K2<C>::NC * sizeof(cf);
+  auto kern = k_cta_fft<C, LM, SM, SIGN, MINB, STAGED>;
+  const size_t smem = (size_t)K2<C>::NC * sizeof(cf) * (STAGED ? 2 : 1) + (STAGED ? 16 : 0);
   static thread_local int per_sm = 0;
   if (per_sm == 0) {
     if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -79,6 +79,17 @@ static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
   return 0;
+}
+// STAGED (TMA-fed) variant when the call is a plain contiguous, 16-byte aligned batch in canonical input order
+// measured slower than register-fed loads at 1024 threads/SM (C3: 0.70 vs 0.79 of HBM peak): opt-in only
+static bool g_cta_stage = getenv("PFFFT_B200_CTA_STAGE") ? atoi(getenv("PFFFT_B200_CTA_STAGE")) != 0 : false;
+template <int C, int LM, int SM, int SIGN>
+static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
+  if constexpr (LM == L_C_ORD || LM == L_R_TIME) {
+    const bool contiguous = p.in_limit < 0 && p.in_stride == (long long)s->per() && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+    if (g_cta_stage && contiguous) return launch_cta_v<C, LM, SM, SIGN, true>(s, p, st);
+  }
+  return launch_cta_v<C, LM, SM, SIGN, false>(s, p, st);
 }
 template <int C>
 static int run_cta(Setup<float>* s, const XformParams<float>& p, int direction, int ordered, cudaStream_t st) {

@@ -17,6 +17,7 @@
 #pragma once
 #include "butterfly.cuh"
 #include "generic_kernels.cuh"
+#include "fast_kernels.cuh"   // mbarrier / bulk-copy helpers
 
 namespace pf {
 
@@ -129,14 +130,28 @@ template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) 
 
 #ifdef __CUDACC__
 // One CTA = one transform at a time, persistent over the batch.  blockDim.x == 16*C.
-template <int C, int LM, int SM, int SIGN, int MINB>
+// STAGED: the input of the NEXT transform is fetched by the TMA engine (1-D cp.async.bulk, SASS UBLKCP) into a
+// second shared buffer while passes 2/3 and the stores of the current one run; pass 1 then reads shared memory.
+// Only for contiguous, 16-byte aligned, fully in-range inputs in canonical order (complex or real time samples).
+template <int C, int LM, int SM, int SIGN, int MINB, bool STAGED>
 __global__ void __launch_bounds__(16 * C, MINB)
 k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* tw2) {
   using K = K2<C>;
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<float>* tile = reinterpret_cast<cpx<float>*>(pf_smem_raw);
+  cpx<float>* stage = tile + K::NC;                                   // STAGED only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + K::NC);         // STAGED only
   const int t = threadIdx.x;
   constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);   // forward real: X[k] needs Z[k] and Z[Nc-k]
+  constexpr uint32_t kStageBytes = K::NC * sizeof(cpx<float>);
+  if (STAGED) {
+    if (t == 0) {
+      mbar_init(bar, 1); fence_mbar_init(); fence_proxy_async();
+      if ((long long)blockIdx.x < p.batch) { mbar_expect_tx(bar, kStageBytes); bulk_g2s(stage, p.in + (long long)blockIdx.x * p.in_stride, kStageBytes, bar); }
+    }
+    __syncthreads();
+  }
+  uint32_t phase = 0;
   for (long long tr = blockIdx.x; tr < p.batch; tr += gridDim.x) {
     // keep the twiddle loads inside the loop: hoisted, the 30 per-thread twiddles are loop invariants the
     // compiler spills to local memory (measured: +2 GB of L2 traffic per 4 GB launch); re-read from L1 instead
@@ -144,13 +159,25 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* t
     asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twr));
     const float* ibase = p.in + tr * p.in_stride;
     float* obase = p.out + tr * p.out_stride;
-    const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
-    const bool vin = vec_aligned<float>(ibase);
-    if (vin && (avail < 0 || avail >= (long long)(2 * K::NC)))
-      k2_pass1<C, LM, SIGN, true, float>(t, ibase, p.N, twr, avail, true, tw1, tile);
-    else
-      k2_pass1<C, LM, SIGN, false, float>(t, ibase, p.N, twr, avail, vin, tw1, tile);
-    __syncthreads();
+    if (STAGED) {
+      mbar_wait(bar, phase); phase ^= 1;
+      k2_pass1<C, LM, SIGN, true, float>(t, reinterpret_cast<const float*>(stage), p.N, twr, -1, true, tw1, tile);
+      __syncthreads();
+      const long long nxt = tr + gridDim.x;
+      if (t == 0 && nxt < p.batch) {                                   // stage is free: fetch the next transform now
+        fence_proxy_async();
+        mbar_expect_tx(bar, kStageBytes);
+        bulk_g2s(stage, p.in + nxt * p.in_stride, kStageBytes, bar);
+      }
+    } else {
+      const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
+      const bool vin = vec_aligned<float>(ibase);
+      if (vin && (avail < 0 || avail >= (long long)(2 * K::NC)))
+        k2_pass1<C, LM, SIGN, true, float>(t, ibase, p.N, twr, avail, true, tw1, tile);
+      else
+        k2_pass1<C, LM, SIGN, false, float>(t, ibase, p.N, twr, avail, vin, tw1, tile);
+      __syncthreads();
+    }
     k2_pass2<C, SIGN, float>(t, tw2, tile);
     __syncthreads();
     cpx<float> u[16];

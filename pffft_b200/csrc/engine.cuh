@@ -290,7 +290,13 @@ int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device
   int cur = 0; cudaGetDevice(&cur);
   if (cur != s->device) PF_CUDA_OK(cudaSetDevice(s->device));
   const size_t per = s->per();
-  long long chunk = (long long)((size_t)(32u << 20) / (per * sizeof(T)));     // ~32 MiB per direction per chunk
+  static const size_t chunk_bytes = []() {                                  // ~32 MiB per direction per chunk (PFFFT_B200_CHUNK_MB overrides)
+    const char* e = getenv("PFFFT_B200_CHUNK_MB");
+    long mb = e ? atol(e) : 32;
+    if (mb < 1) mb = 1; if (mb > 1024) mb = 1024;
+    return (size_t)mb << 20;
+  }();
+  long long chunk = (long long)(chunk_bytes / (per * sizeof(T)));
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   int rc = ensure_slots(s, (size_t)chunk * per);

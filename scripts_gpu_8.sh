@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_full.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_full.log
+tail -n 6 gpurun_out/pytest_full.log
+echo "== staged"; timeout 900 python bench_configs.py --sweep 2> gpurun_out/configs.err | grep -E "C3|cta_" | cut -c1-330
+echo "== not staged"; PFFFT_B200_CTA_STAGE=0 timeout 900 python bench_configs.py --sweep 2> gpurun_out/configs.err | grep -E "C3|cta_" | cut -c1-330
