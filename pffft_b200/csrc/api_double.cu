@@ -1,6 +1,7 @@
 // api_double.cu -- pffftd_* : the double-precision C-ABI (ref include/pffft/pffft_double.h:129-245).
-// All sizes run on the generic Stockham kernels instantiated for double.
+// Complex cores of 512..4096 points run on the 16x16xC CTA kernels, every other size on the generic Stockham kernels.
 #include "../../include/pffft/pffft_b200.h"
 #include "api_impl.cuh"
+#include "cta_hooks.cuh"
 
-PF_API(pffftd_, pffftdb_, PFFFTD_Setup, double, pf::FastHooks<double>, doubles_per_transform)
+PF_API(pffftd_, pffftdb_, PFFFTD_Setup, double, pf::CtaOnlyHooks<double>, doubles_per_transform)

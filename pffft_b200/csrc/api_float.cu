@@ -3,7 +3,7 @@
 #include "../../include/pffft/pffft_b200.h"
 #include "api_impl.cuh"
 #include "fast_kernels.cuh"
-#include "cta_kernels.cuh"
+#include "cta_hooks.cuh"
 
 namespace pf {
 
@@ -55,61 +55,11 @@ static int run_c1024(Setup<float>* s, const float* in, float* out, long long bat
   return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
 }
 
-#ifndef PF_CTA_TPSM
-#define PF_CTA_TPSM 1024
-#endif
-// ---- CTA-per-transform kernels (cta_kernels.cuh): complex cores of 512 / 1024 / 2048 / 4096 points
-template <int C, int LM, int SM, int SIGN, bool STAGED>
-static int launch_cta_v(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
-  constexpr int MINB = PF_CTA_TPSM / (16 * C);              // threads per SM the register budget is sized for
-  auto kern = k_cta_fft<C, LM, SM, SIGN, MINB, STAGED>;
-  const size_t smem = (size_t)K2<C>::NC * sizeof(cf) * (STAGED ? 2 : 1) + (STAGED ? 16 : 0);
-  static thread_local int per_sm = 0;
-  if (per_sm == 0) {
-    if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * C, smem);
-    if (per_sm < 1) per_sm = 1;
-  }
-  long long ctas = p.batch;
-  const long long cap = (long long)s->sm_count * per_sm;
-  if (ctas > cap) ctas = cap;
-  const cf* tw1 = s->tw_fast;
-  const cf* tw2 = s->tw_fast + K2<C>::NC;
-  kern<<<(int)ctas, 16 * C, smem, st>>>(p, tw1, tw2);
-  count_launch();
-  PF_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-// STAGED (TMA-fed) variant when the call is a plain contiguous, 16-byte aligned batch in canonical input order
-// measured slower than register-fed loads at 1024 threads/SM (C3: 0.70 vs 0.79 of HBM peak): opt-in only
-static bool g_cta_stage = getenv("PFFFT_B200_CTA_STAGE") ? atoi(getenv("PFFFT_B200_CTA_STAGE")) != 0 : false;
-template <int C, int LM, int SM, int SIGN>
-static int launch_cta(Setup<float>* s, const XformParams<float>& p, cudaStream_t st) {
-  if constexpr (LM == L_C_ORD || LM == L_R_TIME) {
-    const bool contiguous = p.in_limit < 0 && p.in_stride == (long long)s->per() && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
-    if (g_cta_stage && contiguous) return launch_cta_v<C, LM, SM, SIGN, true>(s, p, st);
-  }
-  return launch_cta_v<C, LM, SM, SIGN, false>(s, p, st);
-}
-template <int C>
-static int run_cta(Setup<float>* s, const XformParams<float>& p, int direction, int ordered, cudaStream_t st) {
-  const bool fwd = direction == DIR_FORWARD;
-  if (s->transform == XF_COMPLEX) {
-    if (fwd) return ordered ? launch_cta<C, L_C_ORD, S_C_ORD, -1>(s, p, st) : launch_cta<C, L_C_ORD, S_C_Z, -1>(s, p, st);
-    return ordered ? launch_cta<C, L_C_ORD, S_C_ORD, +1>(s, p, st) : launch_cta<C, L_C_Z, S_C_ORD, +1>(s, p, st);
-  }
-  if (fwd) return ordered ? launch_cta<C, L_R_TIME, S_R_ORD, -1>(s, p, st) : launch_cta<C, L_R_TIME, S_R_Z, -1>(s, p, st);
-  return ordered ? launch_cta<C, L_R_ORD, S_R_TIME, +1>(s, p, st) : launch_cta<C, L_R_Z, S_R_TIME, +1>(s, p, st);
-}
-static int cta_C_for(int Nc) { return Nc == 512 ? 2 : Nc == 1024 ? 4 : Nc == 2048 ? 8 : Nc == 4096 ? 16 : 0; }
-
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
-    const int Nc = transform == XF_REAL ? N / 2 : N;
-    const int C = cta_C_for(Nc);
-    return C ? (size_t)Nc + 16 * (size_t)C : 0;
+    return cta_table_cpx(transform == XF_REAL ? N / 2 : N);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
     if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
@@ -121,23 +71,7 @@ template <> struct FastHooks<float> {
         }
       return;
     }
-    const int Nc = transform == XF_REAL ? N / 2 : N;
-    const int C = cta_C_for(Nc);
-    if (!C) return;
-    const int BC = 16 * C;
-    for (int ka = 0; ka < 16; ++ka)                         // tw1[ka*BC + m] = exp(-2 pi i m ka / Nc)
-      for (int m = 0; m < BC; ++m) {
-        long double c, sn;
-        pfplan::unit_root((long long)m * ka, Nc, &c, &sn);
-        dst[2 * (ka * BC + m)] = (float)c; dst[2 * (ka * BC + m) + 1] = (float)sn;
-      }
-    float* t2 = dst + 2 * (size_t)Nc;
-    for (int kb = 0; kb < 16; ++kb)                         // tw2[kb*C + nc] = exp(-2 pi i nc kb / BC)
-      for (int nc = 0; nc < C; ++nc) {
-        long double c, sn;
-        pfplan::unit_root((long long)nc * kb, BC, &c, &sn);
-        t2[2 * (kb * C + nc)] = (float)c; t2[2 * (kb * C + nc) + 1] = (float)sn;
-      }
+    cta_fill_tables<float>(transform == XF_REAL ? N / 2 : N, dst);
   }
   static bool plan(Setup<float>* s) {
     if (is_warp1024(s->N, s->transform)) {
@@ -150,7 +84,7 @@ template <> struct FastHooks<float> {
     const int C = cta_C_for(s->Nc);
     if (!C || getenv("PFFFT_B200_NO_CTA")) return false;
     s->fast_variant = 100 + C;
-    s->kernel_name = C == 2 ? "cta_16x16x2" : C == 4 ? "cta_16x16x4" : C == 8 ? "cta_16x16x8" : "cta_16x16x16";
+    s->kernel_name = cta_name(C);
     return true;
   }
   static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
@@ -164,12 +98,7 @@ template <> struct FastHooks<float> {
                      : run_c1024<+1, true, false>(s, in, out, batch, st);
     }
     const XformParams<float> p = make_params(s, in, out, batch, o);
-    switch (s->fast_variant - 100) {
-      case 2: return run_cta<2>(s, p, direction, ordered, st);
-      case 4: return run_cta<4>(s, p, direction, ordered, st);
-      case 8: return run_cta<8>(s, p, direction, ordered, st);
-      default: return run_cta<16>(s, p, direction, ordered, st);
-    }
+    return run_cta_any<float>(s, s->fast_variant - 100, p, direction, ordered, st);
   }
 };
 

@@ -133,17 +133,17 @@ template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) 
 // STAGED: the input of the NEXT transform is fetched by the TMA engine (1-D cp.async.bulk, SASS UBLKCP) into a
 // second shared buffer while passes 2/3 and the stores of the current one run; pass 1 then reads shared memory.
 // Only for contiguous, 16-byte aligned, fully in-range inputs in canonical order (complex or real time samples).
-template <int C, int LM, int SM, int SIGN, int MINB, bool STAGED>
+template <typename T, int C, int LM, int SM, int SIGN, int MINB, bool STAGED>
 __global__ void __launch_bounds__(16 * C, MINB)
-k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* tw2) {
+k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
   using K = K2<C>;
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
-  cpx<float>* tile = reinterpret_cast<cpx<float>*>(pf_smem_raw);
-  cpx<float>* stage = tile + K::NC;                                   // STAGED only
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
+  cpx<T>* stage = tile + K::NC;                                   // STAGED only
   uint64_t* bar = reinterpret_cast<uint64_t*>(stage + K::NC);         // STAGED only
   const int t = threadIdx.x;
   constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);   // forward real: X[k] needs Z[k] and Z[Nc-k]
-  constexpr uint32_t kStageBytes = K::NC * sizeof(cpx<float>);
+  constexpr uint32_t kStageBytes = K::NC * sizeof(cpx<T>);
   if (STAGED) {
     if (t == 0) {
       mbar_init(bar, 1); fence_mbar_init(); fence_proxy_async();
@@ -155,13 +155,13 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* t
   for (long long tr = blockIdx.x; tr < p.batch; tr += gridDim.x) {
     // keep the twiddle loads inside the loop: hoisted, the 30 per-thread twiddles are loop invariants the
     // compiler spills to local memory (measured: +2 GB of L2 traffic per 4 GB launch); re-read from L1 instead
-    const cpx<float>* twr = p.twr;
+    const cpx<T>* twr = p.twr;
     asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twr));
-    const float* ibase = p.in + tr * p.in_stride;
-    float* obase = p.out + tr * p.out_stride;
+    const T* ibase = p.in + tr * p.in_stride;
+    T* obase = p.out + tr * p.out_stride;
     if (STAGED) {
       mbar_wait(bar, phase); phase ^= 1;
-      k2_pass1<C, LM, SIGN, true, float>(t, reinterpret_cast<const float*>(stage), p.N, twr, -1, true, tw1, tile);
+      k2_pass1<C, LM, SIGN, true, T>(t, reinterpret_cast<const T*>(stage), p.N, twr, -1, true, tw1, tile);
       __syncthreads();
       const long long nxt = tr + gridDim.x;
       if (t == 0 && nxt < p.batch) {                                   // stage is free: fetch the next transform now
@@ -171,21 +171,21 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* t
       }
     } else {
       const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
-      const bool vin = vec_aligned<float>(ibase);
+      const bool vin = vec_aligned<T>(ibase);
       if (vin && (avail < 0 || avail >= (long long)(2 * K::NC)))
-        k2_pass1<C, LM, SIGN, true, float>(t, ibase, p.N, twr, avail, true, tw1, tile);
+        k2_pass1<C, LM, SIGN, true, T>(t, ibase, p.N, twr, avail, true, tw1, tile);
       else
-        k2_pass1<C, LM, SIGN, false, float>(t, ibase, p.N, twr, avail, vin, tw1, tile);
+        k2_pass1<C, LM, SIGN, false, T>(t, ibase, p.N, twr, avail, vin, tw1, tile);
       __syncthreads();
     }
-    k2_pass2<C, SIGN, float>(t, tw2, tile);
+    k2_pass2<C, SIGN, T>(t, tw2, tile);
     __syncthreads();
-    cpx<float> u[16];
-    k2_pass3<C, SIGN, float>(t, tile, u);
+    cpx<T> u[16];
+    k2_pass3<C, SIGN, T>(t, tile, u);
     if (!kNeedsPartner) {
-      const bool vok = vec_aligned<float>(obase);
+      const bool vok = vec_aligned<T>(obase);
       if (SM == S_C_ORD || (SM == S_R_TIME && vok && p.out_count >= 2 * K::NC)) {   // whole transform stored: no per-element checks
-        cpx<float>* dst = reinterpret_cast<cpx<float>*>(obase);
+        cpx<T>* dst = reinterpret_cast<cpx<T>*>(obase);
 #pragma unroll
         for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
@@ -194,7 +194,7 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* t
 #pragma unroll
         for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
-          for (int kc = 0; kc < C; ++kc) store_elem<SM, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
+          for (int kc = 0; kc < C; ++kc) store_elem<SM, T>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
       }
       __syncthreads();                          // tile is rewritten by the next transform's pass 1
     } else {
@@ -205,7 +205,7 @@ k_cta_fft(const XformParams<float> p, const cpx<float>* tw1, const cpx<float>* t
         for (int kc = 0; kc < C; ++kc) tile[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
       __syncthreads();
 #pragma unroll 4
-      for (int j = 0; j < 8; ++j) real_post_pair<SM, float>(obase, tile, t + K::T * j, p.N, K::NC, twr);   // k in [0, Nc/2)
+      for (int j = 0; j < 8; ++j) real_post_pair<SM, T>(obase, tile, t + K::T * j, p.N, K::NC, twr);   // k in [0, Nc/2)
       __syncthreads();
     }
   }
