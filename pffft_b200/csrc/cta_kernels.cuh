@@ -125,6 +125,75 @@ PF_HD void real_post_pair(T* base, const cpx<T>* z, int k, int N, int Nc, const 
   spec_put<Z, true>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
 }
 
+
+// ---- forward-real variant of pass 3 for C <= 8: each thread takes, besides its row (k_a, k_b), the row that holds
+// the mirror bins Nc-k, so the real post-rotation happens in registers (no natural-order round trip through shared
+// memory, no extra barriers).  Mirror of k = k_a + 16 k_b + 256 k_c:
+//     k_a != 0          : (16-k_a, 15-k_b, C-1-k_c)
+//     k_a == 0, k_b != 0: (0, 16-k_b, C-1-k_c)
+//     k_a == 0, k_b == 0: inside row (0,0) [k_c <-> C-k_c]; thread 0 pairs it with row (0,8), whose mirror is itself
+// Representative rows are those with k_b < 8: thread t -> k_a = t%16, k_b = t/16 + C*r, r < 8/C.
+template <int C> PF_HD void k2_mirror_row(int ka, int kb, int& ka2, int& kb2) {
+  if (ka != 0) { ka2 = 16 - ka; kb2 = 15 - kb; }
+  else { ka2 = 0; kb2 = (kb == 0) ? 8 : 16 - kb; }
+}
+template <int C, int SIGN, typename T>
+PF_HD void k2_pass3_pairs(int t, const cpx<T>* tile, cpx<T> (&u)[16]) {
+  using K = K2<C>;
+  const int ka = t & 15, kb0 = t >> 4;
+#pragma unroll
+  for (int r = 0; r < 8 / C; ++r) {
+    const int kb = kb0 + C * r;
+    int ka2, kb2;
+    k2_mirror_row<C>(ka, kb, ka2, kb2);
+#pragma unroll
+    for (int p = 0; p < C; ++p) {
+      u[(2 * r) * C + p] = tile[K::idx(ka, kb, brevC<C>(p))];
+      u[(2 * r + 1) * C + p] = tile[K::idx(ka2, kb2, brevC<C>(p))];
+    }
+  }
+  if (C == 8) { dit_fft<8, SIGN, 0, 1>(u); dit_fft<8, SIGN, 8, 1>(u); }
+  if (C == 4) { dit_fft<4, SIGN, 0, 1>(u); dit_fft<4, SIGN, 4, 1>(u); dit_fft<4, SIGN, 8, 1>(u); dit_fft<4, SIGN, 12, 1>(u); }
+  if (C == 2) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { const cpx<T> a = u[2 * r], b = u[2 * r + 1]; u[2 * r] = a + b; u[2 * r + 1] = a - b; }
+  }
+}
+// X[k], X[Nc-k] from a = Z[k], zm = Z[Nc-k]  (same algebra as real_post_pair)
+template <int SM, typename T>
+PF_HD void real_post_regs(T* base, int k, int Nc, int N, cpx<T> a, cpx<T> zm, const cpx<T>* twr) {
+  constexpr bool Z = (SM == S_R_Z);
+  const cpx<T> b = conj(zm);
+  const cpx<T> s = a + b, d = a - b;
+  const cpx<T> u = cmul(d, ldtab(twr + k));
+  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+  spec_put<Z, true>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+}
+template <int C, int SM, typename T>
+PF_HD void k2_store_pairs(int t, const cpx<T> (&u)[16], T* base, int N, const cpx<T>* twr) {
+  using K = K2<C>;
+  constexpr bool Z = (SM == S_R_Z);
+  const int ka = t & 15, kb0 = t >> 4;
+#pragma unroll
+  for (int r = 0; r < 8 / C; ++r) {
+    const int kb = kb0 + C * r;
+    const cpx<T>* A = &u[(2 * r) * C];
+    const cpx<T>* B = &u[(2 * r + 1) * C];
+    if (ka == 0 && kb == 0) {
+      // row (0,0): k = 256 kc, mirror inside the row; row (0,8): k = 128 + 256 kc, mirror inside that row
+      spec_put<Z, true>(base, 0, N, mk<T>(A[0].x + A[0].y, A[0].x - A[0].y));            // (DC, Nyquist)
+      if (C >= 2) spec_put<Z, true>(base, K::NC / 2, N, mk<T>(A[C / 2].x, -A[C / 2].y));  // X[Nc/2] = conj Z[Nc/2]
+#pragma unroll
+      for (int kc = 1; kc < C / 2; ++kc) real_post_regs<SM, T>(base, 256 * kc, K::NC, N, A[kc], A[C - kc], twr);
+#pragma unroll
+      for (int kc = 0; kc < C / 2; ++kc) real_post_regs<SM, T>(base, 128 + 256 * kc, K::NC, N, B[kc], B[C - 1 - kc], twr);
+    } else {
+#pragma unroll
+      for (int kc = 0; kc < C; ++kc) real_post_regs<SM, T>(base, ka + 16 * kb + 256 * kc, K::NC, N, A[kc], B[C - 1 - kc], twr);
+    }
+  }
+}
+
 // natural index of u[r*C + kc] held by thread t after pass 3
 template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) + 16 * ((t >> 4) + C * r) + 256 * kc; }
 
@@ -181,6 +250,12 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
     k2_pass2<C, SIGN, T>(t, tw2, tile);
     __syncthreads();
     cpx<T> u[16];
+    if (kNeedsPartner && C <= 8) {             // forward real, mirror rows in the same thread: rotate in registers
+      k2_pass3_pairs<C, SIGN, T>(t, tile, u);
+      k2_store_pairs<C, SM, T>(t, u, obase, p.N, twr);
+      __syncthreads();
+      continue;
+    }
     k2_pass3<C, SIGN, T>(t, tile, u);
     if (!kNeedsPartner) {
       const bool vok = vec_aligned<T>(obase);

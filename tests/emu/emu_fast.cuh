@@ -56,6 +56,10 @@ static void emu_k2_run(const float* in, float* out, int N, long long in_limit, i
   for (int t = 0; t < K::T; ++t) k2_pass1<C, LM, SIGN, false, float>(t, in, N, ptwr, in_limit, vec_aligned<float>(in), ptw1, tile.data());
   for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, ptw2, tile.data());
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  if (partner && C <= 8) {
+    for (int t = 0; t < K::T; ++t) { cf u[16]; k2_pass3_pairs<C, SIGN, float>(t, tile.data(), u); k2_store_pairs<C, SM, float>(t, u, out, N, ptwr); }
+    return;
+  }
   for (int t = 0; t < K::T; ++t) {
     cf u[16];
     k2_pass3<C, SIGN, float>(t, tile.data(), u);
