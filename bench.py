@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 
 N = 1024
 BYTES_PER_FFT = 2 * N * 2 * 4          # 8 KiB read + 8 KiB written (algorithmic bytes / transform)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the forward kernel, per transform:
+# (2.147577 + 2.097573) GB over a 262144-transform launch (profiles/r01_ncu_full_c1024.txt).  bench.py scales it to
+# the units of its own launch; it is evidence that traffic ~= algorithmic bytes, not a live measurement.
+NCU_DRAM_BYTES_PER_FFT = (2.147577e9 + 2.097573e9) / 262144
 FLOPS_PER_FFT = 5 * N * 10             # 5 N log2 N (bench_pffft.c:1021)
 
 
@@ -302,7 +306,9 @@ def main():
             "gflops": value * FLOPS_PER_FFT / 1e9,
             "gbs_algorithmic": value * BYTES_PER_FFT / 1e9,
             "roofline": {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
-                         "traffic": None, "kernel": setup.kernel + " (forward launch, %d transforms)" % batch,
+                         "traffic": NCU_DRAM_BYTES_PER_FFT * batch if "ldg" in setup.kernel else None,
+                         "traffic_source": "profiles/r01_ncu_full_c1024.txt (ncu --set full, per-transform DRAM bytes x this launch's transforms)",
+                         "kernel": setup.kernel + " (forward launch, %d transforms)" % batch,
                          "algorithmic_bytes_per_launch": batch * BYTES_PER_FFT, "ms_per_launch": fwd_ms,
                          "peak_source": peak_src,
                          "whole_step_frac": (value / world) * BYTES_PER_FFT / 1e9 / peak},

@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     import torch
     import pffft_b200 as pf
@@ -100,6 +101,31 @@ def main():
     th = (time.perf_counter() - t0) / 3
     emit({"config": "C4 pffastconv, host pointers (pageable numpy buffers)", "ms": th * 1e3, "msamples_per_s": produced / th / 1e6})
     fc.close()
+
+    # ---- the reference's CPU path beside each config (oracle/_ref on the host cores, bounded samples)
+    if not args.no_cpu:
+        import ctypes as C
+        from oracle import ref as R
+        so = os.path.join(ROOT, "oracle", "libcpubench.so")
+        if R.have_ref() and os.path.exists(so):
+            cb = C.CDLL(so)
+            cb.cpu_bench_transform.restype = C.c_double
+            cb.cpu_bench_transform.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+            cb.cpu_bench_fastconv.restype = C.c_double
+            cb.cpu_bench_fastconv.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+            cores = len(os.sched_getaffinity(0))
+            path = R.REF_SO.encode()
+            for name, N, tr, sample, fi in (("C2 N=1024 cplx fwd", 1024, 1, 1 << 16, 0), ("C3 N=4096 real fwd", 4096, 0, 1 << 15, 0)):
+                for nt in (1, cores):
+                    smp = sample if nt > 1 else sample // 8
+                    tsec = cb.cpu_bench_transform(path, N, tr, smp, nt, 8, fi, 1, 1235)
+                    emit({"config": "CPU reference " + name, "threads": nt, "sample_transforms": smp, "passes": 8,
+                          "ffts_per_s": smp * 8 / tsec, "gbs_algorithmic": smp * 8 * (16 * N if tr else 8 * N) / tsec / 1e9,
+                          "kind": "reference (oracle/_ref, -O3 -march=haswell)"})
+            prod = C.c_int(0)
+            tsec = cb.cpu_bench_fastconv(path, 1 << 24, 4097, 3, C.byref(prod))
+            emit({"config": "CPU reference C4 pffastconv 2^24 samples, 4097 taps (1 thread: setup not shareable)",
+                  "ms": tsec * 1e3, "msamples_per_s": prod.value / tsec / 1e6, "produced": prod.value})
 
     if args.sweep:
         for N in (64, 256, 512, 2048, 4096, 8192, 16384, 65536, 96, 960, 4000):
