@@ -55,10 +55,40 @@ static int run_c1024(Setup<float>* s, const float* in, float* out, long long bat
   return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
 }
 
+// ---- small complex sizes on the warp machinery (N = 32..256)
+template <int R2, int SIGN, bool ZIN, bool ZOUT>
+static int launch_wsmall(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+  constexpr int WARPS = 4, MINB = 4;
+  auto kern = k_warp_small<R2, SIGN, WARPS, MINB, ZIN, ZOUT>;
+  const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
+  const long long nchunks = (batch + (32 / R2) - 1) / (32 / R2);
+  long long ctas = (nchunks + WARPS - 1) / WARPS;
+  const long long cap = (long long)s->sm_count * MINB;
+  if (ctas > cap) ctas = cap;
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int SIGN, bool ZIN, bool ZOUT>
+static int run_wsmall(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st) {
+  switch (R2) {
+    case 1: return launch_wsmall<1, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 2: return launch_wsmall<2, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 4: return launch_wsmall<4, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    default: return launch_wsmall<8, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+  }
+}
+static int wsmall_R2_for(int N, int transform) {
+  if (transform != XF_COMPLEX) return 0;
+  return N == 32 ? 1 : N == 64 ? 2 : N == 128 ? 4 : N == 256 ? 8 : 0;
+}
+
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
+    if (wsmall_R2_for(N, transform)) return (size_t)N;
     return cta_table_cpx(transform == XF_REAL ? N / 2 : N);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
@@ -71,6 +101,15 @@ template <> struct FastHooks<float> {
         }
       return;
     }
+    if (const int R2 = wsmall_R2_for(N, transform)) {         // tw[k2*32 + l] = exp(-2 pi i l k2 / N)
+      for (int k2 = 0; k2 < R2; ++k2)
+        for (int l = 0; l < 32; ++l) {
+          long double c, sn;
+          pfplan::unit_root((long long)l * k2, N, &c, &sn);
+          dst[2 * (k2 * 32 + l)] = (float)c; dst[2 * (k2 * 32 + l) + 1] = (float)sn;
+        }
+      return;
+    }
     cta_fill_tables<float>(transform == XF_REAL ? N / 2 : N, dst);
   }
   static bool plan(Setup<float>* s) {
@@ -79,6 +118,12 @@ template <> struct FastHooks<float> {
       if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
       s->fast_variant = v;
       s->kernel_name = kVariantName[v];
+      return true;
+    }
+    if (const int R2 = wsmall_R2_for(s->N, s->transform)) {
+      if (getenv("PFFFT_B200_NO_WSMALL")) return false;
+      s->fast_variant = 200 + R2;
+      s->kernel_name = R2 == 1 ? "warp_32x1" : R2 == 2 ? "warp_32x2" : R2 == 4 ? "warp_32x4" : "warp_32x8";
       return true;
     }
     const int C = cta_C_for(s->Nc);
@@ -96,6 +141,15 @@ template <> struct FastHooks<float> {
                                                    : run_c1024<-1, false, true>(s, in, out, batch, st);
       return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
                      : run_c1024<+1, true, false>(s, in, out, batch, st);
+    }
+    if (s->fast_variant >= 200) {                           // small warp kernels: contiguous canonical batches only
+      const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+      if (!plain) return -1;
+      const int R2 = s->fast_variant - 200;
+      if (direction == DIR_FORWARD) return ordered ? run_wsmall<-1, false, false>(s, R2, in, out, batch, st)
+                                                   : run_wsmall<-1, false, true>(s, R2, in, out, batch, st);
+      return ordered ? run_wsmall<+1, false, false>(s, R2, in, out, batch, st)
+                     : run_wsmall<+1, true, false>(s, R2, in, out, batch, st);
     }
     const XformParams<float> p = make_params(s, in, out, batch, o);
     return run_cta_any<float>(s, s->fast_variant - 100, p, direction, ordered, st);

@@ -45,6 +45,7 @@ PF_HD void w1024_cols(cf (&v)[32], int lane, const cf* tile) {
   reg_fft<32, SIGN>(v);
 }
 
+// (device helpers follow)
 #ifdef __CUDACC__
 PF_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 PF_D void mbar_init(uint64_t* bar, uint32_t count) {
@@ -172,5 +173,96 @@ k_c1024_bulk(const cf* __restrict__ in, cf* __restrict__ out, long long batch, c
   }
 }
 #endif  // __CUDACC__
+
+
+// ---------------------------------------------------------------------------------------------
+// Small complex sizes Nc = 32*R2 (R2 = 1,2,4,8 -> N = 32,64,128,256): the same warp machinery, with the
+// warp's 1024-point chunk holding TW = 32/R2 whole transforms.  Lane l loads the chunk's elements l + 32 m
+// (coalesced rows, exactly as for N=1024); m = j*R2 + n2 selects transform j and the stride-32 digit n2.
+//   phase A: per transform j a radix-R2 register FFT over n2, * W_Nc^{l k2}, tile[l][j*R2 + k2]
+//   phase B: lane c = (j, k2) runs the radix-32 FFT down column c  ->  X_j[k2 + R2*k1]
+// tw[k2*32 + l] = exp(-2 pi i l k2 / Nc).  Canonical (ordered) layout in and out.
+// ---------------------------------------------------------------------------------------------
+template <int R2> PF_HD constexpr int brevR2(int p) { return ct::bitrev(p, ct::ilog2(R2)); }
+
+template <int R2, int SIGN>
+PF_HD void wsmall_rows(cf (&v)[32], int lane, const cf* tw, cf* tile) {
+  // v[j*R2 + p] = chunk[lane + 32*(j*R2 + brevR2(p))] on entry
+  if constexpr (R2 == 8) { dit_fft<8, SIGN, 0, 1>(v); dit_fft<8, SIGN, 8, 1>(v); dit_fft<8, SIGN, 16, 1>(v); dit_fft<8, SIGN, 24, 1>(v); }
+  if constexpr (R2 == 4) {
+    dit_fft<4, SIGN, 0, 1>(v); dit_fft<4, SIGN, 4, 1>(v); dit_fft<4, SIGN, 8, 1>(v); dit_fft<4, SIGN, 12, 1>(v);
+    dit_fft<4, SIGN, 16, 1>(v); dit_fft<4, SIGN, 20, 1>(v); dit_fft<4, SIGN, 24, 1>(v); dit_fft<4, SIGN, 28, 1>(v);
+  }
+  if constexpr (R2 == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const cf a = v[2 * j], b = v[2 * j + 1]; v[2 * j] = a + b; v[2 * j + 1] = a - b; }
+  }
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const int k2 = m % R2;
+    tile[lane * 33 + m] = (k2 == 0) ? v[m] : cmul_dir<SIGN>(v[m], tw[k2 * 32 + lane]);
+  }
+}
+
+#ifdef __CUDACC__
+// one warp = one 1024-point chunk = 32/R2 transforms; grid-stride over chunks.
+// ZIN / ZOUT: the transform's input / output is in the reference's z-domain layout (pffft_transform), so the
+// ordered and unordered entry points share one arithmetic path and stay bit-identical to each other.
+template <int R2, int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_warp_small(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g) {
+  constexpr int NC = 32 * R2;
+  constexpr int TW = 32 / R2;                   // transforms per warp chunk
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cf* tw = reinterpret_cast<cf*>(pf_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf* tile = tw + NC + warp * kW1024Tile;
+  for (int i = threadIdx.x; i < NC; i += WARPS * 32) tw[i] = tw_g[i];
+  __syncthreads();
+  const long long nchunks = (batch + TW - 1) / TW;
+  const long long stride = (long long)gridDim.x * WARPS;
+  for (long long c = (long long)blockIdx.x * WARPS + warp; c < nchunks; c += stride) {
+    const cf* src = in + c * 1024;
+    cf* dst = out + c * 1024;
+    const long long left = batch - c * TW;      // transforms of this chunk that exist (>= 1)
+    const int nvalid = left >= TW ? TW : (int)left;
+    cf v[32];
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int p = 0; p < R2; ++p) {
+        const int n = lane + 32 * brevR2<R2>(p);                       // index inside transform j
+        if (j >= nvalid) v[j * R2 + p] = mk<float>(0.f, 0.f);
+        else if (!ZIN) v[j * R2 + p] = ld_stream(src + j * NC + n);
+        else { const float* sz = reinterpret_cast<const float*>(src + j * NC); const int q = zpos_complex(n, NC); v[j * R2 + p] = mk<float>(sz[q], sz[q + 4]); }
+      }
+    wsmall_rows<R2, SIGN>(v, lane, tw, tile);
+    __syncwarp();
+    w1024_cols<SIGN>(v, lane, tile);            // column `lane` = (j = lane / R2, k2 = lane % R2)
+    __syncwarp();
+    const int j = lane / R2, k2 = lane % R2;
+    if (ZOUT) {
+      if (j < nvalid) {
+        float* d = reinterpret_cast<float*>(dst + j * NC);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); d[q] = v[k1].x; d[q + 4] = v[k1].y; }
+      }
+    } else if (R2 <= 2) {
+      // 8/16-byte pieces per lane would scatter: go back through the tile and store whole 256-byte rows
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) { const int e = j * NC + k2 + R2 * k1; tile[(e >> 5) * 33 + (e & 31)] = v[k1]; }
+      __syncwarp();
+      const int rows = nvalid * R2;             // 32-element rows of the chunk that hold existing transforms
+#pragma unroll
+      for (int r = 0; r < 32; ++r) if (r < rows) st_stream(dst + 32 * r + lane, tile[r * 33 + lane]);
+      __syncwarp();
+    } else if (j < nvalid) {
+      cf* d = dst + j * NC + k2;
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) st_stream(d + R2 * k1, v[k1]);
+    }
+  }
+}
+#endif
 
 }  // namespace pf

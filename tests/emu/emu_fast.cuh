@@ -171,3 +171,39 @@ extern "C" long long emu_fastconv(int Nfft, const float* x, long long len, const
   }
   return -1;
 }
+
+// ---- small warp kernel phases (N = 32..256 complex)
+template <int R2, int SIGN> static void emu_wsmall_run(const float* in, float* out, long long batch) {
+  using namespace pf;
+  constexpr int NC = 32 * R2, TW = 32 / R2;
+  std::vector<cf> tw(NC > 32 ? NC : 32);
+  for (int k2 = 0; k2 < R2; ++k2) for (int l = 0; l < 32; ++l) {
+    long double c, s; pfplan::unit_root((long long)l * k2, NC, &c, &s);
+    tw[k2 * 32 + l] = mk<float>((float)c, (float)s);
+  }
+  std::vector<cf> tile(kW1024Tile);
+  const long long nchunks = (batch + TW - 1) / TW;
+  for (long long c = 0; c < nchunks; ++c) {
+    const cf* src = reinterpret_cast<const cf*>(in) + c * 1024;
+    cf* dst = reinterpret_cast<cf*>(out) + c * 1024;
+    const long long left = batch - c * TW; const int nvalid = left >= TW ? TW : (int)left;
+    for (int lane = 0; lane < 32; ++lane) {
+      cf v[32];
+      for (int j = 0; j < TW; ++j) for (int p = 0; p < R2; ++p)
+        v[j * R2 + p] = (j < nvalid) ? src[lane + 32 * (j * R2 + brevR2<R2>(p))] : mk<float>(0.f, 0.f);
+      wsmall_rows<R2, SIGN>(v, lane, tw.data(), tile.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      cf v[32];
+      w1024_cols<SIGN>(v, lane, tile.data());
+      const int j = lane / R2, k2 = lane % R2;
+      if (j < nvalid) for (int k1 = 0; k1 < 32; ++k1) dst[j * NC + k2 + R2 * k1] = v[k1];
+    }
+  }
+}
+extern "C" int emu_wsmall(int N, int dir, const float* in, float* out, long long batch) {
+#define WS(n, r) if (N == n) { if (dir == 0) emu_wsmall_run<r, -1>(in, out, batch); else emu_wsmall_run<r, +1>(in, out, batch); return 0; }
+  WS(32, 1) WS(64, 2) WS(128, 4) WS(256, 8)
+#undef WS
+  return -1;
+}

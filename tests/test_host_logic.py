@@ -133,3 +133,20 @@ def test_cta_kernel_phases_and_swizzle(emu, ref, R):
                  R.relmax(run(Nc, N, L_R_ORD, S_R_TIME, 1, wf), ref.transform(N, 0, wf, 1, True)),
                  R.relmax(run(Nc, N, L_R_Z, S_R_TIME, 1, wz), ref.transform(N, 0, wz, 1, False))]
         assert max(errs) <= 2e-6, (Nc, errs)
+
+
+def test_small_warp_kernel_phases(emu, ref, R):
+    """N = 32..256 complex on the warp machinery (32/R2 transforms per warp chunk), including a partial last chunk"""
+    emu.emu_wsmall.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    rng = np.random.default_rng(4)
+    for N in (32, 64, 128, 256):
+        for batch in (1, 1024 // N, 1024 // N + 3):
+            x = uniform(rng, batch * 2 * N).reshape(batch, 2 * N)
+            pad = np.zeros(((-(batch * N) % 1024) * 2,), np.float32)      # the emulation indexes whole 1024-point chunks
+            xin = np.concatenate([x.ravel(), pad]); o = np.full_like(xin, np.nan)
+            for d in (0, 1):
+                assert emu.emu_wsmall(N, d, xin.ctypes.data, o.ctypes.data, batch) == 0
+                w = ref.transform_batch(N, 1, x, d, True)
+                got = o[: batch * 2 * N].reshape(batch, 2 * N)
+                assert max(R.relmax(got[i], w[i]) for i in range(batch)) <= 2e-6, (N, batch, d)
+                assert np.all(np.isnan(o[batch * 2 * N:])), "wrote beyond the batch"
