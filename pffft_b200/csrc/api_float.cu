@@ -89,7 +89,7 @@ template <> struct FastHooks<float> {
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform)) return (size_t)N;
-    return cta_table_cpx(transform == XF_REAL ? N / 2 : N);
+    return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
     if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
@@ -110,7 +110,7 @@ template <> struct FastHooks<float> {
         }
       return;
     }
-    cta_fill_tables<float>(transform == XF_REAL ? N / 2 : N, dst);
+    CtaOnlyHooks<float>::fill_extra_table(N, transform, dst);
   }
   static bool plan(Setup<float>* s) {
     if (is_warp1024(s->N, s->transform)) {
@@ -126,11 +126,7 @@ template <> struct FastHooks<float> {
       s->kernel_name = R2 == 1 ? "warp_32x1" : R2 == 2 ? "warp_32x2" : R2 == 4 ? "warp_32x4" : "warp_32x8";
       return true;
     }
-    const int C = cta_C_for(s->Nc);
-    if (!C || getenv("PFFFT_B200_NO_CTA")) return false;
-    s->fast_variant = 100 + C;
-    s->kernel_name = cta_name(C);
-    return true;
+    return CtaOnlyHooks<float>::plan(s);
   }
   static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
                  const XformOpts& o) {
@@ -142,7 +138,7 @@ template <> struct FastHooks<float> {
       return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
                      : run_c1024<+1, true, false>(s, in, out, batch, st);
     }
-    if (s->fast_variant >= 200) {                           // small warp kernels: contiguous canonical batches only
+    if (s->fast_variant >= 200 && s->fast_variant < 300) {  // small warp kernels: contiguous batches only
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
       if (!plain) return -1;
       const int R2 = s->fast_variant - 200;
@@ -151,8 +147,7 @@ template <> struct FastHooks<float> {
       return ordered ? run_wsmall<+1, false, false>(s, R2, in, out, batch, st)
                      : run_wsmall<+1, true, false>(s, R2, in, out, batch, st);
     }
-    const XformParams<float> p = make_params(s, in, out, batch, o);
-    return run_cta_any<float>(s, s->fast_variant - 100, p, direction, ordered, st);
+    return CtaOnlyHooks<float>::run(s, in, out, batch, direction, ordered, st, o);
   }
 };
 
@@ -171,7 +166,7 @@ int float_transform_device(PFFFT_Setup* s, const float* in, float* out, long lon
 }
 FloatPlanTables float_plan_tables(PFFFT_Setup* s) {
   FloatPlanTables t{0, s->sm_count, nullptr, nullptr, s->twr};
-  if (s->kind == KK_FAST && s->fast_variant >= 100) {
+  if (s->kind == KK_FAST && s->fast_variant >= 100 && s->fast_variant < 200) {
     t.C = s->fast_variant - 100;
     t.tw1 = s->tw_fast;
     t.tw2 = s->tw_fast + s->Nc;

@@ -87,11 +87,98 @@ int run_cta_any(Setup<T>* s, int C, const XformParams<T>& p, int direction, int 
   }
 }
 
+
+// ---------------------------------------------------------------- large N: Nc = R x 4096, R in {2,4,8,16}
+// (complex N = 8192..65536, real N = 16384..131072).  Decimation in time over the first digit:
+//   rows   : R launches of the 16x16x16 CTA kernel, row n1 = FFT_4096 of x[n1 + R*n2] (element stride R)
+//   combine: k_split_combine finishes with the radix-R butterflies and writes X in natural order.
+// Two HBM round trips (plus one for a real pre-/post-rotation or z-domain pass): ceiling 0.5 of the roofline,
+// against (stages+2) round trips of the global Stockham path it replaces.
+inline int split_R_for(int Nc) { return Nc == 8192 ? 2 : Nc == 16384 ? 4 : Nc == 32768 ? 8 : Nc == 65536 ? 16 : 0; }
+inline const char* split_name(int R) { return R == 2 ? "split_2x4096" : R == 4 ? "split_4x4096" : R == 8 ? "split_8x4096" : "split_16x4096"; }
+
+template <typename T, int SIGN>
+int split_core(Setup<T>* s, int R, const cpx<T>* src, cpx<T>* rows, cpx<T>* dst, long long batch, cudaStream_t st) {
+  constexpr int N2 = 4096;
+  // ONE launch over batch*R rows: consecutive CTAs take the R interleaved sub-sequences of the same transform, so
+  // their stride-R reads of the same 128-byte lines meet in L2 instead of re-reading DRAM R times
+  XformParams<T> q;
+  q.in = reinterpret_cast<const T*>(src); q.out = reinterpret_cast<T*>(rows);
+  q.in_stride = 2LL * s->Nc; q.in_group = R; q.in_gstep = 2; q.in_estride = R;
+  q.out_stride = 2LL * N2; q.in_limit = -1; q.out_count = 2 * N2;
+  q.batch = batch * R; q.N = N2; q.Nc = N2; q.nfac = 0; q.tw = s->tw; q.twr = nullptr;
+  for (int i = 0; i < PF_MAX_FACTORS; ++i) q.fac[i] = 1;
+  { const int rc = launch_cta_v<T, 16, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st); if (rc) return rc; }
+  const long long work = batch * N2;
+  long long g = (work + 255) / 256; const long long cap = (long long)s->sm_count * 16;
+  if (g > cap) g = cap; if (g < 1) g = 1;
+  switch (R) {
+    case 2: k_split_combine<T, 2, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+    case 4: k_split_combine<T, 4, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+    case 8: k_split_combine<T, 8, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+    default: k_split_combine<T, 16, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+  }
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int LM, int SM, int SIGN>
+int run_split_modes(Setup<T>* s, int R, const XformParams<T>& p, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(s->scratch_mu);
+  { const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st); if (rc) return rc; }
+  const long long total = p.batch * (long long)s->Nc;
+  long long g = (total + 255) / 256; const long long cap = (long long)s->sm_count * 32;
+  if (g > cap) g = cap; if (g < 1) g = 1;
+  const bool dense_io = p.in_stride == (long long)s->per() && p.out_stride == (long long)s->per();
+  // input that already IS the dense complex core (complex canonical, or real time samples read as pairs)
+  const bool direct_in = dense_io && p.in_limit < 0 && (LM == L_C_ORD || LM == L_R_TIME) && vec_aligned<T>(p.in);
+  const bool direct_out = dense_io && (SM == S_C_ORD || (SM == S_R_TIME && p.out_count >= s->N)) && vec_aligned<T>(p.out);
+  const cpx<T>* src = reinterpret_cast<const cpx<T>*>(p.in);
+  if (!direct_in) {
+    k_glob_load<T, LM><<<(int)g, 256, 0, st>>>(p, s->d_scratch[0]);
+    count_launch();
+    src = s->d_scratch[0];
+  }
+  cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
+  const int rc = split_core<T, SIGN>(s, R, src, s->d_scratch[1], dst, p.batch, st);
+  if (rc) return rc;
+  if (!direct_out) {
+    k_glob_store<T, SM><<<(int)g, 256, 0, st>>>(p, s->d_scratch[0]);
+    count_launch();
+  }
+  PF_CUDA_OK(cudaGetLastError());
+  PF_CUDA_OK(cudaEventRecord(s->scratch_done, st));
+  return 0;
+}
+template <typename T>
+int run_split(Setup<T>* s, int R, const XformParams<T>& p, int direction, int ordered, cudaStream_t st) {
+  const bool fwd = direction == DIR_FORWARD;
+  if (s->transform == XF_COMPLEX) {
+    if (fwd) return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, -1>(s, R, p, st) : run_split_modes<T, L_C_ORD, S_C_Z, -1>(s, R, p, st);
+    return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, +1>(s, R, p, st) : run_split_modes<T, L_C_Z, S_C_ORD, +1>(s, R, p, st);
+  }
+  if (fwd) return ordered ? run_split_modes<T, L_R_TIME, S_R_ORD, -1>(s, R, p, st) : run_split_modes<T, L_R_TIME, S_R_Z, -1>(s, R, p, st);
+  return ordered ? run_split_modes<T, L_R_ORD, S_R_TIME, +1>(s, R, p, st) : run_split_modes<T, L_R_Z, S_R_TIME, +1>(s, R, p, st);
+}
+
 // hooks for a precision whose only tuned kernels are the CTA ones (double)
 template <typename T> struct CtaOnlyHooks {
-  static size_t extra_table_cpx(int N, int transform) { return cta_table_cpx(transform == XF_REAL ? N / 2 : N); }
-  static void fill_extra_table(int N, int transform, T* dst) { cta_fill_tables<T>(transform == XF_REAL ? N / 2 : N, dst); }
+  static size_t extra_table_cpx(int N, int transform) {
+    const int Nc = transform == XF_REAL ? N / 2 : N;
+    return split_R_for(Nc) ? cta_table_cpx(4096) : cta_table_cpx(Nc);
+  }
+  static void fill_extra_table(int N, int transform, T* dst) {
+    const int Nc = transform == XF_REAL ? N / 2 : N;
+    cta_fill_tables<T>(split_R_for(Nc) ? 4096 : Nc, dst);
+  }
   static bool plan(Setup<T>* s) {
+    if (const int R = split_R_for(s->Nc)) {
+      if (getenv("PFFFT_B200_NO_SPLIT")) return false;
+      s->fast_variant = 300 + R;
+      s->kernel_name = split_name(R);
+      return true;
+    }
     const int C = cta_C_for(s->Nc);
     if (!C || getenv("PFFFT_B200_NO_CTA")) return false;
     s->fast_variant = 100 + C;
@@ -100,6 +187,7 @@ template <typename T> struct CtaOnlyHooks {
   }
   static int run(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered, cudaStream_t st, const XformOpts& o) {
     const XformParams<T> p = make_params(s, in, out, batch, o);
+    if (s->fast_variant >= 300) return run_split<T>(s, s->fast_variant - 300, p, direction, ordered, st);
     return run_cta_any<T>(s, s->fast_variant - 100, p, direction, ordered, st);
   }
 };

@@ -58,7 +58,7 @@ PF_HD void store_elem(T* base, int k, cpx<T> v, int N, int out_count, bool vec_o
 // ---- pass 1: thread m in [0, 16C)
 template <int C, int LM, int SIGN, bool FAST, typename T>
 PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long avail, bool vec_ok,
-                    const cpx<T>* tw1, cpx<T>* tile) {
+                    const cpx<T>* tw1, cpx<T>* tile, int es = 1) {
   using K = K2<C>;
   cpx<T> v[16];
   if (FAST && (LM == L_R_TIME || LM == L_C_ORD)) {      // contiguous, aligned, fully in range: plain 64-bit loads
@@ -67,7 +67,7 @@ PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long av
     for (int p = 0; p < 16; ++p) v[p] = src[K::BC * brev4(p)];
   } else {
 #pragma unroll
-    for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok);
+    for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok, es);
   }
   reg_fft<16, SIGN>(v);
   const int jb = m / C, jc = m % C;
@@ -226,7 +226,8 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
     // compiler spills to local memory (measured: +2 GB of L2 traffic per 4 GB launch); re-read from L1 instead
     const cpx<T>* twr = p.twr;
     asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twr));
-    const T* ibase = p.in + tr * p.in_stride;
+    const long long grp = (p.in_group > 1) ? tr / p.in_group : tr;
+    const T* ibase = p.in + grp * p.in_stride + (tr - grp * p.in_group) * (long long)p.in_gstep;
     T* obase = p.out + tr * p.out_stride;
     if (STAGED) {
       mbar_wait(bar, phase); phase ^= 1;
@@ -241,10 +242,10 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
     } else {
       const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
       const bool vin = vec_aligned<T>(ibase);
-      if (vin && (avail < 0 || avail >= (long long)(2 * K::NC)))
+      if (vin && p.in_estride == 1 && (avail < 0 || avail >= (long long)(2 * K::NC)))
         k2_pass1<C, LM, SIGN, true, T>(t, ibase, p.N, twr, avail, true, tw1, tile);
       else
-        k2_pass1<C, LM, SIGN, false, T>(t, ibase, p.N, twr, avail, vin, tw1, tile);
+        k2_pass1<C, LM, SIGN, false, T>(t, ibase, p.N, twr, avail, vin, tw1, tile, p.in_estride);
       __syncthreads();
     }
     k2_pass2<C, SIGN, T>(t, tw2, tile);

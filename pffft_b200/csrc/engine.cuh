@@ -30,7 +30,7 @@ bool ptr_is_device(const void* p);   // cudaPointerGetAttributes: device/managed
     if (_e != cudaSuccess) { ::pf::set_error(#call, _e); return (int)_e; } \
   } while (0)
 
-enum KernelKind { KK_SMEM = 0, KK_GLOBAL = 1, KK_FAST = 2 };
+enum KernelKind { KK_SMEM = 0, KK_GLOBAL = 1, KK_FAST = 2, KK_SPLIT = 3 };
 
 // per-call options beyond the classic API (used by pffastconv: overlapping strided blocks)
 struct XformOpts {
@@ -177,22 +177,28 @@ template <typename T, typename S> void engine_destroy_setup(S* s) {
   delete s;
 }
 
+// ---------------------------------------------------------------- scratch shared by the multi-launch paths
+// caller holds s->scratch_mu; makes `st` wait for the previous user and grows both buffers to `need` complex words
+template <typename T> int scratch_acquire(Setup<T>* s, size_t need, cudaStream_t st) {
+  if (!s->scratch_done) PF_CUDA_OK(cudaEventCreateWithFlags(&s->scratch_done, cudaEventDisableTiming));
+  PF_CUDA_OK(cudaStreamWaitEvent(st, s->scratch_done, 0));
+  if (need > s->scratch_cpx) {
+    PF_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) { if (s->d_scratch[i]) cudaFree(s->d_scratch[i]); s->d_scratch[i] = nullptr; }
+    PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[0], need * sizeof(cpx<T>)));
+    PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[1], need * sizeof(cpx<T>)));
+    s->scratch_cpx = need;
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------- launches (device pointers)
 template <typename T, int LM, int SM, int SIGN>
 int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
   if (s->kind == KK_GLOBAL) {
     // the ping-pong scratch is shared by every stream using this plan: serialise its users
     std::lock_guard<std::mutex> lock(s->scratch_mu);
-    PF_CUDA_OK(cudaStreamWaitEvent(st, s->scratch_done, 0));
-    // grow scratch to the batch (large-N path only; the batch of such sizes is small)
-    const size_t need = (size_t)p.batch * s->Nc;
-    if (need > s->scratch_cpx) {
-      PF_CUDA_OK(cudaDeviceSynchronize());
-      for (int i = 0; i < 2; ++i) { if (s->d_scratch[i]) cudaFree(s->d_scratch[i]); s->d_scratch[i] = nullptr; }
-      PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[0], need * sizeof(cpx<T>)));
-      PF_CUDA_OK(cudaMalloc((void**)&s->d_scratch[1], need * sizeof(cpx<T>)));
-      s->scratch_cpx = need;
-    }
+    { const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st); if (rc) return rc; }
     const long long total = p.batch * (long long)s->Nc;
     const int thr = 256;
     auto grid_for = [&](long long work) { long long g = (work + thr - 1) / thr; long long cap = (long long)s->sm_count * 32; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); };
@@ -242,6 +248,7 @@ template <typename T> XformParams<T> make_params(Setup<T>* s, const T* in, T* ou
   p.out_stride = o.out_stride >= 0 ? o.out_stride : (long long)s->per();
   p.in_limit = o.in_limit;
   p.out_count = o.out_count >= 0 ? o.out_count : s->N;
+  p.in_estride = 1; p.in_group = 1; p.in_gstep = 0;
   p.batch = batch; p.N = s->N; p.Nc = s->Nc; p.nfac = s->nfac;
   for (int i = 0; i < PF_MAX_FACTORS; ++i) p.fac[i] = i < s->nfac ? s->fac[i] : 1;
   p.tw = s->tw; p.twr = s->twr;

@@ -35,6 +35,10 @@ template <typename T> struct XformParams {
   long long in_limit;     // L_R_TIME only: number of readable elements starting at `in` (<0: no limit);
                           // samples beyond it read as zero (overlap-save tail padding, ref pffastconv.c:231-233)
   int out_count;          // S_R_TIME only: leading real samples stored per transform (ref pffastconv.c:255)
+  int in_group;           // transforms per input group (1 = plain batch): transform tr reads from
+  int in_gstep;           //   in + (tr / in_group) * in_stride + (tr % in_group) * in_gstep   (split large-N rows)
+  int in_estride;         // L_C_ORD only: distance (in complex elements) between consecutive input points (1 = dense);
+                          // >1 feeds the decimated sub-sequences of the split large-N path
   long long batch;
   int N;                  // transform length as the API sees it
   int Nc;                 // complex core length: N (complex) or N/2 (real)
@@ -58,8 +62,8 @@ template <bool ZLAYOUT, bool REAL, typename T> PF_HD void spec_put(T* base, int 
 
 // element i of the complex core's INPUT for this transform
 template <int LM, typename T>
-PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, long long avail, bool vec_ok) {
-  if (LM == L_C_ORD) return spec_get<false, false>(base, i, N);
+PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, long long avail, bool vec_ok, int es = 1) {
+  if (LM == L_C_ORD) return reinterpret_cast<const cpx<T>*>(base)[(long long)i * es];
   if (LM == L_C_Z)   return spec_get<true, false>(base, i, N);
   if (LM == L_R_TIME) {
     const long long e = 2LL * i;
@@ -221,6 +225,33 @@ __global__ void __launch_bounds__(256) k_glob_store(const XformParams<T> p, cons
     const int k = (int)(idx - t * p.Nc);
     T* base = p.out + t * p.out_stride;
     store_core<SM, T>(base, src + t * p.Nc, k, p.N, p.Nc, p.twr, p.out_count, vec_aligned<T>(base));
+  }
+}
+
+// ------------------------------------------------------------------ large N: last radix-R step of the split path
+// Nc = R * N2.  The R decimated sub-sequences x[n1 + R*n2] were transformed by the CTA kernel into Y[n1][k2]
+// (rows of N2); this kernel finishes with   X[k2 + N2*k1] = sum_n1 W_R^{n1 k1} * (W_Nc^{n1 k2} Y[n1][k2]).
+// One thread per (transform, k2): R coalesced reads, R coalesced writes.  tw = exp(-2 pi i k / Nc).
+template <typename T, int R, int SIGN>
+__global__ void __launch_bounds__(256) k_split_combine(const cpx<T>* __restrict__ Y, cpx<T>* __restrict__ X, long long batch,
+                                                       int N2, const cpx<T>* __restrict__ tw) {
+  const long long total = batch * N2;
+  constexpr int bits = ct::ilog2(R);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / N2;
+    const int k2 = (int)(idx - t * N2);
+    const cpx<T>* y = Y + t * (long long)R * N2 + k2;
+    cpx<T> v[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+      const int n1 = ct::bitrev(p, bits);
+      const cpx<T> a = y[(long long)n1 * N2];
+      v[p] = (n1 == 0) ? a : cmul_dir<SIGN>(a, tw[(long long)n1 * k2]);
+    }
+    reg_fft<R, SIGN>(v);
+    cpx<T>* x = X + t * (long long)R * N2 + k2;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) x[(long long)k1 * N2] = v[k1];
   }
 }
 

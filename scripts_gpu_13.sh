@@ -19,6 +19,7 @@ def t(N,tr,lb,dt=torch.float32):
     b.record(); torch.cuda.synchronize(); ms=a.elapsed_time(b)/10
     es=4 if dt==torch.float32 else 8
     print(N,'real' if tr==0 else 'cplx',str(dt)[6:],s.kernel,'%.3f ms'%ms,'%.0f GB/s'%(2*batch*per*es/ms/1e6), '%.2f of peak'%(2*batch*per*es/ms/1e6/6573.2))
-for N in (32,64,128,256): t(N,1,30-int(np.log2(8*N)))
+for N in (8192,16384,65536): t(N,1,30-int(np.log2(8*N)))
+t(16384,0,30-16); t(131072,0,30-19); t(16384,1,29-17,torch.float64); t(262144,1,10)
 t(16,1,23); t(96,1,22); t(960,1,19); t(8192,1,16); t(64,0,23); t(256,0,22); t(512,0,21)
 PY

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 # bench_pffft.c:445 validation sizes + the power-of-two ladder of tests/test_pffft.c:333
-POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144]
 NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864]
 
 
@@ -352,7 +352,13 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(96, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
+        assert s.kernel == "split_16x4096"
+    with pf.Setup(1 << 20, 1) as s:
         assert s.kernel == "global_stockham"
+    with pf.Setup(256, 1) as s:
+        assert s.kernel == "warp_32x8"
+    with pf.Setup(4096, 0) as s:
+        assert s.kernel == "cta_16x16x8"
     n0 = pf.launch_count()
     torch = torch_mod()
     with pf.Setup(1024, 1) as s:
