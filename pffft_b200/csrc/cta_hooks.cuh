@@ -36,7 +36,9 @@ template <typename T, int C, int LM, int SM, int SIGN, bool STAGED>
 int launch_cta_v(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
   constexpr int MINB = cta_tpsm<T>() / (16 * C);
   auto kern = k_cta_fft<T, C, LM, SM, SIGN, MINB, STAGED>;
-  const size_t smem = (size_t)K2<C>::NC * sizeof(cpx<T>) * (STAGED ? 2 : 1) + (STAGED ? 16 : 0);
+  // second buffer: TMA stage, gather staging of z-domain / backward-real inputs, or the z image of a C=16 real forward
+  constexpr bool kSecond = STAGED || LM == L_C_Z || LM == L_R_Z || (SM == S_R_Z && C == 16);
+  const size_t smem = (size_t)K2<C>::NC * sizeof(cpx<T>) * (kSecond ? 2 : 1) + (STAGED ? 16 : 0);
   static thread_local int per_sm = 0;
   if (per_sm == 0) {
     if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -44,10 +44,10 @@ template <typename T> PF_HD cpx<T> ldtab(const cpx<T>* p) {
 template <int C> PF_HD constexpr int brevC(int p) { return ct::bitrev(p, ct::ilog2(C)); }
 
 // direct store of output element k from a register (modes that need no partner element)
-template <int SM, typename T>
+template <int SM, typename T, bool SWZ = false>
 PF_HD void store_elem(T* base, int k, cpx<T> v, int N, int out_count, bool vec_ok) {
   if (SM == S_C_ORD) { spec_put<false, false>(base, k, N, v); return; }
-  if (SM == S_C_Z)   { spec_put<true, false>(base, k, N, v); return; }
+  if (SM == S_C_Z)   { spec_put<true, false, SWZ>(base, k, N, v); return; }
   // S_R_TIME: two real samples, truncated to out_count (pffastconv keeps only the valid ones)
   const int e = 2 * k;
   if (vec_ok && e + 1 < out_count) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
@@ -56,7 +56,7 @@ PF_HD void store_elem(T* base, int k, cpx<T> v, int N, int out_count, bool vec_o
 }
 
 // ---- pass 1: thread m in [0, 16C)
-template <int C, int LM, int SIGN, bool FAST, typename T>
+template <int C, int LM, int SIGN, bool FAST, typename T, bool SWZ = false>
 PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long avail, bool vec_ok,
                     const cpx<T>* tw1, cpx<T>* tile, int es = 1) {
   using K = K2<C>;
@@ -67,7 +67,7 @@ PF_HD void k2_pass1(int m, const T* base, int N, const cpx<T>* twr, long long av
     for (int p = 0; p < 16; ++p) v[p] = src[K::BC * brev4(p)];
   } else {
 #pragma unroll
-    for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok, es);
+    for (int p = 0; p < 16; ++p) v[p] = load_core<LM, T, SWZ>(base, m + K::BC * brev4(p), N, K::NC, twr, avail, vec_ok, es);
   }
   reg_fft<16, SIGN>(v);
   const int jb = m / C, jc = m % C;
@@ -109,20 +109,20 @@ PF_HD void k2_pass3(int t, const cpx<T>* tile, cpx<T> (&u)[16]) {
 // forward-real epilogue on PAIRS: X[k] and X[Nc-k] share s = Z[k] + conj Z[Nc-k] and u = W^k (Z[k] - conj Z[Nc-k])
 //   X[k] = ((s.x + u.y), (s.y - u.x))/2      X[Nc-k] = ((s.x - u.y), (-s.y - u.x))/2
 // k = 0 also emits the self-paired middle bin: slot 0 = (Z0.x + Z0.y, Z0.x - Z0.y), X[Nc/2] = conj Z[Nc/2].
-template <int SM, typename T>
+template <int SM, typename T, bool SWZ = false>
 PF_HD void real_post_pair(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<T>* twr) {
   constexpr bool Z = (SM == S_R_Z);
   if (k == 0) {
     const cpx<T> z0 = z[0], zm = z[Nc / 2];
-    spec_put<Z, true>(base, 0, N, mk<T>(z0.x + z0.y, z0.x - z0.y));
-    spec_put<Z, true>(base, Nc / 2, N, mk<T>(zm.x, -zm.y));
+    spec_put<Z, true, SWZ>(base, 0, N, mk<T>(z0.x + z0.y, z0.x - z0.y));
+    spec_put<Z, true, SWZ>(base, Nc / 2, N, mk<T>(zm.x, -zm.y));
     return;
   }
   const cpx<T> a = z[k], b = conj(z[Nc - k]);
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, ldtab(twr + k));
-  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
-  spec_put<Z, true>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+  spec_put<Z, true, SWZ>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+  spec_put<Z, true, SWZ>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
 }
 
 
@@ -160,16 +160,16 @@ PF_HD void k2_pass3_pairs(int t, const cpx<T>* tile, cpx<T> (&u)[16]) {
   }
 }
 // X[k], X[Nc-k] from a = Z[k], zm = Z[Nc-k]  (same algebra as real_post_pair)
-template <int SM, typename T>
+template <int SM, typename T, bool SWZ = false>
 PF_HD void real_post_regs(T* base, int k, int Nc, int N, cpx<T> a, cpx<T> zm, const cpx<T>* twr) {
   constexpr bool Z = (SM == S_R_Z);
   const cpx<T> b = conj(zm);
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, ldtab(twr + k));
-  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
-  spec_put<Z, true>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+  spec_put<Z, true, SWZ>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+  spec_put<Z, true, SWZ>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
 }
-template <int C, int SM, typename T>
+template <int C, int SM, typename T, bool SWZ = false>
 PF_HD void k2_store_pairs(int t, const cpx<T> (&u)[16], T* base, int N, const cpx<T>* twr) {
   using K = K2<C>;
   constexpr bool Z = (SM == S_R_Z);
@@ -181,15 +181,15 @@ PF_HD void k2_store_pairs(int t, const cpx<T> (&u)[16], T* base, int N, const cp
     const cpx<T>* B = &u[(2 * r + 1) * C];
     if (ka == 0 && kb == 0) {
       // row (0,0): k = 256 kc, mirror inside the row; row (0,8): k = 128 + 256 kc, mirror inside that row
-      spec_put<Z, true>(base, 0, N, mk<T>(A[0].x + A[0].y, A[0].x - A[0].y));            // (DC, Nyquist)
-      if (C >= 2) spec_put<Z, true>(base, K::NC / 2, N, mk<T>(A[C / 2].x, -A[C / 2].y));  // X[Nc/2] = conj Z[Nc/2]
+      spec_put<Z, true, SWZ>(base, 0, N, mk<T>(A[0].x + A[0].y, A[0].x - A[0].y));       // (DC, Nyquist)
+      if (C >= 2) spec_put<Z, true, SWZ>(base, K::NC / 2, N, mk<T>(A[C / 2].x, -A[C / 2].y));  // X[Nc/2] = conj Z[Nc/2]
 #pragma unroll
-      for (int kc = 1; kc < C / 2; ++kc) real_post_regs<SM, T>(base, 256 * kc, K::NC, N, A[kc], A[C - kc], twr);
+      for (int kc = 1; kc < C / 2; ++kc) real_post_regs<SM, T, SWZ>(base, 256 * kc, K::NC, N, A[kc], A[C - kc], twr);
 #pragma unroll
-      for (int kc = 0; kc < C / 2; ++kc) real_post_regs<SM, T>(base, 128 + 256 * kc, K::NC, N, B[kc], B[C - 1 - kc], twr);
+      for (int kc = 0; kc < C / 2; ++kc) real_post_regs<SM, T, SWZ>(base, 128 + 256 * kc, K::NC, N, B[kc], B[C - 1 - kc], twr);
     } else {
 #pragma unroll
-      for (int kc = 0; kc < C; ++kc) real_post_regs<SM, T>(base, ka + 16 * kb + 256 * kc, K::NC, N, A[kc], B[C - 1 - kc], twr);
+      for (int kc = 0; kc < C; ++kc) real_post_regs<SM, T, SWZ>(base, ka + 16 * kb + 256 * kc, K::NC, N, A[kc], B[C - 1 - kc], twr);
     }
   }
 }
@@ -202,16 +202,46 @@ template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) 
 // STAGED: the input of the NEXT transform is fetched by the TMA engine (1-D cp.async.bulk, SASS UBLKCP) into a
 // second shared buffer while passes 2/3 and the stores of the current one run; pass 1 then reads shared memory.
 // Only for contiguous, 16-byte aligned, fully in-range inputs in canonical order (complex or real time samples).
+// 16-byte granule copies between a dense global spectrum and its shared staging copy (optionally z-swizzled)
+template <typename T, int NTHR, bool SWZ> PF_D void stage_in16(const T* g, T* sm, int nelem, int t) {
+  constexpr int EPG = 16 / sizeof(T);                      // elements per 16-byte granule
+  for (int G = t; G < nelem / EPG; G += NTHR) {
+    const int e = G * EPG;
+    *reinterpret_cast<float4*>(sm + (SWZ ? zswz(e) : e)) = *reinterpret_cast<const float4*>(g + e);
+  }
+}
+template <typename T, int NTHR, bool SWZ> PF_D void stage_out16(T* g, const T* sm, int nelem, int t) {
+  constexpr int EPG = 16 / sizeof(T);
+  for (int G = t; G < nelem / EPG; G += NTHR) {
+    const int e = G * EPG;
+    *reinterpret_cast<float4*>(g + e) = *reinterpret_cast<const float4*>(sm + (SWZ ? zswz(e) : e));
+  }
+}
+PF_HD bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// One CTA = one transform at a time, persistent over the batch.  blockDim.x == 16*C.
+// STAGED: the input of the NEXT transform is fetched by the TMA engine (1-D cp.async.bulk, SASS UBLKCP) into a
+// second shared buffer while passes 2/3 and the stores of the current one run; pass 1 then reads shared memory.
+// Only for contiguous, 16-byte aligned, fully in-range inputs in canonical order (complex or real time samples).
+// Inputs whose elements are gathered (z-domain layouts, backward-real pre-rotation: X[k] and X[Nc-k]) are first
+// copied with coalesced 128-bit loads into a second shared buffer, and z-domain outputs are assembled in shared
+// memory and written with coalesced 128-bit stores, both with the granule swizzle `zswz`.
 template <typename T, int C, int LM, int SM, int SIGN, int MINB, bool STAGED>
 __global__ void __launch_bounds__(16 * C, MINB)
 k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
   using K = K2<C>;
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
-  cpx<T>* stage = tile + K::NC;                                   // STAGED only
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + K::NC);         // STAGED only
+  cpx<T>* stage = tile + K::NC;                                   // STAGED or kGatherIn
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + K::NC);     // STAGED only
   const int t = threadIdx.x;
-  constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);   // forward real: X[k] needs Z[k] and Z[Nc-k]
+  constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);  // forward real: X[k] needs Z[k] and Z[Nc-k]
+  // (staging the ORDERED backward-real input was measured slower than its direct mirrored loads: 0.58 vs 0.75)
+  constexpr bool kGatherIn = (LM == L_C_Z || LM == L_R_Z);
+  // the API length is fixed by the kernel: a compile-time N turns the z-domain index maps into shifts and masks
+  constexpr int kN = (LM == L_C_ORD || LM == L_C_Z) ? K::NC : 2 * K::NC;
+  constexpr bool kZIn = (LM == L_C_Z || LM == L_R_Z);
+  constexpr bool kZOut = (SM == S_C_Z || SM == S_R_Z);
   constexpr uint32_t kStageBytes = K::NC * sizeof(cpx<T>);
   if (STAGED) {
     if (t == 0) {
@@ -231,7 +261,7 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
     T* obase = p.out + tr * p.out_stride;
     if (STAGED) {
       mbar_wait(bar, phase); phase ^= 1;
-      k2_pass1<C, LM, SIGN, true, T>(t, reinterpret_cast<const T*>(stage), p.N, twr, -1, true, tw1, tile);
+      k2_pass1<C, LM, SIGN, true, T>(t, reinterpret_cast<const T*>(stage), kN, twr, -1, true, tw1, tile);
       __syncthreads();
       const long long nxt = tr + gridDim.x;
       if (t == 0 && nxt < p.batch) {                                   // stage is free: fetch the next transform now
@@ -239,21 +269,35 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
         mbar_expect_tx(bar, kStageBytes);
         bulk_g2s(stage, p.in + nxt * p.in_stride, kStageBytes, bar);
       }
+    } else if (kGatherIn && aligned16(ibase)) {
+      // whole spectrum -> shared (coalesced), then every thread gathers its 16 points (and their mirrors) from there
+      stage_in16<T, 16 * C, kZIn>(ibase, reinterpret_cast<T*>(stage), 2 * K::NC, t);
+      __syncthreads();
+      k2_pass1<C, LM, SIGN, false, T, kZIn>(t, reinterpret_cast<const T*>(stage), kN, twr, -1, true, tw1, tile);
+      __syncthreads();
     } else {
       const long long avail = (p.in_limit < 0) ? -1 : (p.in_limit - tr * p.in_stride);
       const bool vin = vec_aligned<T>(ibase);
       if (vin && p.in_estride == 1 && (avail < 0 || avail >= (long long)(2 * K::NC)))
-        k2_pass1<C, LM, SIGN, true, T>(t, ibase, p.N, twr, avail, true, tw1, tile);
+        k2_pass1<C, LM, SIGN, true, T>(t, ibase, kN, twr, avail, true, tw1, tile);
       else
-        k2_pass1<C, LM, SIGN, false, T>(t, ibase, p.N, twr, avail, vin, tw1, tile, p.in_estride);
+        k2_pass1<C, LM, SIGN, false, T>(t, ibase, kN, twr, avail, vin, tw1, tile, p.in_estride);
       __syncthreads();
     }
     k2_pass2<C, SIGN, T>(t, tw2, tile);
     __syncthreads();
     cpx<T> u[16];
+    const bool zstage = kZOut && aligned16(obase) && !(STAGED && C == 16 && SM == S_R_Z);   // CTA-uniform
     if (kNeedsPartner && C <= 8) {             // forward real, mirror rows in the same thread: rotate in registers
       k2_pass3_pairs<C, SIGN, T>(t, tile, u);
-      k2_store_pairs<C, SM, T>(t, u, obase, p.N, twr);
+      if (zstage) {
+        __syncthreads();                        // all pass-3 reads done: the tile becomes the z-domain staging buffer
+        k2_store_pairs<C, SM, T, true>(t, u, reinterpret_cast<T*>(tile), kN, twr);
+        __syncthreads();
+        stage_out16<T, 16 * C, true>(obase, reinterpret_cast<const T*>(tile), 2 * K::NC, t);
+      } else {
+        k2_store_pairs<C, SM, T>(t, u, obase, kN, twr);
+      }
       __syncthreads();
       continue;
     }
@@ -266,11 +310,19 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
         for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
           for (int kc = 0; kc < C; ++kc) dst[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
+      } else if (SM == S_C_Z && zstage) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+          for (int kc = 0; kc < C; ++kc) store_elem<SM, T, true>(reinterpret_cast<T*>(tile), k2_out_index<C>(t, r, kc), u[r * C + kc], kN, p.out_count, true);
+        __syncthreads();
+        stage_out16<T, 16 * C, true>(obase, reinterpret_cast<const T*>(tile), 2 * K::NC, t);
       } else {
 #pragma unroll
         for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
-          for (int kc = 0; kc < C; ++kc) store_elem<SM, T>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], p.N, p.out_count, vok);
+          for (int kc = 0; kc < C; ++kc) store_elem<SM, T>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], kN, p.out_count, vok);
       }
       __syncthreads();                          // tile is rewritten by the next transform's pass 1
     } else {
@@ -280,8 +332,16 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
 #pragma unroll
         for (int kc = 0; kc < C; ++kc) tile[k2_out_index<C>(t, r, kc)] = u[r * C + kc];
       __syncthreads();
+      if (zstage) {
+        // C == 16: natural-order spectrum in `tile`; assemble the z-domain image in `stage`, then stream it out
 #pragma unroll 4
-      for (int j = 0; j < 8; ++j) real_post_pair<SM, T>(obase, tile, t + K::T * j, p.N, K::NC, twr);   // k in [0, Nc/2)
+        for (int j = 0; j < 8; ++j) real_post_pair<SM, T, true>(reinterpret_cast<T*>(stage), tile, t + K::T * j, kN, K::NC, twr);
+        __syncthreads();
+        stage_out16<T, 16 * C, true>(obase, reinterpret_cast<const T*>(stage), 2 * K::NC, t);
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < 8; ++j) real_post_pair<SM, T>(obase, tile, t + K::T * j, kN, K::NC, twr);   // k in [0, Nc/2)
+      }
       __syncthreads();
     }
   }

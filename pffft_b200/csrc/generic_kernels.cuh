@@ -49,22 +49,29 @@ template <typename T> struct XformParams {
 };
 
 // ------------------------------------------------------------------ element-wise load / store
-template <bool ZLAYOUT, bool REAL, typename T> PF_HD cpx<T> spec_get(const T* base, int k, int N) {
+// z-domain positions inside a SHARED-MEMORY staging copy of a spectrum are XOR-swizzled at 16-byte-granule level
+// (element-index bits 2..4 ^= bits 5..7): consecutive bins land in 4-element groups 32 elements apart, which without
+// the swizzle all hit the same 4 banks.  Granules stay intact, so the global side is copied with plain 128-bit accesses.
+PF_HD int zswz(int p) { return p ^ (((p >> 5) & 7) << 2); }
+
+template <bool ZLAYOUT, bool REAL, bool SWZ = false, typename T> PF_HD cpx<T> spec_get(const T* base, int k, int N) {
   if (!ZLAYOUT) return reinterpret_cast<const cpx<T>*>(base)[k];
   const int p = zpos<REAL>(k, N);
+  if (SWZ) return mk<T>(base[zswz(p)], base[zswz(p + 4)]);
   return mk<T>(base[p], base[p + 4]);
 }
-template <bool ZLAYOUT, bool REAL, typename T> PF_HD void spec_put(T* base, int k, int N, cpx<T> v) {
+template <bool ZLAYOUT, bool REAL, bool SWZ = false, typename T> PF_HD void spec_put(T* base, int k, int N, cpx<T> v) {
   if (!ZLAYOUT) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
   const int p = zpos<REAL>(k, N);
+  if (SWZ) { base[zswz(p)] = v.x; base[zswz(p + 4)] = v.y; return; }
   base[p] = v.x; base[p + 4] = v.y;
 }
 
 // element i of the complex core's INPUT for this transform
-template <int LM, typename T>
+template <int LM, typename T, bool SWZ = false>
 PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, long long avail, bool vec_ok, int es = 1) {
   if (LM == L_C_ORD) return reinterpret_cast<const cpx<T>*>(base)[(long long)i * es];
-  if (LM == L_C_Z)   return spec_get<true, false>(base, i, N);
+  if (LM == L_C_Z)   return spec_get<true, false, SWZ>(base, i, N);
   if (LM == L_R_TIME) {
     const long long e = 2LL * i;
     if (vec_ok && (avail < 0 || e + 1 < avail)) return reinterpret_cast<const cpx<T>*>(base)[i];
@@ -76,11 +83,11 @@ PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, l
   // the factor 2 keeps BACKWARD(FORWARD(x)) = N x, ref pffft.h:134)
   constexpr bool Z = (LM == L_R_Z);
   if (i == 0) {
-    const cpx<T> s0 = spec_get<Z, true>(base, 0, N);      // (X[0], X[N/2])
+    const cpx<T> s0 = spec_get<Z, true, SWZ>(base, 0, N);      // (X[0], X[N/2])
     return mk<T>(s0.x + s0.y, s0.x - s0.y);
   }
-  const cpx<T> a = spec_get<Z, true>(base, i, N);
-  const cpx<T> b = conj(spec_get<Z, true>(base, Nc - i, N));
+  const cpx<T> a = spec_get<Z, true, SWZ>(base, i, N);
+  const cpx<T> b = conj(spec_get<Z, true, SWZ>(base, Nc - i, N));
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul_dir<+1>(d, twr[i]);               // d * exp(+2 pi i k/N)
   return mk<T>(s.x - u.y, s.y + u.x);                     // s + i u
