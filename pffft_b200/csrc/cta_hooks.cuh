@@ -109,7 +109,8 @@ int split_core(Setup<T>* s, int R, const cpx<T>* src, cpx<T>* rows, cpx<T>* dst,
   q.in_stride = 2LL * s->Nc; q.in_group = R; q.in_gstep = 2; q.in_estride = R;
   q.out_stride = 2LL * N2; q.in_limit = -1; q.out_count = 2 * N2;
   q.batch = batch * R; q.N = N2; q.Nc = N2; q.nfac = 0; q.tw = s->tw; q.twr = nullptr;
-  for (int i = 0; i < PF_MAX_FACTORS; ++i) q.fac[i] = 1;
+  for (int i = 0; i < PF_MAX_FACTORS; ++i) { q.fac[i] = 1; q.magic[i] = 0; }
+  q.magic_nc = 0;
   { const int rc = launch_cta_v<T, 16, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st); if (rc) return rc; }
   const long long work = batch * N2;
   long long g = (work + 255) / 256; const long long cap = (long long)s->sm_count * 16;

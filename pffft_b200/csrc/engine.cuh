@@ -23,6 +23,8 @@ void set_error(const char* where, cudaError_t e);
 void set_error_msg(const char* msg);
 void count_launch(int n = 1);
 bool ptr_is_device(const void* p);   // cudaPointerGetAttributes: device/managed -> true, host/unregistered -> false
+bool host_mapped_pointer(const void* p, void** dev);   // page-locked + mapped host memory -> its device alias
+bool zero_copy_enabled();
 
 #define PF_CUDA_OK(call)                                        \
   do {                                                          \
@@ -61,7 +63,8 @@ template <typename T> struct Setup {
   // kernel choice
   int kind = KK_SMEM;
   int fast_variant = 0;
-  int tpc = 1;                            // transforms resident per CTA (shared-memory kernel)
+  int tpc = 1;                            // transforms resident per CTA (shared-memory kernel), a power of two
+  int log2_tpt = 8;                       // log2(threads per transform) = log2(256 / tpc)
   size_t smem_bytes = 0;
   const char* kernel_name = "";
   // host-pointer pipeline (3 slots: H2D / kernels / D2H overlap across slots)
@@ -131,8 +134,10 @@ S* engine_new_setup(int N, int transform) {
   const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;      // 227 KB on sm_100
   if (2 * (size_t)s->Nc * cbytes + 1024 <= smem_cap) {
     s->kind = KK_SMEM;
-    int tpc = (int)(2048 / (size_t)s->Nc); if (tpc < 1) tpc = 1;    // ~16-32 KB of transforms per CTA
+    int tpc = 1;                                                   // ~16 KB of transforms per CTA, power of two so
+    while (tpc < 128 && (size_t)(2 * tpc) * s->Nc <= 2048) tpc *= 2;  // that thread -> (transform, lane) is shift/mask
     s->tpc = tpc;
+    s->log2_tpt = 8; for (int v = tpc; v > 1; v >>= 1) --s->log2_tpt;
     s->smem_bytes = 2 * (size_t)tpc * s->Nc * cbytes;
     s->kernel_name = "smem_stockham";
   } else {
@@ -207,7 +212,7 @@ int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
     int cur = 0, stride = 1;
     for (int f = 0; f < s->nfac; ++f) {
       const int r = s->fac[f];
-      k_glob_stage<T, SIGN><<<grid_for(total / r), thr, 0, st>>>(s->d_scratch[cur], s->d_scratch[cur ^ 1], p.batch, s->Nc, r, stride, s->tw);
+      k_glob_stage<T, SIGN><<<grid_for(total / r), thr, 0, st>>>(s->d_scratch[cur], s->d_scratch[cur ^ 1], p.batch, s->Nc, r, stride, stage_magic(stride), s->tw);
       count_launch();
       cur ^= 1; stride *= r;
     }
@@ -235,7 +240,7 @@ int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
   const long long cap = (long long)s->sm_count * per_sm;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  kern<<<(int)ctas, 256, s->smem_bytes, st>>>(p, s->tpc);
+  kern<<<(int)ctas, 256, s->smem_bytes, st>>>(p, s->tpc, s->log2_tpt);
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
   return 0;
@@ -250,7 +255,8 @@ template <typename T> XformParams<T> make_params(Setup<T>* s, const T* in, T* ou
   p.out_count = o.out_count >= 0 ? o.out_count : s->N;
   p.in_estride = 1; p.in_group = 1; p.in_gstep = 0;
   p.batch = batch; p.N = s->N; p.Nc = s->Nc; p.nfac = s->nfac;
-  for (int i = 0; i < PF_MAX_FACTORS; ++i) p.fac[i] = i < s->nfac ? s->fac[i] : 1;
+  p.magic_nc = stage_magic(s->Nc);
+  { int prod = 1; for (int i = 0; i < PF_MAX_FACTORS; ++i) { p.fac[i] = i < s->nfac ? s->fac[i] : 1; p.magic[i] = stage_magic(prod); prod *= p.fac[i]; } }
   p.tw = s->tw; p.twr = s->twr;
   return p;
 }
@@ -330,6 +336,19 @@ int engine_transform(Setup<T>* s, const T* in, T* out, long long batch, int dire
   const bool din = ptr_is_device(in), dout = ptr_is_device(out);
   if (din != dout) { set_error_msg("pffft transform: input and output must both be host or both be device pointers"); return (int)cudaErrorInvalidValue; }
   if (din) return engine_transform_device<T, Hooks>(s, in, out, batch, direction, ordered, s->stream);
+  // page-locked host buffers (pffft_aligned_malloc, cudaHostAlloc, cudaHostRegister) are mapped into the device's
+  // address space: with PFFFT_B200_ZEROCOPY=1 the kernels read and write them directly over PCIe (no staging copies)
+  if (zero_copy_enabled()) {
+    void *din_p = nullptr, *dout_p = nullptr;
+    if (host_mapped_pointer(in, &din_p) && host_mapped_pointer(out, &dout_p)) {
+      std::lock_guard<std::mutex> lock(s->mu);
+      cudaStream_t st = s->slot[0].stream;
+      const int rc = engine_transform_device<T, Hooks>(s, (const T*)din_p, (T*)dout_p, batch, direction, ordered, st);
+      if (rc) return rc;
+      PF_CUDA_OK(cudaStreamSynchronize(st));
+      return 0;
+    }
+  }
   return host_pipeline<T>(s, in, out, batch, [&](const T* di, T* dst_, long long nb, cudaStream_t st) {
     return engine_transform_device<T, Hooks>(s, di, dst_, nb, direction, ordered, st);
   });

@@ -24,6 +24,17 @@ bool ptr_is_device(const void* p) {
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+bool host_mapped_pointer(const void* p, void** dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+  *dev = a.devicePointer;
+  return true;
+}
+bool zero_copy_enabled() {
+  static const bool on = getenv("PFFFT_B200_ZEROCOPY") ? atoi(getenv("PFFFT_B200_ZEROCOPY")) != 0 : false;
+  return on;
+}
 }  // namespace pf
 
 // ---- aligned host memory.  Layout of one allocation: [raw ... | header(16 B: raw ptr, kind) | user (64-B aligned)]

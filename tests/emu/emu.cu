@@ -21,7 +21,7 @@ static void run_generic(XformParams<T> p) {
     int s = 1;
     for (int f = 0; f < p.nfac; ++f) {
       const int r = p.fac[f], m = p.Nc / r;
-      for (int b = 0; b < m; ++b) stockham_any<SIGN, T>(r, src, dst, b, p.Nc, s, p.tw);
+      for (int li = 0; li < 4; ++li) stockham_stage<SIGN, T>(r, src, dst, li, 4, p.Nc, s, p.magic[f], p.tw);   // 4 emulated lanes
       std::swap(src, dst); s *= r;
     }
     T* obase = p.out + t * p.out_stride;
@@ -40,7 +40,7 @@ static int emu_generic_t(int N, int transform, int dir, int lm, int sm, const T*
   XformParams<T> p{};
   p.N = N; p.Nc = transform == 0 ? N / 2 : N;
   auto f = pfplan::factorize(p.Nc);
-  p.nfac = (int)f.size(); for (int i = 0; i < p.nfac; ++i) p.fac[i] = f[i];
+  p.nfac = (int)f.size(); { int prod = 1; for (int i = 0; i < p.nfac; ++i) { p.fac[i] = f[i]; p.magic[i] = stage_magic(prod); prod *= f[i]; } }
   std::vector<T> tw(2 * (size_t)p.Nc), twr(2 * (size_t)(N / 2));
   pfplan::fill_roots<T>(tw.data(), p.Nc, p.Nc);
   pfplan::fill_roots<T>(twr.data(), N / 2, N);
