@@ -76,29 +76,54 @@ PF_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;
 PF_D cf ld_stream(const cf* p) { float2 t = __ldcs(reinterpret_cast<const float2*>(p)); return mk<float>(t.x, t.y); }
 PF_D void st_stream(cf* p, cf v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
 
-// store the finished transform: lane owns X[lane + 32*k1].  ZOUT selects the reference's
-// z-domain layout (4-lane groups: bins lane..lane+3 contiguous, re|im split) for pffft_transform.
+// store the finished transform: lane owns X[lane + 32*k1].  ZOUT selects the reference's z-domain layout
+// (pffft_transform): the z image is assembled in the warp's tile (4-byte scatters, granule-swizzled so they are
+// bank-conflict free) and leaves with coalesced 128-bit stores.
 template <bool ZOUT>
-PF_D void w1024_store(const cf (&v)[32], int lane, cf* dst) {
+PF_D void w1024_store(const cf (&v)[32], int lane, cf* dst, cf* tile) {
   if (!ZOUT) {
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) st_stream(dst + lane + 32 * k1, v[k1]);
   } else {
-    float* d = reinterpret_cast<float*>(dst);
+    float* tf = reinterpret_cast<float*>(tile);
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) {
       const int p = zpos_complex(lane + 32 * k1, 1024);
-      d[p] = v[k1].x; d[p + 4] = v[k1].y;
+      tf[zswz(p)] = v[k1].x; tf[zswz(p + 4)] = v[k1].y;
     }
+    __syncwarp();
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int e = 4 * (lane + 32 * j);                    // first float of granule lane + 32 j
+      __stcs(d4 + lane + 32 * j, *reinterpret_cast<const float4*>(tf + zswz(e)));
+    }
+    __syncwarp();
   }
 }
-// element loader for the first phase; ZIN gathers from the z-domain layout (backward unordered)
+// first-phase loader; ZIN: the whole z-domain transform is copied into the tile with coalesced 128-bit loads
+// (granule-swizzled), then every lane gathers its 32 points from there
 template <bool ZIN>
-PF_D cf w1024_ld(const cf* src, int idx) {
-  if (!ZIN) return ld_stream(src + idx);
-  const float* s = reinterpret_cast<const float*>(src);
-  const int p = zpos_complex(idx, 1024);
-  return mk<float>(s[p], s[p + 4]);
+PF_D void w1024_load(cf (&v)[32], int lane, const cf* src, cf* tile) {
+  if (!ZIN) {
+#pragma unroll
+    for (int p = 0; p < 32; ++p) v[p] = ld_stream(src + lane + 32 * brev5(p));
+  } else {
+    float* tf = reinterpret_cast<float*>(tile);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int e = 4 * (lane + 32 * j);
+      *reinterpret_cast<float4*>(tf + zswz(e)) = __ldcs(s4 + lane + 32 * j);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+      const int q = zpos_complex(lane + 32 * brev5(p), 1024);
+      v[p] = mk<float>(tf[zswz(q)], tf[zswz(q + 4)]);
+    }
+    __syncwarp();                                           // the tile is rewritten by the row phase
+  }
 }
 
 // ---------------------------------------------------------------- register-fed variant
@@ -115,13 +140,12 @@ k_c1024_ldg(const cf* __restrict__ in, cf* __restrict__ out, long long batch, co
   for (long long t = (long long)blockIdx.x * WARPS + warp; t < batch; t += stride) {
     const cf* src = in + t * 1024;
     cf v[32];
-#pragma unroll
-    for (int p = 0; p < 32; ++p) v[p] = w1024_ld<ZIN>(src, lane + 32 * brev5(p));
+    w1024_load<ZIN>(v, lane, src, tile);
     w1024_rows<SIGN>(v, lane, tw, tile);
     __syncwarp();
     w1024_cols<SIGN>(v, lane, tile);
     __syncwarp();                               // tile is rewritten by the next iteration
-    w1024_store<ZOUT>(v, lane, out + t * 1024);
+    w1024_store<ZOUT>(v, lane, out + t * 1024, tile);
   }
 }
 
@@ -160,8 +184,9 @@ k_c1024_bulk(const cf* __restrict__ in, cf* __restrict__ out, long long batch, c
     w1024_rows<SIGN>(v, lane, tw, buf);
     __syncwarp();
     w1024_cols<SIGN>(v, lane, buf);
-    __syncwarp();                               // tile consumed: hand the stage back to the TMA engine
-    if (lane == 0) {
+    __syncwarp();                               // tile consumed
+    if (ZOUT) w1024_store<true>(v, lane, out + t * 1024, buf);   // the z image is assembled in the stage: store first
+    if (lane == 0) {                            // hand the stage back to the TMA engine
       const long long tn = t + 2 * stride;
       if (tn < batch) {
         fence_proxy_async();                    // order our generic-proxy accesses before the async-proxy write
@@ -169,7 +194,7 @@ k_c1024_bulk(const cf* __restrict__ in, cf* __restrict__ out, long long batch, c
         bulk_g2s(buf, in + tn * 1024, 8192, &bars[s]);
       }
     }
-    w1024_store<ZOUT>(v, lane, out + t * 1024);
+    if (!ZOUT) w1024_store<false>(v, lane, out + t * 1024, buf);
   }
 }
 #endif  // __CUDACC__

@@ -51,11 +51,6 @@ template <typename T> struct XformParams {
 };
 
 // ------------------------------------------------------------------ element-wise load / store
-// z-domain positions inside a SHARED-MEMORY staging copy of a spectrum are XOR-swizzled at 16-byte-granule level
-// (element-index bits 2..4 ^= bits 5..7): consecutive bins land in 4-element groups 32 elements apart, which without
-// the swizzle all hit the same 4 banks.  Granules stay intact, so the global side is copied with plain 128-bit accesses.
-PF_HD int zswz(int p) { return p ^ (((p >> 5) & 7) << 2); }
-
 template <bool ZLAYOUT, bool REAL, bool SWZ = false, typename T> PF_HD cpx<T> spec_get(const T* base, int k, int N) {
   if (!ZLAYOUT) return reinterpret_cast<const cpx<T>*>(base)[k];
   const int p = zpos<REAL>(k, N);

@@ -35,6 +35,11 @@ PF_HD int zpos_real(int k, int N) {
   return 32 * (u >> 2) + 8 * q + (u & 3);
 }
 
+// z-domain positions inside a SHARED-MEMORY staging copy of a spectrum are XOR-swizzled at 16-byte-granule level
+// (element-index bits 2..4 ^= bits 5..7): consecutive bins land in 4-element groups 32 elements apart, which without
+// the swizzle all hit the same 4 banks.  Granules stay intact, so the global side is copied with plain 128-bit accesses.
+PF_HD int zswz(int p) { return p ^ (((p >> 5) & 7) << 2); }
+
 template <bool REAL> PF_HD int zpos(int c, int N) { return REAL ? zpos_real(c, N) : zpos_complex(c, N); }
 
 }  // namespace pf
