@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""sanitize_cases.py -- one small launch of every kernel family, for compute-sanitizer (memcheck / racecheck / initcheck).
+    compute-sanitizer --tool racecheck python tools/sanitize_cases.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pffft_b200 as pf
+rng = np.random.default_rng(0)
+def run(N, tr, dt=np.float32, batch=5):
+    per = N if tr == 0 else 2 * N
+    x = torch.from_numpy((rng.random((batch, per)) * 2 - 1).astype(dt)).cuda()
+    with pf.Setup(N, tr, dt) as s:
+        f = s.transform_batch(x, 0, True); z = s.transform_batch(x, 0, False)
+        b = s.transform_batch(f, 1, True); bz = s.transform_batch(z, 1, False)
+        r = s.zreorder_batch(z, 0); s.zreorder_batch(r, 1)
+        acc = torch.zeros_like(z); s.zconvolve_batch(z, z, acc, 0.5, True); s.zconvolve_batch(z, z[0].contiguous(), acc, 0.5, False, True)
+        torch.cuda.synchronize()
+        err = float((b / N - x).abs().max()); errz = float((bz / N - x).abs().max())
+        print("%-6d %-7s %-8s %-18s roundtrip %.1e / %.1e" % (N, "real" if tr == 0 else "cplx", np.dtype(dt).name, s.kernel, err, errz), flush=True)
+variant = os.environ.get("PFFFT_B200_C1024", "0")
+for N, tr in [(1024, 1), (64, 1), (256, 1), (32, 1), (512, 1), (2048, 1), (4096, 1), (1024, 0), (2048, 0), (4096, 0), (8192, 0),
+              (16, 1), (96, 1), (160, 0), (480, 1), (8192, 1), (16384, 0), (12000, 1)]:
+    run(N, tr)
+for N, tr in [(1024, 1), (4096, 0), (96, 1), (8192, 1)]:
+    run(N, tr, np.float64, 3)
+# overlap-save: fused (Nfft 1024, 8192) and three-launch (Nfft 256, 16384) paths, tail block, complex modes
+for taps, bl, n in [(100, 1024, 5000), (4097, 0, 40000), (31, 0, 3000), (200, 16384, 70000)]:
+    x = torch.from_numpy((np.arange(n) % 4093).astype(np.float32)).cuda(); y = torch.zeros(n + 64, device="cuda")
+    h = np.array([(-1.0, 1.0, 0.5)[j % 3] for j in range(taps)], np.float32)
+    for flags in (0, 1, 17):
+        fc = pf.FastConv(h, bl, flags)
+        got = fc.apply(x, y, n // (2 if flags & 1 else 1), 1)
+        torch.cuda.synchronize(); fc.close()
+        print("fastconv taps=%d Nfft=%d flags=%d produced=%d" % (taps, fc.block_len, flags, got), flush=True)
+print("done")
