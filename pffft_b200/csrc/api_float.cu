@@ -84,11 +84,44 @@ static int wsmall_R2_for(int N, int transform) {
   return N == 32 ? 1 : N == 64 ? 2 : N == 128 ? 4 : N == 256 ? 8 : 0;
 }
 
+// ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15})
+template <int R2, int SIGN, bool ZIN, bool ZOUT>
+static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+  constexpr int WARPS = 4, MINB = 4;
+  auto kern = k_warp_mixed<R2, SIGN, WARPS, MINB, ZIN, ZOUT>;
+  const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
+  const long long nchunks = (batch + (32 / R2) - 1) / (32 / R2);
+  long long ctas = (nchunks + WARPS - 1) / WARPS;
+  const long long cap = (long long)s->sm_count * MINB;
+  if (ctas > cap) ctas = cap;
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int SIGN, bool ZIN, bool ZOUT>
+static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st) {
+  switch (R2) {
+    case 3: return launch_wmixed<3, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 5: return launch_wmixed<5, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 6: return launch_wmixed<6, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 9: return launch_wmixed<9, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 10: return launch_wmixed<10, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 12: return launch_wmixed<12, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    default: return launch_wmixed<15, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+  }
+}
+static int wmixed_R2_for(int N, int transform) {
+  if (transform != XF_COMPLEX || N % 32) return 0;
+  const int r = N / 32;
+  return (r == 3 || r == 5 || r == 6 || r == 9 || r == 10 || r == 12 || r == 15) ? r : 0;
+}
+
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
-    if (wsmall_R2_for(N, transform)) return (size_t)N;
+    if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)N;
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
@@ -101,7 +134,7 @@ template <> struct FastHooks<float> {
         }
       return;
     }
-    if (const int R2 = wsmall_R2_for(N, transform)) {         // tw[k2*32 + l] = exp(-2 pi i l k2 / N)
+    if (const int R2 = wsmall_R2_for(N, transform) ? wsmall_R2_for(N, transform) : wmixed_R2_for(N, transform)) {   // tw[k2*32 + l] = exp(-2 pi i l k2 / N)
       for (int k2 = 0; k2 < R2; ++k2)
         for (int l = 0; l < 32; ++l) {
           long double c, sn;
@@ -118,6 +151,14 @@ template <> struct FastHooks<float> {
       if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
       s->fast_variant = v;
       s->kernel_name = kVariantName[v];
+      return true;
+    }
+    if (const int R2 = wmixed_R2_for(s->N, s->transform)) {
+      if (getenv("PFFFT_B200_NO_WMIXED")) return false;
+      static const char* names[16] = {"", "", "", "warp_32x3", "", "warp_32x5", "warp_32x6", "", "", "warp_32x9", "warp_32x10", "",
+                                      "warp_32x12", "", "", "warp_32x15"};
+      s->fast_variant = 400 + R2;
+      s->kernel_name = names[R2];
       return true;
     }
     if (const int R2 = wsmall_R2_for(s->N, s->transform)) {
@@ -137,6 +178,15 @@ template <> struct FastHooks<float> {
                                                    : run_c1024<-1, false, true>(s, in, out, batch, st);
       return ordered ? run_c1024<+1, false, false>(s, in, out, batch, st)
                      : run_c1024<+1, true, false>(s, in, out, batch, st);
+    }
+    if (s->fast_variant >= 400) {                           // non-power-of-two warp kernels: contiguous batches only
+      const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+      if (!plain) return -1;
+      const int R2 = s->fast_variant - 400;
+      if (direction == DIR_FORWARD) return ordered ? run_wmixed<-1, false, false>(s, R2, in, out, batch, st)
+                                                   : run_wmixed<-1, false, true>(s, R2, in, out, batch, st);
+      return ordered ? run_wmixed<+1, false, false>(s, R2, in, out, batch, st)
+                     : run_wmixed<+1, true, false>(s, R2, in, out, batch, st);
     }
     if (s->fast_variant >= 200 && s->fast_variant < 300) {  // small warp kernels: contiguous batches only
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;

@@ -290,4 +290,84 @@ k_warp_small(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
 }
 #endif
 
+
+// ---------------------------------------------------------------------------------------------
+// Non-power-of-two complex sizes N = 32*R2, R2 in {3,5,6,9,10,12,15} (N = 96,160,192,288,320,384,480): the warp
+// machinery again, with a mixed-radix register DFT (radix 3/5 butterflies) as the row transform.  A warp chunk holds
+// TW = floor(32/R2) transforms; lane l loads x_j[l + 32*n2]; phase A: TW DFTs of size R2 per lane, * W_N^{l k2},
+// tile[l][j*R2 + k2]; phase B: lanes c = (j,k2) < TW*R2 run the radix-32 column FFT -> X_j[k2 + R2*k1]; the result
+// goes back through the tile so that global stores are whole 256-byte rows.  tw[k2*32 + l] = exp(-2 pi i l k2 / N).
+// ---------------------------------------------------------------------------------------------
+template <int R2, int SIGN>
+PF_HD void wmixed_rows(cf (&v)[32], int lane, const cf* tw, cf* tile) {
+  constexpr int TW = 32 / R2;
+#pragma unroll
+  for (int j = 0; j < TW; ++j) dft_small<R2, SIGN>(&v[j * R2]);
+#pragma unroll
+  for (int m = 0; m < TW * R2; ++m) {
+    const int k2 = m % R2;
+    tile[lane * 33 + m] = (k2 == 0) ? v[m] : cmul_dir<SIGN>(v[m], tw[k2 * 32 + lane]);
+  }
+}
+
+#ifdef __CUDACC__
+template <int R2, int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g) {
+  constexpr int NC = 32 * R2;
+  constexpr int TW = 32 / R2;                   // transforms per warp chunk
+  constexpr int COLS = TW * R2;                 // active lanes in phase B
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cf* tw = reinterpret_cast<cf*>(pf_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf* tile = tw + NC + warp * kW1024Tile;
+  for (int i = threadIdx.x; i < NC; i += WARPS * 32) tw[i] = tw_g[i];
+  __syncthreads();
+  const long long nchunks = (batch + TW - 1) / TW;
+  const long long stride = (long long)gridDim.x * WARPS;
+  for (long long c = (long long)blockIdx.x * WARPS + warp; c < nchunks; c += stride) {
+    const cf* src = in + c * (TW * NC);
+    cf* dst = out + c * (TW * NC);
+    const long long left = batch - c * TW;
+    const int nvalid = left >= TW ? TW : (int)left;
+    cf v[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) v[m] = mk<float>(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) {
+        const int n = lane + 32 * n2;
+        if (j < nvalid) {
+          if (!ZIN) v[j * R2 + n2] = ld_stream(src + j * NC + n);
+          else { const float* sz = reinterpret_cast<const float*>(src + j * NC); const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(sz[q], sz[q + 4]); }
+        }
+      }
+    wmixed_rows<R2, SIGN>(v, lane, tw, tile);
+    __syncwarp();
+    w1024_cols<SIGN>(v, lane, tile);            // lanes >= COLS transform unused columns (harmless, never stored)
+    __syncwarp();
+    const int j = lane / R2, k2 = lane % R2;
+    const bool mine = lane < COLS && j < nvalid;
+    if (ZOUT) {
+      if (mine) {
+        float* d = reinterpret_cast<float*>(dst + j * NC);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); d[q] = v[k1].x; d[q + 4] = v[k1].y; }
+      }
+    } else {
+      if (mine) {
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) { const int e = j * NC + k2 + R2 * k1; tile[(e >> 5) * 33 + (e & 31)] = v[k1]; }
+      }
+      __syncwarp();
+      const int rows = nvalid * R2;
+#pragma unroll
+      for (int r = 0; r < COLS; ++r) if (r < rows) st_stream(dst + 32 * r + lane, tile[r * 33 + lane]);
+      __syncwarp();
+    }
+  }
+}
+#endif
+
 }  // namespace pf

@@ -207,3 +207,40 @@ extern "C" int emu_wsmall(int N, int dir, const float* in, float* out, long long
 #undef WS
   return -1;
 }
+
+// ---- non-power-of-two warp kernel phases (N = 32*R2)
+template <int R2, int SIGN> static void emu_wmixed_run(const float* in, float* out, long long batch) {
+  using namespace pf;
+  constexpr int NC = 32 * R2, TW = 32 / R2, COLS = TW * R2;
+  std::vector<cf> tw(NC);
+  for (int k2 = 0; k2 < R2; ++k2) for (int l = 0; l < 32; ++l) {
+    long double c, s; pfplan::unit_root((long long)l * k2, NC, &c, &s);
+    tw[k2 * 32 + l] = mk<float>((float)c, (float)s);
+  }
+  std::vector<cf> tile(kW1024Tile);
+  const long long nchunks = (batch + TW - 1) / TW;
+  for (long long c = 0; c < nchunks; ++c) {
+    const cf* src = reinterpret_cast<const cf*>(in) + c * (TW * NC);
+    cf* dst = reinterpret_cast<cf*>(out) + c * (TW * NC);
+    const long long left = batch - c * TW; const int nvalid = left >= TW ? TW : (int)left;
+    for (int lane = 0; lane < 32; ++lane) {
+      cf v[32];
+      for (int m = 0; m < 32; ++m) v[m] = mk<float>(0.f, 0.f);
+      for (int j = 0; j < TW; ++j) for (int n2 = 0; n2 < R2; ++n2) if (j < nvalid) v[j * R2 + n2] = src[j * NC + lane + 32 * n2];
+      wmixed_rows<R2, SIGN>(v, lane, tw.data(), tile.data());
+    }
+    std::vector<cf> res((size_t)TW * NC);
+    for (int lane = 0; lane < COLS; ++lane) {
+      cf v[32];
+      w1024_cols<SIGN>(v, lane, tile.data());
+      const int j = lane / R2, k2 = lane % R2;
+      if (j < nvalid) for (int k1 = 0; k1 < 32; ++k1) dst[j * NC + k2 + R2 * k1] = v[k1];
+    }
+  }
+}
+extern "C" int emu_wmixed(int N, int dir, const float* in, float* out, long long batch) {
+#define WM(r) if (N == 32 * r) { if (dir == 0) emu_wmixed_run<r, -1>(in, out, batch); else emu_wmixed_run<r, +1>(in, out, batch); return 0; }
+  WM(3) WM(5) WM(6) WM(9) WM(10) WM(12) WM(15)
+#undef WM
+  return -1;
+}

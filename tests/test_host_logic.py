@@ -150,3 +150,23 @@ def test_small_warp_kernel_phases(emu, ref, R):
                 got = o[: batch * 2 * N].reshape(batch, 2 * N)
                 assert max(R.relmax(got[i], w[i]) for i in range(batch)) <= 2e-6, (N, batch, d)
                 assert np.all(np.isnan(o[batch * 2 * N:])), "wrote beyond the batch"
+
+
+def test_mixed_radix_warp_kernel_phases(emu, ref, R):
+    """N = 32*R2, R2 in {3,5,6,9,10,12,15}: register radix-3/5 DFTs + radix-32 columns, stepped on the CPU"""
+    emu.emu_wmixed.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    rng = np.random.default_rng(5)
+    for r2 in (3, 5, 6, 9, 10, 12, 15):
+        N = 32 * r2
+        tw = 32 // r2
+        for batch in (1, tw, tw + 2):
+            x = uniform(rng, batch * 2 * N).reshape(batch, 2 * N)
+            nchunks = -(-batch // tw)
+            xin = np.zeros(nchunks * tw * 2 * N, np.float32); xin[: x.size] = x.ravel()
+            o = np.full_like(xin, np.nan)
+            for d in (0, 1):
+                assert emu.emu_wmixed(N, d, xin.ctypes.data, o.ctypes.data, batch) == 0
+                w = ref.transform_batch(N, 1, x, d, True)
+                got = o[: batch * 2 * N].reshape(batch, 2 * N)
+                assert max(R.relmax(got[i], w[i]) for i in range(batch)) <= 2e-6, (N, batch, d)
+                assert np.all(np.isnan(o[batch * 2 * N:])), "wrote beyond the batch"

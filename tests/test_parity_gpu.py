@@ -350,6 +350,8 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(1024, 1) as s:
         assert "c1024" in s.kernel
     with pf.Setup(96, 1) as s:
+        assert s.kernel == "warp_32x3"
+    with pf.Setup(800, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "split_16x4096"
