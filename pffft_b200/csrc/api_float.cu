@@ -84,7 +84,7 @@ static int wsmall_R2_for(int N, int transform) {
   return N == 32 ? 1 : N == 64 ? 2 : N == 128 ? 4 : N == 256 ? 8 : 0;
 }
 
-// ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15})
+// ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15,18,20,24,25,27,30})
 template <int R2, int SIGN, bool ZIN, bool ZOUT>
 static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
   constexpr int WARPS = 4, MINB = 4;
@@ -108,13 +108,20 @@ static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long
     case 9: return launch_wmixed<9, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
     case 10: return launch_wmixed<10, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
     case 12: return launch_wmixed<12, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    default: return launch_wmixed<15, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 15: return launch_wmixed<15, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 18: return launch_wmixed<18, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 20: return launch_wmixed<20, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 24: return launch_wmixed<24, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 25: return launch_wmixed<25, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    case 27: return launch_wmixed<27, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+    default: return launch_wmixed<30, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
   }
 }
 static int wmixed_R2_for(int N, int transform) {
   if (transform != XF_COMPLEX || N % 32) return 0;
   const int r = N / 32;
-  return (r == 3 || r == 5 || r == 6 || r == 9 || r == 10 || r == 12 || r == 15) ? r : 0;
+  switch (r) { case 3: case 5: case 6: case 9: case 10: case 12: case 15: case 18: case 20: case 24: case 25: case 27: case 30: return r; }
+  return 0;
 }
 
 template <> struct FastHooks<float> {
@@ -155,8 +162,8 @@ template <> struct FastHooks<float> {
     }
     if (const int R2 = wmixed_R2_for(s->N, s->transform)) {
       if (getenv("PFFFT_B200_NO_WMIXED")) return false;
-      static const char* names[16] = {"", "", "", "warp_32x3", "", "warp_32x5", "warp_32x6", "", "", "warp_32x9", "warp_32x10", "",
-                                      "warp_32x12", "", "", "warp_32x15"};
+      static char names[32][16];
+      snprintf(names[R2], sizeof(names[R2]), "warp_32x%d", R2);
       s->fast_variant = 400 + R2;
       s->kernel_name = names[R2];
       return true;

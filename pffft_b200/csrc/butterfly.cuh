@@ -159,8 +159,8 @@ template <int N, int SIGN, typename T> PF_HD void reg_fft(cpx<T> (&v)[N]) { dit_
 
 
 // ---------------------------------------------------------------------------------------------
-// Small mixed-radix register DFTs (R = 3,5,6,9,10,12,15) for the non-power-of-two warp kernels: one
-// Cooley-Tukey split R = R1 x R2 with compile-time twiddles, natural order in and out.
+// Small mixed-radix register DFTs (R = 3,5,6,9,10,12,15,18,20,24,25,27,30) for the non-power-of-two warp kernels:
+// (nested) Cooley-Tukey splits R = R1 x R2 with compile-time twiddles, natural order in and out.
 //   X[k1 + R1*k2] = sum_n2 W_R2^{n2 k2} * ( W_R^{n2 k1} * sum_n1 a[R2*n1 + n2] W_R1^{n1 k1} )
 // These are the register-resident counterparts of the reference's passf3_ps / passf5_ps
 // (src/pffft_priv_impl.h:151-183, :256-321).
@@ -173,12 +173,7 @@ template <int J, int N, int SIGN, typename T> PF_HD cpx<T> mul_root(cpx<T> x) { 
     return mk<T>(fma(x.x, c, -(x.y * s)), fma(x.x, s, x.y * c));
   }
 }
-template <int R, int SIGN, typename T> PF_HD void dft_prime(cpx<T>* a) {
-  if constexpr (R == 2) dft2<SIGN>(a);
-  else if constexpr (R == 3) dft3<SIGN>(a);
-  else if constexpr (R == 4) dft4<SIGN>(a);
-  else dft5<SIGN>(a);
-}
+template <int R, int SIGN, typename T> PF_HD void dft_small(cpx<T>* a);   // any supported size, defined below
 template <int R1, int R2, int SIGN, int I = 0, typename T> PF_HD void ct_twiddle(cpx<T>* b) {   // b[k1*R2 + n2] *= W_R^{n2 k1}
   if constexpr (I < R1 * R2) {
     constexpr int k1 = I / R2, n2 = I % R2;
@@ -193,7 +188,7 @@ template <int R1, int R2, int SIGN, typename T> PF_HD void dft_ct(cpx<T>* a) {
     cpx<T> t[R1];
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) t[n1] = a[R2 * n1 + n2];
-    dft_prime<R1, SIGN>(t);
+    dft_small<R1, SIGN>(t);
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) b[k1 * R2 + n2] = t[k1];
   }
@@ -203,18 +198,27 @@ template <int R1, int R2, int SIGN, typename T> PF_HD void dft_ct(cpx<T>* a) {
     cpx<T> t[R2];
 #pragma unroll
     for (int n2 = 0; n2 < R2; ++n2) t[n2] = b[k1 * R2 + n2];
-    dft_prime<R2, SIGN>(t);
+    dft_small<R2, SIGN>(t);
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) a[k1 + R1 * k2] = t[k2];
   }
 }
 template <int R, int SIGN, typename T> PF_HD void dft_small(cpx<T>* a) {
-  if constexpr (R == 3 || R == 5) dft_prime<R, SIGN>(a);
+  if constexpr (R == 2) dft2<SIGN>(a);
+  else if constexpr (R == 3) dft3<SIGN>(a);
+  else if constexpr (R == 4) dft4<SIGN>(a);
+  else if constexpr (R == 5) dft5<SIGN>(a);
   else if constexpr (R == 6) dft_ct<2, 3, SIGN>(a);
   else if constexpr (R == 9) dft_ct<3, 3, SIGN>(a);
   else if constexpr (R == 10) dft_ct<2, 5, SIGN>(a);
   else if constexpr (R == 12) dft_ct<4, 3, SIGN>(a);
-  else dft_ct<3, 5, SIGN>(a);                    // 15
+  else if constexpr (R == 15) dft_ct<3, 5, SIGN>(a);
+  else if constexpr (R == 18) dft_ct<2, 9, SIGN>(a);
+  else if constexpr (R == 20) dft_ct<4, 5, SIGN>(a);
+  else if constexpr (R == 24) dft_ct<4, 6, SIGN>(a);
+  else if constexpr (R == 25) dft_ct<5, 5, SIGN>(a);
+  else if constexpr (R == 27) dft_ct<3, 9, SIGN>(a);
+  else dft_ct<5, 6, SIGN>(a);                    // 30
 }
 
 }  // namespace pf

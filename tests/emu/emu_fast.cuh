@@ -240,7 +240,7 @@ template <int R2, int SIGN> static void emu_wmixed_run(const float* in, float* o
 }
 extern "C" int emu_wmixed(int N, int dir, const float* in, float* out, long long batch) {
 #define WM(r) if (N == 32 * r) { if (dir == 0) emu_wmixed_run<r, -1>(in, out, batch); else emu_wmixed_run<r, +1>(in, out, batch); return 0; }
-  WM(3) WM(5) WM(6) WM(9) WM(10) WM(12) WM(15)
+  WM(3) WM(5) WM(6) WM(9) WM(10) WM(12) WM(15) WM(18) WM(20) WM(24) WM(25) WM(27) WM(30)
 #undef WM
   return -1;
 }

@@ -156,7 +156,7 @@ def test_mixed_radix_warp_kernel_phases(emu, ref, R):
     """N = 32*R2, R2 in {3,5,6,9,10,12,15}: register radix-3/5 DFTs + radix-32 columns, stepped on the CPU"""
     emu.emu_wmixed.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
     rng = np.random.default_rng(5)
-    for r2 in (3, 5, 6, 9, 10, 12, 15):
+    for r2 in (3, 5, 6, 9, 10, 12, 15, 18, 20, 24, 25, 27, 30):
         N = 32 * r2
         tw = 32 // r2
         for batch in (1, tw, tw + 2):

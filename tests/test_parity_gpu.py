@@ -352,6 +352,8 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(96, 1) as s:
         assert s.kernel == "warp_32x3"
     with pf.Setup(800, 1) as s:
+        assert s.kernel == "warp_32x25"
+    with pf.Setup(4000, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "split_16x4096"
