@@ -230,6 +230,26 @@ PF_HD void wsmall_rows(cf (&v)[32], int lane, const cf* tw, cf* tile) {
 }
 
 #ifdef __CUDACC__
+
+#ifdef __CUDACC__
+// z-domain images of the `nvalid` transforms of a warp chunk, staged in the warp tile (granule-swizzled per transform)
+// and moved to / from global memory with coalesced 128-bit accesses.  NC complex points = 2*NC floats per transform.
+template <int NC> PF_D void chunk_z_out(const float* tf, float* dst, int nvalid, int lane) {
+  const int ngran = nvalid * (2 * NC) / 4;
+  for (int G = lane; G < ngran; G += 32) {
+    const int e = 4 * G, j = e / (2 * NC), p = e - j * (2 * NC);
+    __stcs(reinterpret_cast<float4*>(dst) + G, *reinterpret_cast<const float4*>(tf + j * (2 * NC) + zswz(p)));
+  }
+}
+template <int NC> PF_D void chunk_z_in(float* tf, const float* src, int nvalid, int lane) {
+  const int ngran = nvalid * (2 * NC) / 4;
+  for (int G = lane; G < ngran; G += 32) {
+    const int e = 4 * G, j = e / (2 * NC), p = e - j * (2 * NC);
+    *reinterpret_cast<float4*>(tf + j * (2 * NC) + zswz(p)) = __ldcs(reinterpret_cast<const float4*>(src) + G);
+  }
+}
+#endif
+
 // one warp = one 1024-point chunk = 32/R2 transforms; grid-stride over chunks.
 // ZIN / ZOUT: the transform's input / output is in the reference's z-domain layout (pffft_transform), so the
 // ordered and unordered entry points share one arithmetic path and stay bit-identical to each other.
@@ -252,6 +272,8 @@ k_warp_small(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     const long long left = batch - c * TW;      // transforms of this chunk that exist (>= 1)
     const int nvalid = left >= TW ? TW : (int)left;
     cf v[32];
+    float* tf = reinterpret_cast<float*>(tile);
+    if (ZIN) { chunk_z_in<NC>(tf, reinterpret_cast<const float*>(src), nvalid, lane); __syncwarp(); }
 #pragma unroll
     for (int j = 0; j < TW; ++j)
 #pragma unroll
@@ -259,8 +281,9 @@ k_warp_small(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
         const int n = lane + 32 * brevR2<R2>(p);                       // index inside transform j
         if (j >= nvalid) v[j * R2 + p] = mk<float>(0.f, 0.f);
         else if (!ZIN) v[j * R2 + p] = ld_stream(src + j * NC + n);
-        else { const float* sz = reinterpret_cast<const float*>(src + j * NC); const int q = zpos_complex(n, NC); v[j * R2 + p] = mk<float>(sz[q], sz[q + 4]); }
+        else { const int q = zpos_complex(n, NC); v[j * R2 + p] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
       }
+    if (ZIN) __syncwarp();
     wsmall_rows<R2, SIGN>(v, lane, tw, tile);
     __syncwarp();
     w1024_cols<SIGN>(v, lane, tile);            // column `lane` = (j = lane / R2, k2 = lane % R2)
@@ -268,10 +291,12 @@ k_warp_small(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     const int j = lane / R2, k2 = lane % R2;
     if (ZOUT) {
       if (j < nvalid) {
-        float* d = reinterpret_cast<float*>(dst + j * NC);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); d[q] = v[k1].x; d[q + 4] = v[k1].y; }
+        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); tf[j * 2 * NC + zswz(q)] = v[k1].x; tf[j * 2 * NC + zswz(q + 4)] = v[k1].y; }
       }
+      __syncwarp();
+      chunk_z_out<NC>(tf, reinterpret_cast<float*>(dst), nvalid, lane);
+      __syncwarp();
     } else if (R2 <= 2) {
       // 8/16-byte pieces per lane would scatter: go back through the tile and store whole 256-byte rows
 #pragma unroll
@@ -331,6 +356,8 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     const long long left = batch - c * TW;
     const int nvalid = left >= TW ? TW : (int)left;
     cf v[32];
+    float* tf = reinterpret_cast<float*>(tile);
+    if (ZIN) { chunk_z_in<NC>(tf, reinterpret_cast<const float*>(src), nvalid, lane); __syncwarp(); }
 #pragma unroll
     for (int m = 0; m < 32; ++m) v[m] = mk<float>(0.f, 0.f);
 #pragma unroll
@@ -340,9 +367,10 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
         const int n = lane + 32 * n2;
         if (j < nvalid) {
           if (!ZIN) v[j * R2 + n2] = ld_stream(src + j * NC + n);
-          else { const float* sz = reinterpret_cast<const float*>(src + j * NC); const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(sz[q], sz[q + 4]); }
+          else { const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
         }
       }
+    if (ZIN) __syncwarp();
     wmixed_rows<R2, SIGN>(v, lane, tw, tile);
     __syncwarp();
     w1024_cols<SIGN>(v, lane, tile);            // lanes >= COLS transform unused columns (harmless, never stored)
@@ -351,10 +379,12 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     const bool mine = lane < COLS && j < nvalid;
     if (ZOUT) {
       if (mine) {
-        float* d = reinterpret_cast<float*>(dst + j * NC);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); d[q] = v[k1].x; d[q + 4] = v[k1].y; }
+        for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); tf[j * 2 * NC + zswz(q)] = v[k1].x; tf[j * 2 * NC + zswz(q + 4)] = v[k1].y; }
       }
+      __syncwarp();
+      chunk_z_out<NC>(tf, reinterpret_cast<float*>(dst), nvalid, lane);
+      __syncwarp();
     } else {
       if (mine) {
 #pragma unroll
