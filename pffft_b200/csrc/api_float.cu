@@ -85,42 +85,46 @@ static int wsmall_R2_for(int N, int transform) {
 }
 
 // ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15,18,20,24,25,27,30})
-template <int R2, int SIGN, bool ZIN, bool ZOUT>
+template <int R2, int SIGN, bool ZIN, bool ZOUT, bool REAL>
 static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
   constexpr int WARPS = 4, MINB = 4;
-  auto kern = k_warp_mixed<R2, SIGN, WARPS, MINB, ZIN, ZOUT>;
+  auto kern = k_warp_mixed<R2, SIGN, WARPS, MINB, ZIN, ZOUT, REAL>;
   const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
   const long long nchunks = (batch + (32 / R2) - 1) / (32 / R2);
   long long ctas = (nchunks + WARPS - 1) / WARPS;
   const long long cap = (long long)s->sm_count * MINB;
   if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast, s->twr);
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-template <int SIGN, bool ZIN, bool ZOUT>
+template <int SIGN, bool ZIN, bool ZOUT, bool REAL>
 static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st) {
   switch (R2) {
-    case 3: return launch_wmixed<3, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 5: return launch_wmixed<5, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 6: return launch_wmixed<6, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 9: return launch_wmixed<9, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 10: return launch_wmixed<10, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 12: return launch_wmixed<12, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 15: return launch_wmixed<15, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 18: return launch_wmixed<18, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 20: return launch_wmixed<20, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 24: return launch_wmixed<24, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 25: return launch_wmixed<25, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 27: return launch_wmixed<27, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    default: return launch_wmixed<30, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
+#define PF_WM(r) case r: return launch_wmixed<r, SIGN, ZIN, ZOUT, REAL>(s, in, out, batch, st);
+    PF_WM(3) PF_WM(5) PF_WM(6) PF_WM(9) PF_WM(10) PF_WM(12) PF_WM(15) PF_WM(18) PF_WM(20) PF_WM(24) PF_WM(25) PF_WM(27) PF_WM(30)
+#undef PF_WM
+    default: break;
   }
+  if constexpr (REAL) {                                     // power-of-two packed lengths only exist as real plans here
+    switch (R2) {
+      case 1: return launch_wmixed<1, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
+      case 2: return launch_wmixed<2, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
+      case 4: return launch_wmixed<4, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
+      case 8: return launch_wmixed<8, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
+      default: break;
+    }
+  }
+  return -1;
 }
+// complex N = 32*R2 (non-pow2 R2) and real N = 64*R2 (any supported R2)
 static int wmixed_R2_for(int N, int transform) {
-  if (transform != XF_COMPLEX || N % 32) return 0;
-  const int r = N / 32;
+  const int Nc = transform == XF_REAL ? N / 2 : N;
+  if (Nc % 32) return 0;
+  const int r = Nc / 32;
   switch (r) { case 3: case 5: case 6: case 9: case 10: case 12: case 15: case 18: case 20: case 24: case 25: case 27: case 30: return r; }
+  if (transform == XF_REAL && (r == 1 || r == 2 || r == 4 || r == 8)) return r;
   return 0;
 }
 
@@ -128,7 +132,7 @@ template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
-    if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)N;
+    if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
@@ -141,11 +145,12 @@ template <> struct FastHooks<float> {
         }
       return;
     }
-    if (const int R2 = wsmall_R2_for(N, transform) ? wsmall_R2_for(N, transform) : wmixed_R2_for(N, transform)) {   // tw[k2*32 + l] = exp(-2 pi i l k2 / N)
+    if (const int R2 = wsmall_R2_for(N, transform) ? wsmall_R2_for(N, transform) : wmixed_R2_for(N, transform)) {   // tw[k2*32 + l] = exp(-2 pi i l k2 / Nc)
+      const int Nc = transform == XF_REAL ? N / 2 : N;
       for (int k2 = 0; k2 < R2; ++k2)
         for (int l = 0; l < 32; ++l) {
           long double c, sn;
-          pfplan::unit_root((long long)l * k2, N, &c, &sn);
+          pfplan::unit_root((long long)l * k2, Nc, &c, &sn);
           dst[2 * (k2 * 32 + l)] = (float)c; dst[2 * (k2 * 32 + l) + 1] = (float)sn;
         }
       return;
@@ -162,10 +167,11 @@ template <> struct FastHooks<float> {
     }
     if (const int R2 = wmixed_R2_for(s->N, s->transform)) {
       if (getenv("PFFFT_B200_NO_WMIXED")) return false;
-      static char names[32][16];
-      snprintf(names[R2], sizeof(names[R2]), "warp_32x%d", R2);
+      static char names[64][20];
+      const int slot = R2 + (s->transform == XF_REAL ? 32 : 0);
+      snprintf(names[slot], sizeof(names[slot]), s->transform == XF_REAL ? "warp_real_32x%d" : "warp_32x%d", R2);
+      s->kernel_name = names[slot];
       s->fast_variant = 400 + R2;
-      s->kernel_name = names[R2];
       return true;
     }
     if (const int R2 = wsmall_R2_for(s->N, s->transform)) {
@@ -190,10 +196,16 @@ template <> struct FastHooks<float> {
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
       if (!plain) return -1;
       const int R2 = s->fast_variant - 400;
-      if (direction == DIR_FORWARD) return ordered ? run_wmixed<-1, false, false>(s, R2, in, out, batch, st)
-                                                   : run_wmixed<-1, false, true>(s, R2, in, out, batch, st);
-      return ordered ? run_wmixed<+1, false, false>(s, R2, in, out, batch, st)
-                     : run_wmixed<+1, true, false>(s, R2, in, out, batch, st);
+      if (s->transform == XF_REAL) {
+        if (direction == DIR_FORWARD) return ordered ? run_wmixed<-1, false, false, true>(s, R2, in, out, batch, st)
+                                                     : run_wmixed<-1, false, true, true>(s, R2, in, out, batch, st);
+        return ordered ? run_wmixed<+1, false, false, true>(s, R2, in, out, batch, st)
+                       : run_wmixed<+1, true, false, true>(s, R2, in, out, batch, st);
+      }
+      if (direction == DIR_FORWARD) return ordered ? run_wmixed<-1, false, false, false>(s, R2, in, out, batch, st)
+                                                   : run_wmixed<-1, false, true, false>(s, R2, in, out, batch, st);
+      return ordered ? run_wmixed<+1, false, false, false>(s, R2, in, out, batch, st)
+                     : run_wmixed<+1, true, false, false>(s, R2, in, out, batch, st);
     }
     if (s->fast_variant >= 200 && s->fast_variant < 300) {  // small warp kernels: contiguous batches only
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;

@@ -208,7 +208,9 @@ template <int R, int SIGN, typename T> PF_HD void dft_small(cpx<T>* a) {
   else if constexpr (R == 3) dft3<SIGN>(a);
   else if constexpr (R == 4) dft4<SIGN>(a);
   else if constexpr (R == 5) dft5<SIGN>(a);
+  else if constexpr (R == 1) { }
   else if constexpr (R == 6) dft_ct<2, 3, SIGN>(a);
+  else if constexpr (R == 8) dft_ct<2, 4, SIGN>(a);
   else if constexpr (R == 9) dft_ct<3, 3, SIGN>(a);
   else if constexpr (R == 10) dft_ct<2, 5, SIGN>(a);
   else if constexpr (R == 12) dft_ct<4, 3, SIGN>(a);

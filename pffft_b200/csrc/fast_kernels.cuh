@@ -335,10 +335,16 @@ PF_HD void wmixed_rows(cf (&v)[32], int lane, const cf* tw, cf* tile) {
   }
 }
 
+// real transforms on the same kernel (REAL): N = 64*R2 real points are NC = 32*R2 packed complex points
+// (z[i] = x[2i] + i x[2i+1]); the rotation that turns the packed spectrum into the real one (and back) is applied
+// while the chunk sits in the warp tile:  X[k] = ((s.x + u.y), (s.y - u.x))/2,  s = Z[k] + conj Z[NC-k],
+// u = W_N^k (Z[k] - conj Z[NC-k]);   Z'[i] = (s.x - u.y, s.y + u.x),  s = X[i] + conj X[NC-i], u = conj(W_N^i)(X[i] - conj X[NC-i]).
+template <int NC> PF_HD int chunk_tile_idx(int j, int k) { const int e = j * NC + k; return (e >> 5) * 33 + (e & 31); }
+
 #ifdef __CUDACC__
-template <int R2, int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
+template <int R2, int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT, bool REAL>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g) {
+k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g, const cf* __restrict__ twr) {
   constexpr int NC = 32 * R2;
   constexpr int TW = 32 / R2;                   // transforms per warp chunk
   constexpr int COLS = TW * R2;                 // active lanes in phase B
@@ -355,29 +361,94 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     cf* dst = out + c * (TW * NC);
     const long long left = batch - c * TW;
     const int nvalid = left >= TW ? TW : (int)left;
+    const int rows = nvalid * R2;               // 32-element rows of the chunk that hold existing transforms
     cf v[32];
     float* tf = reinterpret_cast<float*>(tile);
-    if (ZIN) { chunk_z_in<NC>(tf, reinterpret_cast<const float*>(src), nvalid, lane); __syncwarp(); }
 #pragma unroll
     for (int m = 0; m < 32; ++m) v[m] = mk<float>(0.f, 0.f);
+    if (REAL && SIGN > 0) {
+      // ---- backward real: spectrum (canonical or z-domain) -> tile -> packed half-length spectrum Z'
+      if (ZIN) chunk_z_in<NC>(tf, reinterpret_cast<const float*>(src), nvalid, lane);
+      else {
 #pragma unroll
-    for (int j = 0; j < TW; ++j)
-#pragma unroll
-      for (int n2 = 0; n2 < R2; ++n2) {
-        const int n = lane + 32 * n2;
-        if (j < nvalid) {
-          if (!ZIN) v[j * R2 + n2] = ld_stream(src + j * NC + n);
-          else { const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
-        }
+        for (int r = 0; r < COLS; ++r) if (r < rows) tile[r * 33 + lane] = ld_stream(src + 32 * r + lane);
       }
-    if (ZIN) __syncwarp();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < TW; ++j)
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+          if (j >= nvalid) continue;
+          const int i = lane + 32 * n2;
+          auto X = [&](int k) -> cf {
+            if (ZIN) { const int q = zpos_real(k, 2 * NC); return mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
+            return tile[chunk_tile_idx<NC>(j, k)];
+          };
+          if (i == 0) { const cf s0 = X(0); v[j * R2 + n2] = mk<float>(s0.x + s0.y, s0.x - s0.y); }
+          else {
+            const cf a = X(i), b = conj(X(NC - i));
+            const cf s = a + b, d = a - b;
+            const float2 wv = __ldg(reinterpret_cast<const float2*>(twr + i));
+            const cf u = cmul_dir<+1>(d, mk<float>(wv.x, wv.y));
+            v[j * R2 + n2] = mk<float>(s.x - u.y, s.y + u.x);
+          }
+        }
+      __syncwarp();
+    } else {
+      if (ZIN) { chunk_z_in<NC>(tf, reinterpret_cast<const float*>(src), nvalid, lane); __syncwarp(); }
+#pragma unroll
+      for (int j = 0; j < TW; ++j)
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+          const int n = lane + 32 * n2;
+          if (j < nvalid) {
+            if (!ZIN) v[j * R2 + n2] = ld_stream(src + j * NC + n);
+            else { const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
+          }
+        }
+      if (ZIN) __syncwarp();
+    }
     wmixed_rows<R2, SIGN>(v, lane, tw, tile);
     __syncwarp();
     w1024_cols<SIGN>(v, lane, tile);            // lanes >= COLS transform unused columns (harmless, never stored)
     __syncwarp();
     const int j = lane / R2, k2 = lane % R2;
     const bool mine = lane < COLS && j < nvalid;
-    if (ZOUT) {
+    if (REAL && SIGN < 0) {
+      // ---- forward real: packed spectrum Z -> tile (natural order) -> X, canonical or z-domain
+      if (mine) {
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) tile[chunk_tile_idx<NC>(j, k2 + R2 * k1)] = v[k1];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < COLS; ++r) {
+        if (r >= rows) continue;
+        const int e = 32 * r + lane, jj = e / NC, k = e - jj * NC;
+        cf x;
+        if (k == 0) { const cf z0 = tile[chunk_tile_idx<NC>(jj, 0)]; x = mk<float>(z0.x + z0.y, z0.x - z0.y); }
+        else {
+          const cf a = tile[chunk_tile_idx<NC>(jj, k)], b = conj(tile[chunk_tile_idx<NC>(jj, NC - k)]);
+          const float2 wv = __ldg(reinterpret_cast<const float2*>(twr + k));
+          const cf s = a + b, d = a - b, u = cmul(d, mk<float>(wv.x, wv.y));
+          x = mk<float>(0.5f * (s.x + u.y), 0.5f * (s.y - u.x));
+        }
+        if (!ZOUT) st_stream(dst + e, x); else v[r] = x;
+      }
+      if (ZOUT) {
+        __syncwarp();                           // every lane has read its Z values: the tile becomes the z image
+#pragma unroll
+        for (int r = 0; r < COLS; ++r) {
+          if (r >= rows) continue;
+          const int e = 32 * r + lane, jj = e / NC, k = e - jj * NC;
+          const int q = zpos_real(k, 2 * NC);
+          tf[jj * 2 * NC + zswz(q)] = v[r].x; tf[jj * 2 * NC + zswz(q + 4)] = v[r].y;
+        }
+        __syncwarp();
+        chunk_z_out<NC>(tf, reinterpret_cast<float*>(dst), nvalid, lane);
+      }
+      __syncwarp();
+    } else if (ZOUT) {
       if (mine) {
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) { const int q = zpos_complex(k2 + R2 * k1, NC); tf[j * 2 * NC + zswz(q)] = v[k1].x; tf[j * 2 * NC + zswz(q + 4)] = v[k1].y; }
@@ -388,10 +459,9 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
     } else {
       if (mine) {
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) { const int e = j * NC + k2 + R2 * k1; tile[(e >> 5) * 33 + (e & 31)] = v[k1]; }
+        for (int k1 = 0; k1 < 32; ++k1) tile[chunk_tile_idx<NC>(j, k2 + R2 * k1)] = v[k1];
       }
       __syncwarp();
-      const int rows = nvalid * R2;
 #pragma unroll
       for (int r = 0; r < COLS; ++r) if (r < rows) st_stream(dst + 32 * r + lane, tile[r * 33 + lane]);
       __syncwarp();

@@ -400,3 +400,28 @@ def test_every_c1024_variant_is_correct(pf, ref, R, variant, monkeypatch):
     W = np.fft.fft(cx, axis=1)
     got = f_[:, 0::2] + 1j * f_[:, 1::2]
     assert np.max(np.abs(got - W)) / np.max(np.abs(W)) <= 1e-5
+
+
+@pytest.mark.parametrize("r2", [1, 2, 4, 8, 3, 5, 6, 9, 10, 12, 15, 18, 20, 24, 25, 27, 30])
+def test_warp_family_real_sizes(pf, ref, R, r2):
+    """real N = 64*R2 on the warp kernels (packed N/2-point core + in-tile rotation): ordered and z-domain, forward
+    and backward, partial last chunk, and ordered == zreorder(unordered) bit-exact"""
+    torch = torch_mod()
+    N = 64 * r2
+    rng = np.random.default_rng(r2)
+    batch = 2 * (32 // r2) + 1
+    x = uniform(rng, batch * N).reshape(batch, N)
+    with pf.Setup(N, 0) as s:
+        assert s.kernel == "warp_real_32x%d" % r2
+        xd = torch.from_numpy(x).cuda()
+        fo = s.transform_batch(xd, 0, True); fz = s.transform_batch(xd, 0, False)
+        bo = s.transform_batch(fo, 1, True); bz = s.transform_batch(fz, 1, False)
+        ro = s.zreorder_batch(fz, 0)
+        torch.cuda.synchronize()
+        assert torch.equal(ro, fo)
+        fo_, fz_, bo_, bz_ = [t.cpu().numpy() for t in (fo, fz, bo, bz)]
+    idx = [0, 1, batch // 2, batch - 1]
+    wo = ref.transform_batch(N, 0, x[idx], 0, True); wz = ref.transform_batch(N, 0, x[idx], 0, False)
+    for j, i in enumerate(idx):
+        assert R.relmax(fo_[i], wo[j]) <= 1e-5 and R.relmax(fz_[i], wz[j]) <= 1e-5
+        assert R.relmax(bo_[i], x[i] * N) <= 1e-5 and R.relmax(bz_[i], x[i] * N) <= 1e-5

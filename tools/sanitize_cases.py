@@ -19,7 +19,8 @@ def run(N, tr, dt=np.float32, batch=5):
         print("%-6d %-7s %-8s %-18s roundtrip %.1e / %.1e" % (N, "real" if tr == 0 else "cplx", np.dtype(dt).name, s.kernel, err, errz), flush=True)
 variant = os.environ.get("PFFFT_B200_C1024", "0")
 for N, tr in [(1024, 1), (64, 1), (256, 1), (32, 1), (512, 1), (2048, 1), (4096, 1), (1024, 0), (2048, 0), (4096, 0), (8192, 0),
-              (16, 1), (96, 1), (160, 0), (480, 1), (8192, 1), (16384, 0), (12000, 1)]:
+              (16, 1), (96, 1), (160, 0), (480, 1), (8192, 1), (16384, 0), (12000, 1),
+              (64, 0), (192, 0), (512, 0), (960, 0), (1920, 0), (800, 1), (128, 1), (48, 1), (4000, 1)]:
     run(N, tr)
 for N, tr in [(1024, 1), (4096, 0), (96, 1), (8192, 1)]:
     run(N, tr, np.float64, 3)
