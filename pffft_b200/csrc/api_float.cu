@@ -86,7 +86,7 @@ static int wsmall_R2_for(int N, int transform) {
 
 // ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15,18,20,24,25,27,30})
 template <int R2, int SIGN, bool ZIN, bool ZOUT, bool REAL>
-static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
+static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st, int grp = 1) {
   constexpr int WARPS = 4, MINB = 4;
   auto kern = k_warp_mixed<R2, SIGN, WARPS, MINB, ZIN, ZOUT, REAL>;
   const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
@@ -94,15 +94,15 @@ static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long
   long long ctas = (nchunks + WARPS - 1) / WARPS;
   const long long cap = (long long)s->sm_count * MINB;
   if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast, s->twr);
+  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast, s->twr, grp);
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 template <int SIGN, bool ZIN, bool ZOUT, bool REAL>
-static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st) {
+static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st, int grp = 1) {
   switch (R2) {
-#define PF_WM(r) case r: return launch_wmixed<r, SIGN, ZIN, ZOUT, REAL>(s, in, out, batch, st);
+#define PF_WM(r) case r: return launch_wmixed<r, SIGN, ZIN, ZOUT, REAL>(s, in, out, batch, st, grp);
     PF_WM(3) PF_WM(5) PF_WM(6) PF_WM(9) PF_WM(10) PF_WM(12) PF_WM(15) PF_WM(18) PF_WM(20) PF_WM(24) PF_WM(25) PF_WM(27) PF_WM(30)
 #undef PF_WM
     default: break;
@@ -128,11 +128,28 @@ static int wmixed_R2_for(int N, int transform) {
   return 0;
 }
 
+// ---- rows of two-pass (split) float plans: CTA kernel sizes or complex warp-kernel sizes 32*R2
+static int wmixed_complex_R2(int n) { return wmixed_R2_for(n, XF_COMPLEX); }
+static bool is_float_row_size(int n) { return cta_C_for(n) != 0 || wmixed_complex_R2(n) != 0; }
+template <int SIGN>
+static int split_rows_float(Setup<float>* s, const cf* src, cf* rows, long long batch, cudaStream_t st) {
+  if (cta_C_for(s->split_N2)) return split_rows_cta<float, SIGN>(s, src, rows, batch, st);
+  return run_wmixed<SIGN, false, false, false>(s, wmixed_complex_R2(s->split_N2), reinterpret_cast<const float*>(src),
+                                               reinterpret_cast<float*>(rows), batch * s->split_R, st, s->split_R);
+}
+static bool float_split_for(int N, int transform, int* R, int* N2) {
+  const int Nc = transform == XF_REAL ? N / 2 : N;
+  if (Nc <= 1024 && transform == XF_COMPLEX && Nc == 1024) return false;
+  return split_choose(Nc, is_float_row_size, R, N2);
+}
+
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
+    { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
+      if (!cta_C_for(Nc) && float_split_for(N, transform, &R, &N2)) return cta_C_for(N2) ? cta_table_cpx(N2) : (size_t)N2; }
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
@@ -155,6 +172,18 @@ template <> struct FastHooks<float> {
         }
       return;
     }
+    { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
+      if (!cta_C_for(Nc) && float_split_for(N, transform, &R, &N2)) {
+        if (cta_C_for(N2)) { cta_fill_tables<float>(N2, dst); return; }
+        const int R2 = wmixed_complex_R2(N2);                 // warp rows: tw[k2*32 + l] = exp(-2 pi i l k2 / N2)
+        for (int k2 = 0; k2 < R2; ++k2)
+          for (int l = 0; l < 32; ++l) {
+            long double c, sn;
+            pfplan::unit_root((long long)l * k2, N2, &c, &sn);
+            dst[2 * (k2 * 32 + l)] = (float)c; dst[2 * (k2 * 32 + l) + 1] = (float)sn;
+          }
+        return;
+      } }
     CtaOnlyHooks<float>::fill_extra_table(N, transform, dst);
   }
   static bool plan(Setup<float>* s) {
@@ -180,6 +209,14 @@ template <> struct FastHooks<float> {
       s->kernel_name = R2 == 1 ? "warp_32x1" : R2 == 2 ? "warp_32x2" : R2 == 4 ? "warp_32x4" : "warp_32x8";
       return true;
     }
+    { int R = 0, N2 = 0;
+      if (!cta_C_for(s->Nc) && !getenv("PFFFT_B200_NO_SPLIT") && float_split_for(s->N, s->transform, &R, &N2)) {
+        s->split_R = R; s->split_N2 = N2;
+        s->fast_variant = 300;
+        snprintf(s->name_buf, sizeof(s->name_buf), "split_%dx%d", R, N2);
+        s->kernel_name = s->name_buf;
+        return true;
+      } }
     return CtaOnlyHooks<float>::plan(s);
   }
   static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
@@ -215,6 +252,10 @@ template <> struct FastHooks<float> {
                                                    : run_wsmall<-1, false, true>(s, R2, in, out, batch, st);
       return ordered ? run_wsmall<+1, false, false>(s, R2, in, out, batch, st)
                      : run_wsmall<+1, true, false>(s, R2, in, out, batch, st);
+    }
+    if (s->fast_variant >= 300 && s->fast_variant < 400) {
+      const XformParams<float> p = make_params(s, in, out, batch, o);
+      return run_split<float>(s, split_rows_float<-1>, split_rows_float<+1>, p, direction, ordered, st);
     }
     return CtaOnlyHooks<float>::run(s, in, out, batch, direction, ordered, st, o);
   }

@@ -90,35 +90,48 @@ int run_cta_any(Setup<T>* s, int C, const XformParams<T>& p, int direction, int 
 }
 
 
-// ---------------------------------------------------------------- large N: Nc = R x 4096, R in {2,4,8,16}
-// (complex N = 8192..65536, real N = 16384..131072).  Decimation in time over the first digit:
-//   rows   : R launches of the 16x16x16 CTA kernel, row n1 = FFT_4096 of x[n1 + R*n2] (element stride R)
-//   combine: k_split_combine finishes with the radix-R butterflies and writes X in natural order.
-// Two HBM round trips (plus one for a real pre-/post-rotation or z-domain pass): ceiling 0.5 of the roofline,
-// against (stages+2) round trips of the global Stockham path it replaces.
-inline int split_R_for(int Nc) { return Nc == 8192 ? 2 : Nc == 16384 ? 4 : Nc == 32768 ? 8 : Nc == 65536 ? 16 : 0; }
-inline const char* split_name(int R) { return R == 2 ? "split_2x4096" : R == 4 ? "split_4x4096" : R == 8 ? "split_8x4096" : "split_16x4096"; }
+// ---------------------------------------------------------------- two-pass plans: Nc = R x N2
+// Sizes without a single-kernel path (complex cores > 4096, non-power-of-two cores > 1024) are split by decimation in
+// time over the first digit:
+//   rows   : ONE launch of a tuned kernel over batch*R rows; row n1 of a transform = FFT_N2 of x[n1 + R*n2] (element
+//            stride R; consecutive CTAs/warps take the R sub-sequences of the same transform so their strided reads of
+//            the same 128-byte lines meet in L2)
+//   combine: radix-R register DFTs with W_Nc^{n1 k2} twiddles finish the transform in natural order (coalesced).
+// Two HBM round trips (plus one for a real pre-/post-rotation or z-domain pass): ceiling 0.5 of the roofline, against
+// (stages+2) round trips of the global Stockham path it replaces.  R is any size of the register DFT library
+// (2,3,4,5,6,8,9,10,12,15,16); N2 is a CTA-kernel size (512..4096) or, for float, a warp-kernel size 32*R2.
+static const int kSplitRadices[] = {2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16};
+template <typename IsRow> inline bool split_choose(int Nc, IsRow is_row_size, int* R, int* N2) {
+  for (int r : kSplitRadices) if (Nc % r == 0 && is_row_size(Nc / r)) { *R = r; *N2 = Nc / r; return true; }
+  return false;
+}
 
 template <typename T, int SIGN>
-int split_core(Setup<T>* s, int R, const cpx<T>* src, cpx<T>* rows, cpx<T>* dst, long long batch, cudaStream_t st) {
-  constexpr int N2 = 4096;
-  // ONE launch over batch*R rows: consecutive CTAs take the R interleaved sub-sequences of the same transform, so
-  // their stride-R reads of the same 128-byte lines meet in L2 instead of re-reading DRAM R times
+int split_rows_cta(Setup<T>* s, const cpx<T>* src, cpx<T>* rows, long long batch, cudaStream_t st) {
+  const int R = s->split_R, N2 = s->split_N2;
   XformParams<T> q;
   q.in = reinterpret_cast<const T*>(src); q.out = reinterpret_cast<T*>(rows);
   q.in_stride = 2LL * s->Nc; q.in_group = R; q.in_gstep = 2; q.in_estride = R;
   q.out_stride = 2LL * N2; q.in_limit = -1; q.out_count = 2 * N2;
-  q.batch = batch * R; q.N = N2; q.Nc = N2; q.nfac = 0; q.tw = s->tw; q.twr = nullptr;
+  q.batch = batch * R; q.N = N2; q.Nc = N2; q.nfac = 0; q.tw = s->tw; q.twr = nullptr; q.magic_nc = 0;
   for (int i = 0; i < PF_MAX_FACTORS; ++i) { q.fac[i] = 1; q.magic[i] = 0; }
-  q.magic_nc = 0;
-  { const int rc = launch_cta_v<T, 16, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st); if (rc) return rc; }
+  switch (cta_C_for(N2)) {
+    case 2: return launch_cta_v<T, 2, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st);
+    case 4: return launch_cta_v<T, 4, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st);
+    case 8: return launch_cta_v<T, 8, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st);
+    default: return launch_cta_v<T, 16, L_C_ORD, S_C_ORD, SIGN, false>(s, q, st);
+  }
+}
+template <typename T, int SIGN>
+int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch, cudaStream_t st) {
+  const int R = s->split_R, N2 = s->split_N2;
   const long long work = batch * N2;
   long long g = (work + 255) / 256; const long long cap = (long long)s->sm_count * 16;
   if (g > cap) g = cap; if (g < 1) g = 1;
   switch (R) {
-    case 2: k_split_combine<T, 2, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
-    case 4: k_split_combine<T, 4, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
-    case 8: k_split_combine<T, 8, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+#define PF_CMB(r) case r: k_split_combine_any<T, r, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+    PF_CMB(2) PF_CMB(3) PF_CMB(4) PF_CMB(5) PF_CMB(6) PF_CMB(8) PF_CMB(9) PF_CMB(10) PF_CMB(12) PF_CMB(15)
+#undef PF_CMB
     default: k_split_combine<T, 16, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
   }
   count_launch();
@@ -126,8 +139,9 @@ int split_core(Setup<T>* s, int R, const cpx<T>* src, cpx<T>* rows, cpx<T>* dst,
   return 0;
 }
 
-template <typename T, int LM, int SM, int SIGN>
-int run_split_modes(Setup<T>* s, int R, const XformParams<T>& p, cudaStream_t st) {
+// Rows: functor (Setup*, src, rows, batch, stream) -> rc, chosen by the caller for the direction SIGN
+template <typename T, int LM, int SM, int SIGN, typename Rows>
+int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(s->scratch_mu);
   { const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st); if (rc) return rc; }
   const long long total = p.batch * (long long)s->Nc;
@@ -144,8 +158,8 @@ int run_split_modes(Setup<T>* s, int R, const XformParams<T>& p, cudaStream_t st
     src = s->d_scratch[0];
   }
   cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
-  const int rc = split_core<T, SIGN>(s, R, src, s->d_scratch[1], dst, p.batch, st);
-  if (rc) return rc;
+  { const int rc = rows_fn(s, src, s->d_scratch[1], p.batch, st); if (rc) return rc; }
+  { const int rc = split_combine<T, SIGN>(s, s->d_scratch[1], dst, p.batch, st); if (rc) return rc; }
   if (!direct_out) {
     k_glob_store<T, SM><<<(int)g, 256, 0, st>>>(p, s->d_scratch[0]);
     count_launch();
@@ -154,32 +168,45 @@ int run_split_modes(Setup<T>* s, int R, const XformParams<T>& p, cudaStream_t st
   PF_CUDA_OK(cudaEventRecord(s->scratch_done, st));
   return 0;
 }
-template <typename T>
-int run_split(Setup<T>* s, int R, const XformParams<T>& p, int direction, int ordered, cudaStream_t st) {
+// RowsF / RowsB: row launchers for the forward / backward direction
+template <typename T, typename RowsF, typename RowsB>
+int run_split(Setup<T>* s, RowsF rf, RowsB rb, const XformParams<T>& p, int direction, int ordered, cudaStream_t st) {
   const bool fwd = direction == DIR_FORWARD;
   if (s->transform == XF_COMPLEX) {
-    if (fwd) return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, -1>(s, R, p, st) : run_split_modes<T, L_C_ORD, S_C_Z, -1>(s, R, p, st);
-    return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, +1>(s, R, p, st) : run_split_modes<T, L_C_Z, S_C_ORD, +1>(s, R, p, st);
+    if (fwd) return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, -1>(s, rf, p, st) : run_split_modes<T, L_C_ORD, S_C_Z, -1>(s, rf, p, st);
+    return ordered ? run_split_modes<T, L_C_ORD, S_C_ORD, +1>(s, rb, p, st) : run_split_modes<T, L_C_Z, S_C_ORD, +1>(s, rb, p, st);
   }
-  if (fwd) return ordered ? run_split_modes<T, L_R_TIME, S_R_ORD, -1>(s, R, p, st) : run_split_modes<T, L_R_TIME, S_R_Z, -1>(s, R, p, st);
-  return ordered ? run_split_modes<T, L_R_ORD, S_R_TIME, +1>(s, R, p, st) : run_split_modes<T, L_R_Z, S_R_TIME, +1>(s, R, p, st);
+  if (fwd) return ordered ? run_split_modes<T, L_R_TIME, S_R_ORD, -1>(s, rf, p, st) : run_split_modes<T, L_R_TIME, S_R_Z, -1>(s, rf, p, st);
+  return ordered ? run_split_modes<T, L_R_ORD, S_R_TIME, +1>(s, rb, p, st) : run_split_modes<T, L_R_Z, S_R_TIME, +1>(s, rb, p, st);
 }
+inline bool is_cta_row_size(int n) { return cta_C_for(n) != 0; }
 
 // hooks for a precision whose only tuned kernels are the CTA ones (double)
 template <typename T> struct CtaOnlyHooks {
+  static int rows_size(int N, int transform) {               // N2 of the split plan, 0 if the size is not split
+    const int Nc = transform == XF_REAL ? N / 2 : N;
+    int R = 0, N2 = 0;
+    if (cta_C_for(Nc) || !split_choose(Nc, is_cta_row_size, &R, &N2)) return 0;
+    return N2;
+  }
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    return split_R_for(Nc) ? cta_table_cpx(4096) : cta_table_cpx(Nc);
+    const int n2 = rows_size(N, transform);
+    return n2 ? cta_table_cpx(n2) : cta_table_cpx(Nc);
   }
   static void fill_extra_table(int N, int transform, T* dst) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    cta_fill_tables<T>(split_R_for(Nc) ? 4096 : Nc, dst);
+    const int n2 = rows_size(N, transform);
+    cta_fill_tables<T>(n2 ? n2 : Nc, dst);
   }
   static bool plan(Setup<T>* s) {
-    if (const int R = split_R_for(s->Nc)) {
+    int R = 0, N2 = 0;
+    if (!cta_C_for(s->Nc) && split_choose(s->Nc, is_cta_row_size, &R, &N2)) {
       if (getenv("PFFFT_B200_NO_SPLIT")) return false;
-      s->fast_variant = 300 + R;
-      s->kernel_name = split_name(R);
+      s->split_R = R; s->split_N2 = N2;
+      s->fast_variant = 300;
+      snprintf(s->name_buf, sizeof(s->name_buf), "split_%dx%d", R, N2);
+      s->kernel_name = s->name_buf;
       return true;
     }
     const int C = cta_C_for(s->Nc);
@@ -190,7 +217,8 @@ template <typename T> struct CtaOnlyHooks {
   }
   static int run(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered, cudaStream_t st, const XformOpts& o) {
     const XformParams<T> p = make_params(s, in, out, batch, o);
-    if (s->fast_variant >= 300) return run_split<T>(s, s->fast_variant - 300, p, direction, ordered, st);
+    if (s->fast_variant >= 300)
+      return run_split<T>(s, split_rows_cta<T, -1>, split_rows_cta<T, +1>, p, direction, ordered, st);
     return run_cta_any<T>(s, s->fast_variant - 100, p, direction, ordered, st);
   }
 };

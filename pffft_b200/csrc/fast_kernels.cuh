@@ -344,7 +344,9 @@ template <int NC> PF_HD int chunk_tile_idx(int j, int k) { const int e = j * NC 
 #ifdef __CUDACC__
 template <int R2, int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT, bool REAL>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g, const cf* __restrict__ twr) {
+k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g, const cf* __restrict__ twr, int grp) {
+  // grp > 1 (complex canonical input only): transform g reads the decimated sub-sequence
+  //   in[(g / grp) * grp * NC + (g % grp) + n * grp]   -- the rows of a two-pass (split) plan
   constexpr int NC = 32 * R2;
   constexpr int TW = 32 / R2;                   // transforms per warp chunk
   constexpr int COLS = TW * R2;                 // active lanes in phase B
@@ -402,8 +404,14 @@ k_warp_mixed(const cf* in, cf* out, long long batch, const cf* __restrict__ tw_g
         for (int n2 = 0; n2 < R2; ++n2) {
           const int n = lane + 32 * n2;
           if (j < nvalid) {
-            if (!ZIN) v[j * R2 + n2] = ld_stream(src + j * NC + n);
-            else { const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
+            if (ZIN) { const int q = zpos_complex(n, NC); v[j * R2 + n2] = mk<float>(tf[j * 2 * NC + zswz(q)], tf[j * 2 * NC + zswz(q + 4)]); }
+            else if (grp == 1) v[j * R2 + n2] = ld_stream(src + j * NC + n);
+            else {
+              const long long g = c * TW + j, t = g / grp;
+              const int n1 = (int)(g - t * grp);
+              const float2 w2 = __ldg(reinterpret_cast<const float2*>(in + t * (long long)grp * NC + n1 + (long long)n * grp));
+              v[j * R2 + n2] = mk<float>(w2.x, w2.y);
+            }
           }
         }
       if (ZIN) __syncwarp();

@@ -303,6 +303,28 @@ __global__ void __launch_bounds__(256) k_split_combine(const cpx<T>* __restrict_
   }
 }
 
+// same, for any radix the register DFT library offers (3,5,6,9,10,12,15 ... natural order in and out)
+template <typename T, int R, int SIGN>
+__global__ void __launch_bounds__(256) k_split_combine_any(const cpx<T>* __restrict__ Y, cpx<T>* __restrict__ X, long long batch,
+                                                           int N2, const cpx<T>* __restrict__ tw) {
+  const long long total = batch * N2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / N2;
+    const int k2 = (int)(idx - t * N2);
+    const cpx<T>* y = Y + t * (long long)R * N2 + k2;
+    cpx<T> v[R];
+#pragma unroll
+    for (int n1 = 0; n1 < R; ++n1) {
+      const cpx<T> a = y[(long long)n1 * N2];
+      v[n1] = (n1 == 0) ? a : cmul_dir<SIGN>(a, tw[(long long)n1 * k2]);
+    }
+    dft_small<R, SIGN>(v);
+    cpx<T>* x = X + t * (long long)R * N2 + k2;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) x[(long long)k1 * N2] = v[k1];
+  }
+}
+
 // ------------------------------------------------------------------ zreorder (pure permutation)
 // one thread per canonical complex slot; TOZ=false: z-domain -> canonical (PFFFT_FORWARD),
 // TOZ=true: canonical -> z-domain (PFFFT_BACKWARD).  ref pffft_priv_impl.h:1158-1193

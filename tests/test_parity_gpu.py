@@ -354,6 +354,10 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(800, 1) as s:
         assert s.kernel == "warp_32x25"
     with pf.Setup(4000, 1) as s:
+        assert s.kernel == "split_5x800"
+    with pf.Setup(36864, 1) as s:
+        assert s.kernel == "split_9x4096"
+    with pf.Setup(144, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "split_16x4096"
