@@ -128,14 +128,19 @@ def main():
                   "ms": tsec * 1e3, "msamples_per_s": prod.value / tsec / 1e6, "produced": prod.value})
 
     if args.sweep:
-        for N in (64, 256, 512, 2048, 4096, 8192, 16384, 65536, 96, 960, 4000):
-            batch = max(1, (1 << 28) // (8 * N))
-            xform_case("sweep cplx fwd", N, 1, batch, 0, True)
-        for N in (1024, 8192, 65536):
-            batch = max(1, (1 << 28) // (4 * N))
-            xform_case("sweep real fwd", N, 0, batch, 0, True)
-        xform_case("sweep cplx fwd f64", 1024, 1, 1 << 17, 0, True, torch.float64)
-        xform_case("sweep cplx fwd z-domain", 1024, 1, 1 << 18, 0, False)
+        # ~1 GiB per buffer so that L2 (126 MB) cannot hold the working set
+        for N in (16, 32, 64, 96, 128, 160, 192, 256, 384, 480, 512, 640, 800, 960, 1024, 2048, 4000, 4096, 8192, 12000,
+                  16384, 36864, 65536):
+            xform_case("sweep cplx fwd", N, 1, max(1, (1 << 30) // (8 * N)), 0, True)
+        for N in (64, 192, 256, 512, 960, 1024, 1920, 2048, 4096, 8192, 16384, 65536, 131072):
+            xform_case("sweep real fwd", N, 0, max(1, (1 << 30) // (4 * N)), 0, True)
+        for N in (256, 1024, 4096):
+            xform_case("sweep real bwd", N, 0, max(1, (1 << 30) // (4 * N)), 1, True)
+        for N, tr in ((1024, 1), (4096, 1), (4096, 0), (96, 1), (8192, 1)):
+            xform_case("sweep f64 fwd", N, tr, max(1, (1 << 30) // (16 * N)), 0, True, torch.float64)
+        for N, tr in ((256, 1), (1024, 1), (4096, 1), (4096, 0), (960, 1)):
+            xform_case("sweep fwd z-domain (pffft_transform)", N, tr, max(1, (1 << 30) // (8 * N)), 0, False)
+            xform_case("sweep bwd z-domain (pffft_transform)", N, tr, max(1, (1 << 30) // (8 * N)), 1, False)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
 
