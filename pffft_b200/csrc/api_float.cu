@@ -139,7 +139,6 @@ static int split_rows_float(Setup<float>* s, const cf* src, cf* rows, long long 
 }
 static bool float_split_for(int N, int transform, int* R, int* N2) {
   const int Nc = transform == XF_REAL ? N / 2 : N;
-  if (Nc <= 1024 && transform == XF_COMPLEX && Nc == 1024) return false;
   return split_choose(Nc, is_float_row_size, R, N2);
 }
 

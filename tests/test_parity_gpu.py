@@ -429,3 +429,47 @@ def test_warp_family_real_sizes(pf, ref, R, r2):
     for j, i in enumerate(idx):
         assert R.relmax(fo_[i], wo[j]) <= 1e-5 and R.relmax(fz_[i], wz[j]) <= 1e-5
         assert R.relmax(bo_[i], x[i] * N) <= 1e-5 and R.relmax(bz_[i], x[i] * N) <= 1e-5
+
+
+def test_edge_cases_empty_batches_and_pointer_mixing(pf):
+    """empty batch is a no-op; host/device pointer mixing is rejected with an error code and message (no silent path)"""
+    import ctypes as C
+    torch = torch_mod()
+    with pf.Setup(1024, 1) as s:
+        x = torch.zeros(2048, device="cuda"); y = torch.full((2048,), 7.0, device="cuda")
+        n0 = pf.launch_count()
+        pf.pffftb_transform_batch(s.handle, x, y, 0, 0, 1)            # batch = 0
+        assert pf.launch_count() == n0 and float(y[0]) == 7.0
+        h = np.zeros(2048, np.float32)
+        rc = pf.lib.pffftb_transform_batch(s.handle, pf.ptr(h), pf.ptr(y), 1, 0, 1)
+        assert rc != 0 and "host or both be device" in pf.last_error()
+        rc = pf.lib.pffftb_transform_batch(s.handle, pf.ptr(x), pf.ptr(y), 1, 7, 1)   # bad direction
+        assert rc != 0
+        rc = pf.lib.pffftb_zreorder_batch(s.handle, pf.ptr(x), pf.ptr(x), 1, 0)       # zreorder must not alias
+        assert rc != 0 and "alias" in pf.last_error()
+    # pffastconv: input shorter than the filter produces nothing and writes nothing
+    fc = pf.FastConv(np.ones(100, np.float32), 0, 0)
+    xs = torch.ones(50, device="cuda"); ys = torch.full((64,), float("nan"), device="cuda")
+    assert fc.apply(xs, ys, 50, 1) == 0 and bool(torch.isnan(ys).all())
+    assert fc.apply(xs, ys, 0, 1) == 0
+    fc.close()
+
+
+def test_one_setup_shared_by_concurrent_host_threads(pf, ref, R):
+    """a PFFFT_Setup is shareable between threads (include/pffft/pffft.h:102-106): concurrent host-pointer calls"""
+    import threading
+    N = 1024
+    rng = np.random.default_rng(11)
+    xs = [uniform(rng, 16 * 2 * N).reshape(16, 2 * N) for _ in range(4)]
+    outs = [None] * 4
+    with pf.Setup(N, 1) as s:
+        def work(i):
+            o = np.empty_like(xs[i])
+            for _ in range(5):
+                pf.pffftb_transform_batch(s.handle, xs[i], o, 16, 0, 1)
+            outs[i] = o
+        th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in th]; [t.join() for t in th]
+    for i in range(4):
+        w = ref.transform_batch(N, 1, xs[i][:3], 0, True)
+        assert max(R.relmax(outs[i][j], w[j]) for j in range(3)) <= 1e-5
