@@ -139,6 +139,7 @@ static int split_rows_float(Setup<float>* s, const cf* src, cf* rows, long long 
 }
 static bool float_split_for(int N, int transform, int* R, int* N2) {
   const int Nc = transform == XF_REAL ? N / 2 : N;
+  if (!getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_choose_fused<float>(Nc, R, N2)) return true;   // one-kernel plan first
   return split_choose(Nc, is_float_row_size, R, N2);
 }
 
@@ -211,8 +212,9 @@ template <> struct FastHooks<float> {
     { int R = 0, N2 = 0;
       if (!cta_C_for(s->Nc) && !getenv("PFFFT_B200_NO_SPLIT") && float_split_for(s->N, s->transform, &R, &N2)) {
         s->split_R = R; s->split_N2 = N2;
+        s->split_fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_fused_ok<float>(R, N2);
         s->fast_variant = 300;
-        snprintf(s->name_buf, sizeof(s->name_buf), "split_%dx%d", R, N2);
+        snprintf(s->name_buf, sizeof(s->name_buf), s->split_fused ? "cta_split_%dx%d" : "split_%dx%d", R, N2);
         s->kernel_name = s->name_buf;
         return true;
       } }

@@ -215,12 +215,13 @@ template <int R, int SIGN, typename T> PF_HD void dft_small(cpx<T>* a) {
   else if constexpr (R == 10) dft_ct<2, 5, SIGN>(a);
   else if constexpr (R == 12) dft_ct<4, 3, SIGN>(a);
   else if constexpr (R == 15) dft_ct<3, 5, SIGN>(a);
+  else if constexpr (R == 16) dft_ct<4, 4, SIGN>(a);
   else if constexpr (R == 18) dft_ct<2, 9, SIGN>(a);
   else if constexpr (R == 20) dft_ct<4, 5, SIGN>(a);
   else if constexpr (R == 24) dft_ct<4, 6, SIGN>(a);
   else if constexpr (R == 25) dft_ct<5, 5, SIGN>(a);
   else if constexpr (R == 27) dft_ct<3, 9, SIGN>(a);
-  else dft_ct<5, 6, SIGN>(a);                    // 30
+  else { static_assert(R == 30, "dft_small: unsupported size"); dft_ct<5, 6, SIGN>(a); }
 }
 
 }  // namespace pf

@@ -101,8 +101,14 @@ int run_cta_any(Setup<T>* s, int C, const XformParams<T>& p, int direction, int 
 // (stages+2) round trips of the global Stockham path it replaces.  R is any size of the register DFT library
 // (2,3,4,5,6,8,9,10,12,15,16); N2 is a CTA-kernel size (512..4096) or, for float, a warp-kernel size 32*R2.
 static const int kSplitRadices[] = {2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16};
+template <typename T> inline bool split_fused_ok_fwd(int R, int N2);   // defined with the fused launcher below
 template <typename IsRow> inline bool split_choose(int Nc, IsRow is_row_size, int* R, int* N2) {
   for (int r : kSplitRadices) if (Nc % r == 0 && is_row_size(Nc / r)) { *R = r; *N2 = Nc / r; return true; }
+  return false;
+}
+// decomposition that the single-kernel variant can run, if any
+template <typename T> inline bool split_choose_fused(int Nc, int* R, int* N2) {
+  for (int r : kSplitRadices) if (Nc % r == 0 && split_fused_ok_fwd<T>(r, Nc / r)) { *R = r; *N2 = Nc / r; return true; }
   return false;
 }
 
@@ -139,11 +145,56 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
   return 0;
 }
 
+// ---- single-kernel variant (k_cta_split): (C, R) pairs that are instantiated; each Nc has exactly one of them
+inline bool split_fused_combo(int C, int R) {
+  switch (C) {
+    case 16: return R == 2;
+    case 8: return R == 3 || R == 5 || R == 6;
+    case 4: return R == 3 || R == 5 || R == 6 || R == 9 || R == 10 || R == 12;
+    case 2: return R == 3 || R == 5 || R == 9 || R == 15;
+  }
+  return false;
+}
+template <typename T> inline bool split_fused_ok(int R, int N2);
+template <typename T> inline bool split_fused_ok_fwd(int R, int N2) { return split_fused_ok<T>(R, N2); }
+template <typename T> inline bool split_fused_ok(int R, int N2) {
+  const int C = cta_C_for(N2);
+  return C && split_fused_combo(C, R) && (size_t)(R + 1) * N2 * sizeof(cpx<T>) <= 113 * 1024;   // two CTAs per SM
+}
+template <typename T, int C, int R, int SIGN>
+int launch_split_fused_v(Setup<T>* s, const cpx<T>* src, cpx<T>* dst, long long batch, cudaStream_t st) {
+  constexpr int MINB = (cta_tpsm<T>() / (16 * C)) < 2 ? 1 : 2;
+  auto kern = k_cta_split<T, C, R, SIGN, MINB>;
+  const size_t smem = (size_t)(R + 1) * K2<C>::NC * sizeof(cpx<T>);
+  static thread_local int per_sm = 0;
+  if (per_sm == 0) {
+    if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * C, smem);
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long ctas = batch;
+  const long long cap = (long long)s->sm_count * per_sm;
+  if (ctas > cap) ctas = cap;
+  kern<<<(int)ctas, 16 * C, smem, st>>>(reinterpret_cast<const T*>(src), reinterpret_cast<T*>(dst), batch,
+                                         s->tw_fast, s->tw_fast + K2<C>::NC, s->tw);
+  count_launch();
+  PF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <typename T, int SIGN>
+int launch_split_fused(Setup<T>* s, const cpx<T>* src, cpx<T>* dst, long long batch, cudaStream_t st) {
+  const int C = cta_C_for(s->split_N2), R = s->split_R;
+#define PF_SF(c, r) if (C == c && R == r) return launch_split_fused_v<T, c, r, SIGN>(s, src, dst, batch, st);
+  PF_SF(16, 2) PF_SF(8, 3) PF_SF(8, 5) PF_SF(8, 6) PF_SF(4, 3) PF_SF(4, 5) PF_SF(4, 6) PF_SF(4, 9) PF_SF(4, 10) PF_SF(4, 12)
+  PF_SF(2, 3) PF_SF(2, 5) PF_SF(2, 9) PF_SF(2, 15)
+#undef PF_SF
+  set_error_msg("split plan marked fused without an instantiated kernel");
+  return (int)cudaErrorInvalidValue;
+}
+
 // Rows: functor (Setup*, src, rows, batch, stream) -> rc, chosen by the caller for the direction SIGN
 template <typename T, int LM, int SM, int SIGN, typename Rows>
 int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStream_t st) {
-  std::lock_guard<std::mutex> lock(s->scratch_mu);
-  { const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st); if (rc) return rc; }
   const long long total = p.batch * (long long)s->Nc;
   long long g = (total + 255) / 256; const long long cap = (long long)s->sm_count * 32;
   if (g > cap) g = cap; if (g < 1) g = 1;
@@ -151,21 +202,34 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   // input that already IS the dense complex core (complex canonical, or real time samples read as pairs)
   const bool direct_in = dense_io && p.in_limit < 0 && (LM == L_C_ORD || LM == L_R_TIME) && vec_aligned<T>(p.in);
   const bool direct_out = dense_io && (SM == S_C_ORD || (SM == S_R_TIME && p.out_count >= s->N)) && vec_aligned<T>(p.out);
+  const bool need_scratch = !direct_in || !direct_out || !s->split_fused;
+  std::unique_lock<std::mutex> lock(s->scratch_mu, std::defer_lock);
+  if (need_scratch) {
+    lock.lock();
+    const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st);
+    if (rc) return rc;
+  }
   const cpx<T>* src = reinterpret_cast<const cpx<T>*>(p.in);
   if (!direct_in) {
     k_glob_load<T, LM><<<(int)g, 256, 0, st>>>(p, s->d_scratch[0]);
     count_launch();
     src = s->d_scratch[0];
   }
+  // (the fused kernel reads a whole transform before it writes it, so src == dst is fine)
   cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
-  { const int rc = rows_fn(s, src, s->d_scratch[1], p.batch, st); if (rc) return rc; }
-  { const int rc = split_combine<T, SIGN>(s, s->d_scratch[1], dst, p.batch, st); if (rc) return rc; }
+  if (s->split_fused) {
+    const int rc = launch_split_fused<T, SIGN>(s, src, dst, p.batch, st);
+    if (rc) return rc;
+  } else {
+    { const int rc = rows_fn(s, src, s->d_scratch[1], p.batch, st); if (rc) return rc; }
+    { const int rc = split_combine<T, SIGN>(s, s->d_scratch[1], dst, p.batch, st); if (rc) return rc; }
+  }
   if (!direct_out) {
     k_glob_store<T, SM><<<(int)g, 256, 0, st>>>(p, s->d_scratch[0]);
     count_launch();
   }
   PF_CUDA_OK(cudaGetLastError());
-  PF_CUDA_OK(cudaEventRecord(s->scratch_done, st));
+  if (need_scratch) PF_CUDA_OK(cudaEventRecord(s->scratch_done, st));
   return 0;
 }
 // RowsF / RowsB: row launchers for the forward / backward direction
@@ -186,7 +250,9 @@ template <typename T> struct CtaOnlyHooks {
   static int rows_size(int N, int transform) {               // N2 of the split plan, 0 if the size is not split
     const int Nc = transform == XF_REAL ? N / 2 : N;
     int R = 0, N2 = 0;
-    if (cta_C_for(Nc) || !split_choose(Nc, is_cta_row_size, &R, &N2)) return 0;
+    if (cta_C_for(Nc)) return 0;
+    if (split_choose_fused<T>(Nc, &R, &N2)) return N2;
+    if (!split_choose(Nc, is_cta_row_size, &R, &N2)) return 0;
     return N2;
   }
   static size_t extra_table_cpx(int N, int transform) {
@@ -201,11 +267,12 @@ template <typename T> struct CtaOnlyHooks {
   }
   static bool plan(Setup<T>* s) {
     int R = 0, N2 = 0;
-    if (!cta_C_for(s->Nc) && split_choose(s->Nc, is_cta_row_size, &R, &N2)) {
+    const bool fused = !cta_C_for(s->Nc) && !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_choose_fused<T>(s->Nc, &R, &N2);
+    if (!cta_C_for(s->Nc) && (fused || split_choose(s->Nc, is_cta_row_size, &R, &N2))) {
       if (getenv("PFFFT_B200_NO_SPLIT")) return false;
-      s->split_R = R; s->split_N2 = N2;
+      s->split_R = R; s->split_N2 = N2; s->split_fused = fused;
       s->fast_variant = 300;
-      snprintf(s->name_buf, sizeof(s->name_buf), "split_%dx%d", R, N2);
+      snprintf(s->name_buf, sizeof(s->name_buf), fused ? "cta_split_%dx%d" : "split_%dx%d", R, N2);
       s->kernel_name = s->name_buf;
       return true;
     }

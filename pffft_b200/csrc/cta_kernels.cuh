@@ -348,4 +348,59 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
 }
 #endif  // __CUDACC__
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-level plans that still fit one CTA: Nc = R x N2 with N2 = 256*C.  The CTA runs the R row transforms
+// (decimated sub-sequences x[n1 + R*n2], the three register passes above) one after the other, parks each row,
+// already multiplied by W_Nc^{n1 k}, in shared memory, and finishes with radix-R register DFTs across the rows:
+//     X[k2 + N2*k1] = sum_n1 W_R^{n1 k1} * ( W_Nc^{n1 k2} * Y_n1[k2] )
+// One HBM read and one HBM write per transform instead of the two round trips of the split (rows + combine) plan.
+// Shared memory: (R + 1) * N2 complex words.  Complex canonical in and out only (other layouts wrap it).
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename T, int C, int R, int SIGN, int MINB>
+__global__ void __launch_bounds__(16 * C, MINB)
+k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T>* tw2, const cpx<T>* twN) {
+  using K = K2<C>;
+  constexpr int N2 = K::NC;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
+  cpx<T>* rows = tile + N2;                                   // [R][N2]
+  const int t = threadIdx.x;
+  for (long long tr = blockIdx.x; tr < batch; tr += gridDim.x) {
+    asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twN));
+    const cpx<T>* src = reinterpret_cast<const cpx<T>*>(in) + tr * (long long)(R * N2);
+    cpx<T>* dst = reinterpret_cast<cpx<T>*>(out) + tr * (long long)(R * N2);
+#pragma unroll 1
+    for (int n1 = 0; n1 < R; ++n1) {
+      k2_pass1<C, L_C_ORD, SIGN, false, T>(t, reinterpret_cast<const T*>(src + n1), N2, nullptr, -1, true, tw1, tile, R);
+      __syncthreads();
+      k2_pass2<C, SIGN, T>(t, tw2, tile);
+      __syncthreads();
+      cpx<T> u[16];
+      k2_pass3<C, SIGN, T>(t, tile, u);
+#pragma unroll
+      for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+        for (int kc = 0; kc < C; ++kc) {
+          const int k = k2_out_index<C>(t, r, kc);
+          rows[n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], ldtab(twN + (long long)n1 * k));
+        }
+      __syncthreads();                                        // tile free for the next row; row n1 complete
+    }
+#pragma unroll 2
+    for (int j = 0; j < 16; ++j) {
+      const int k2 = t + K::T * j;
+      cpx<T> v[R];
+#pragma unroll
+      for (int n1 = 0; n1 < R; ++n1) v[n1] = rows[n1 * N2 + k2];
+      dft_small<R, SIGN>(v);
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) dst[k2 + N2 * k1] = v[k1];
+    }
+    __syncthreads();                                          // rows are rewritten by the next transform
+  }
+}
+#endif  // __CUDACC__
+
 }  // namespace pf

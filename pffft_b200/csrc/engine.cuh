@@ -63,7 +63,8 @@ template <typename T> struct Setup {
   // kernel choice
   int kind = KK_SMEM;
   int fast_variant = 0;
-  int split_R = 0, split_N2 = 0;          // Nc = split_R x split_N2 two-pass plans (rows on a tuned kernel + radix-R combine)
+  int split_R = 0, split_N2 = 0;          // Nc = split_R x split_N2 two-level plans (rows on a tuned kernel + radix-R combine)
+  bool split_fused = false;               // ... small enough for ONE kernel (rows parked in shared memory): one HBM round trip
   char name_buf[40] = {0};
   int tpc = 1;                            // transforms resident per CTA (shared-memory kernel), a power of two
   int log2_tpt = 8;                       // log2(threads per transform) = log2(256 / tpc)

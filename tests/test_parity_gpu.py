@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 # bench_pffft.c:445 validation sizes + the power-of-two ladder of tests/test_pffft.c:333
 POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144]
-NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864]
+NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864,
+           1536, 2560, 3072, 5120, 6144, 7680, 9216, 10240, 12288]     # two-level plans that run as one kernel
 
 
 def torch_mod():
@@ -357,6 +358,10 @@ def test_kernel_selection_reports_tuned_kernel(pf):
         assert s.kernel == "split_5x800"
     with pf.Setup(36864, 1) as s:
         assert s.kernel == "split_9x4096"
+    with pf.Setup(8192, 1) as s:
+        assert s.kernel == "cta_split_2x4096"
+    with pf.Setup(9216, 1) as s:
+        assert s.kernel == "cta_split_9x1024"
     with pf.Setup(144, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
