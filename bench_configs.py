@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-spectral", action="store_true")
+    ap.add_argument("--only-spectral", action="store_true")
     args = ap.parse_args()
     import torch
     import pffft_b200 as pf
@@ -45,6 +47,43 @@ def main():
     def emit(d):
         print(json.dumps(d), flush=True)
         out.append(d)
+
+    # spectral-domain kernels of the path: pffft_zreorder, pffft_zconvolve_accumulate/_no_accu,
+    # batched, device resident, 1 GiB per array (>> L2).  Algorithmic bytes: zreorder reads 1 + writes 1 array;
+    # zconvolve reads a (+ab when accumulating) and writes ab, b is ONE shared filter spectrum (L2 resident) or per-batch.
+    def spectral_case(N, tr):
+        per = N if tr == 0 else 2 * N
+        batch = max(1, (1 << 30) // (4 * per))
+        g = torch.Generator(device="cuda"); g.manual_seed(77)
+        a = torch.rand((batch, per), generator=g, device="cuda") * 2 - 1
+        b = torch.rand((batch, per), generator=g, device="cuda") * 2 - 1
+        ab = torch.zeros_like(a)
+        st = pf.Setup(N, tr)
+        nb = batch * per * 4
+        tag = "N=%d %s" % (N, "real" if tr == 0 else "cplx")
+        for d, nm in ((0, "z->canonical"), (1, "canonical->z")):
+            t = ev_time(lambda: pf.pffftb_zreorder_batch(st.handle, a, ab, batch, d), args.iters)
+            emit({"config": "zreorder %s %s" % (nm, tag), "batch": batch, "ms": t * 1e3, "gbs_algorithmic": 2 * nb / t / 1e9,
+                  "frac_of_hbm_peak": 2 * nb / t / 1e9 / peak})
+        for acc, shared, arrays in ((1, 1, 3), (0, 1, 2), (1, 0, 4), (0, 0, 3)):
+            bb = b[0].contiguous() if shared else b
+            t = ev_time(lambda: pf.pffftb_zconvolve_batch(st.handle, a, bb, ab, 0.5, batch, shared, acc), args.iters)
+            emit({"config": "zconvolve_%s %s b=%s" % ("accumulate" if acc else "no_accu", tag, "shared" if shared else "per-batch"),
+                  "batch": batch, "ms": t * 1e3, "gbs_algorithmic": arrays * nb / t / 1e9,
+                  "frac_of_hbm_peak": arrays * nb / t / 1e9 / peak})
+        st.close()
+        del a, b, ab
+        torch.cuda.empty_cache()
+
+    def dump():
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+
+    if args.only_spectral:
+        for N, tr in ((1024, 1), (4096, 0), (8192, 0)):
+            spectral_case(N, tr)
+        dump()
+        return
 
     # C1: N=64 complex forward, batch 1, host pointers through the classic entry point (latency)
     x = (np.random.default_rng(1).random(128) * 2 - 1).astype(np.float32)
@@ -81,6 +120,11 @@ def main():
     xform_case("C2 N=1024 cplx bwd batch=2^20", 1024, 1, 1 << 20, 1, True)
     xform_case("C3 N=4096 real fwd batch=2^18", 4096, 0, 1 << 18, 0, True)
     xform_case("C3' N=4096 real bwd batch=2^18", 4096, 0, 1 << 18, 1, True)
+
+    if not args.no_spectral:
+        spectral_case(1024, 1)
+        spectral_case(4096, 0)
+        spectral_case(8192, 0)
 
     # C4: pffastconv 2^24-sample real stream, 4097 taps, device resident, one apply(flush=1) call
     n, taps = 1 << 24, 4097
@@ -141,8 +185,7 @@ def main():
         for N, tr in ((256, 1), (1024, 1), (4096, 1), (4096, 0), (960, 1)):
             xform_case("sweep fwd z-domain (pffft_transform)", N, tr, max(1, (1 << 30) // (8 * N)), 0, False)
             xform_case("sweep bwd z-domain (pffft_transform)", N, tr, max(1, (1 << 30) // (8 * N)), 1, False)
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+    dump()
 
 
 if __name__ == "__main__":

@@ -317,15 +317,32 @@ int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device
   if (chunk > batch) chunk = batch;
   int rc = ensure_slots(s, (size_t)chunk * per);
   if (rc) return rc;
+  // Chunk schedule: sizes double from chunk/32 up to `chunk` at the head and mirror back down at the tail, so the
+  // un-overlapped first H2D copy and last D2H copy (pipeline fill and drain) are ~1 MiB instead of a whole 32 MiB chunk
+  // (at 2^16 transforms of 8 KiB per call, fill + drain of full-size chunks cost 11 % of the call).
+  const long long c0 = chunk / 32 > 0 ? chunk / 32 : 1;
+  int ramp_steps = 0;
+  long long ramp = 0;
+  static const bool ramp_on = getenv("PFFFT_B200_RAMP") ? atoi(getenv("PFFFT_B200_RAMP")) != 0 : true;     // A/B switch
+  while (ramp_on && (c0 << ramp_steps) < chunk && 2 * (ramp + (c0 << ramp_steps)) <= batch) { ramp += c0 << ramp_steps; ++ramp_steps; }
   int i = 0;
-  for (long long b0 = 0; b0 < batch; b0 += chunk, i = (i + 1) % 3) {
-    const long long nb = (batch - b0 < chunk) ? (batch - b0) : chunk;
+  long long b0 = 0;
+  auto submit = [&](long long nb) -> int {
     Slot& sl = s->slot[i];
     PF_CUDA_OK(cudaMemcpyAsync(sl.d_in, in + (size_t)b0 * per, (size_t)nb * per * sizeof(T), cudaMemcpyHostToDevice, sl.stream));
-    rc = device_op((const T*)sl.d_in, (T*)sl.d_out, nb, sl.stream);
-    if (rc) return rc;
+    const int r = device_op((const T*)sl.d_in, (T*)sl.d_out, nb, sl.stream);
+    if (r) return r;
     PF_CUDA_OK(cudaMemcpyAsync(out + (size_t)b0 * per, sl.d_out, (size_t)nb * per * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+    b0 += nb; i = (i + 1) % 3;
+    return 0;
+  };
+  for (int j = 0; j < ramp_steps; ++j) { rc = submit(c0 << j); if (rc) return rc; }
+  for (long long mid = batch - 2 * ramp; mid > 0; ) {
+    const long long nb = mid < chunk ? mid : chunk;
+    rc = submit(nb); if (rc) return rc;
+    mid -= nb;
   }
+  for (int j = ramp_steps - 1; j >= 0; --j) { rc = submit(c0 << j); if (rc) return rc; }
   for (int k = 0; k < 3; ++k) PF_CUDA_OK(cudaStreamSynchronize(s->slot[k].stream));
   if (cur != s->device) cudaSetDevice(cur);
   return 0;
@@ -388,8 +405,8 @@ template <typename T, typename Hooks, typename S> int engine_selftest(FILE* dbg)
 
 // ---------------------------------------------------------------- zreorder / zconvolve
 template <typename T> int engine_zreorder_device(Setup<T>* s, const T* in, T* out, long long batch, int direction, cudaStream_t st) {
-  const long long slots = batch * (s->transform == XF_REAL ? s->N / 2 : s->N);
-  long long g = (slots + 255) / 256; const long long cap = (long long)s->sm_count * 32;
+  const long long groups = batch * (long long)(s->per() / 8);      // one thread per 8-element z-domain group
+  long long g = (groups + 255) / 256; const long long cap = (long long)s->sm_count * 32;
   if (g > cap) g = cap; if (g < 1) g = 1;
   const bool toz = direction == DIR_BACKWARD;
   if (s->transform == XF_REAL) {

@@ -325,31 +325,7 @@ __global__ void __launch_bounds__(256) k_split_combine_any(const cpx<T>* __restr
   }
 }
 
-// ------------------------------------------------------------------ zreorder (pure permutation)
-// one thread per canonical complex slot; TOZ=false: z-domain -> canonical (PFFFT_FORWARD),
-// TOZ=true: canonical -> z-domain (PFFFT_BACKWARD).  ref pffft_priv_impl.h:1158-1193
-template <typename T, bool REAL, bool TOZ>
-__global__ void __launch_bounds__(256) k_zreorder(const T* __restrict__ in, T* __restrict__ out, long long batch, int N) {
-  const int nslots = REAL ? N / 2 : N;
-  const long long per = REAL ? N : 2LL * N;
-  const long long total = batch * nslots;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long t = idx / nslots;
-    const int k = (int)(idx - t * nslots);
-    const T* ib = in + t * per;
-    T* ob = out + t * per;
-    if (TOZ) spec_put<true, REAL>(ob, k, N, spec_get<false, REAL>(ib, k, N));
-    else     spec_put<false, REAL>(ob, k, N, spec_get<true, REAL>(ib, k, N));
-  }
-}
-
-// ------------------------------------------------------------------ zconvolve
-// z-domain spectra are groups of 8 elements (4 re, 4 im).  One thread per group: 2x 4-wide
-// loads of a, b (and ab when accumulating).  Arithmetic is done with explicitly un-fused
-// mul/add in the reference's operation order (VCPLXMUL then VMADD, src/simd/pf_float.h:76,
-// pf_sse1_float.h:61) so results are bit-identical to the CPU library; the kernel is
-// bandwidth-bound, the extra instructions are free.  Real setups multiply element 0 (DC) and
-// element 4 (Nyquist) as independent reals (pffft_priv_impl.h:1626-1629, :1680-1683).
+// 4-element vector accesses (128-bit for float, 2 x 128-bit for double)
 template <typename T> struct vec4 { T v[4]; };
 template <typename T> PF_D vec4<T> ld4(const T* p);
 template <> PF_D vec4<float> ld4<float>(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return {{t.x, t.y, t.z, t.w}}; }
@@ -363,6 +339,66 @@ template <> PF_D void st4<double>(double* p, const vec4<double>& v) {
   *reinterpret_cast<double2*>(p) = make_double2(v.v[0], v.v[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(v.v[2], v.v[3]);
 }
+
+// ------------------------------------------------------------------ zreorder (pure permutation)
+// ref pffft_priv_impl.h:1158-1193.  TOZ=false: z-domain -> canonical (PFFFT_FORWARD); TOZ=true: canonical -> z-domain
+// (PFFFT_BACKWARD).  One thread per z-domain GROUP of 8 elements [4 re | 4 im] = elements u = 4*blk..4*blk+3 of quarter q
+// (layout.cuh): consecutive threads take consecutive groups, so the z side is one contiguous 32-byte (float) piece
+// per thread and a contiguous 1 KiB per warp, moved with 128-bit accesses.  On the canonical side a group is four
+// consecutive complex slots: ascending (complex, and the even quarters of a real spectrum) -> two 128-bit accesses per
+// thread, 256 contiguous bytes per quarter per warp; descending (odd quarters of a real spectrum, k = M - u with the
+// u = 0 element parked at k = M - N/8) -> four complex-sized accesses.  Every 32-byte sector is used in full both ways.
+template <typename T, bool REAL, bool TOZ>
+__global__ void __launch_bounds__(256) k_zreorder(const T* __restrict__ in, T* __restrict__ out, long long batch, int N) {
+  const long long per = REAL ? N : 2LL * N;
+  const int groups = (int)(per >> 3);
+  const int nq = REAL ? (N >> 3) : (N >> 2);                 // canonical slots per quarter
+  const long long total = batch * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / groups;
+    const int g = (int)(idx - t * groups);
+    const int blk = g >> 2, q = g & 3;
+    const T* ib = in + t * per;
+    T* ob = out + t * per;
+    const int zoff = 8 * g;                                  // = 32*blk + 8*q
+    if (!REAL || !(q & 1)) {
+      const int coff = 2 * (q * nq + 4 * blk);               // first element of canonical slot k0 = q*nq + 4*blk
+      if (TOZ) {
+        const vec4<T> c0 = ld4(ib + coff), c1 = ld4(ib + coff + 4);
+        st4(ob + zoff,     vec4<T>{{c0.v[0], c0.v[2], c1.v[0], c1.v[2]}});
+        st4(ob + zoff + 4, vec4<T>{{c0.v[1], c0.v[3], c1.v[1], c1.v[3]}});
+      } else {
+        const vec4<T> zr = ld4(ib + zoff), zi = ld4(ib + zoff + 4);
+        st4(ob + coff,     vec4<T>{{zr.v[0], zi.v[0], zr.v[1], zi.v[1]}});
+        st4(ob + coff + 4, vec4<T>{{zr.v[2], zi.v[2], zr.v[3], zi.v[3]}});
+      }
+    } else {
+      const int M = (q + 1) * nq;                            // q=1: N/4, q=3: N/2
+      int k[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int u = 4 * blk + j; k[j] = (u == 0) ? M - nq : M - u; }
+      if (TOZ) {
+        vec4<T> zr, zi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const cpx<T> c = reinterpret_cast<const cpx<T>*>(ib)[k[j]]; zr.v[j] = c.x; zi.v[j] = c.y; }
+        st4(ob + zoff, zr);
+        st4(ob + zoff + 4, zi);
+      } else {
+        const vec4<T> zr = ld4(ib + zoff), zi = ld4(ib + zoff + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reinterpret_cast<cpx<T>*>(ob)[k[j]] = mk<T>(zr.v[j], zi.v[j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ zconvolve
+// z-domain spectra are groups of 8 elements (4 re, 4 im).  One thread per group: 2x 4-wide
+// loads of a, b (and ab when accumulating).  Arithmetic is done with explicitly un-fused
+// mul/add in the reference's operation order (VCPLXMUL then VMADD, src/simd/pf_float.h:76,
+// pf_sse1_float.h:61) so results are bit-identical to the CPU library; the kernel is
+// bandwidth-bound, the extra instructions are free.  Real setups multiply element 0 (DC) and
+// element 4 (Nyquist) as independent reals (pffft_priv_impl.h:1626-1629, :1680-1683).
 PF_D float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
 PF_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 PF_D float  add_rn(float a, float b)   { return __fadd_rn(a, b); }
