@@ -145,6 +145,53 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
   return 0;
 }
 
+// ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked
+// in the distributed shared memory of a CL-CTA cluster -> one HBM round trip for 16384 .. 65536 points
+bool cluster_shape_exists(int CL, int Q, bool scatter);
+int cluster_max_active_float(int CL, int Q, bool scatter);      // co-resident clusters on the current device (0: unusable)
+int cluster_launch_float(int CL, int Q, bool scatter, int sign, const cpx<float>* src, cpx<float>* dst, long long batch,
+                         const cpx<float>* tw1, const cpx<float>* tw2, const cpx<float>* twP, cudaStream_t st);
+// cluster shape for a float plan R x N2 (0 = none).  PFFFT_B200_CLUSTER=0 disables, PFFFT_B200_CLUSTER_SCATTER=0/1 picks
+// the row distribution (strided L2 reads / DSMEM scatter), PFFFT_B200_CLUSTER_R16=16 runs 65536 on 16-CTA clusters,
+// PFFFT_B200_CLUSTER_8192=1 also moves 2 x 4096 from the single-CTA kernel to a 2-CTA cluster.
+inline bool cluster_choose(int R, int N2, int* CL, int* Q, bool* scatter) {
+  if (N2 != 4096) return false;
+  if (const char* e = getenv("PFFFT_B200_CLUSTER")) if (atoi(e) == 0) return false;
+  bool sc = true;
+  if (const char* e = getenv("PFFFT_B200_CLUSTER_SCATTER")) sc = atoi(e) != 0;
+  int cl = 0, q = 1;
+  switch (R) {
+    case 2: if (getenv("PFFFT_B200_CLUSTER_8192") && atoi(getenv("PFFFT_B200_CLUSTER_8192"))) cl = 2; break;
+    case 4: cl = 4; break;
+    case 8: cl = 8; break;
+    case 16:
+      if (getenv("PFFFT_B200_CLUSTER_R16") && atoi(getenv("PFFFT_B200_CLUSTER_R16")) == 16) cl = 16;
+      else { cl = 8; q = 2; }
+      break;
+  }
+  if (!cl) return false;
+  if (q > 1) sc = false;
+  if (!cluster_shape_exists(cl, q, sc)) return false;
+  if (cluster_max_active_float(cl, q, sc) <= 0) return false;
+  *CL = cl; *Q = q; *scatter = sc;
+  return true;
+}
+
+// tables of a split plan whose rows run on the CTA core: [tw1: N2][tw2: 16*C][twP: Nc], twP[n1*N2 + k2] = exp(-2 pi i n1 k2 / Nc)
+// (row-major copy of the combine twiddles: the single-kernel variants read it with unit stride)
+inline size_t split_table_cpx(int Nc, int N2) { return cta_table_cpx(N2) + (size_t)Nc; }
+template <typename T> void split_fill_tables(int Nc, int N2, T* dst) {
+  cta_fill_tables<T>(N2, dst);
+  T* tp = dst + 2 * cta_table_cpx(N2);
+  const int R = Nc / N2;
+  for (int n1 = 0; n1 < R; ++n1)
+    for (int k2 = 0; k2 < N2; ++k2) {
+      long double c, sn;
+      pfplan::unit_root((long long)n1 * k2, Nc, &c, &sn);
+      tp[2 * ((size_t)n1 * N2 + k2)] = (T)c; tp[2 * ((size_t)n1 * N2 + k2) + 1] = (T)sn;
+    }
+}
+
 // ---- single-kernel variant (k_cta_split): (C, R) pairs that are instantiated; each Nc has exactly one of them
 inline bool split_fused_combo(int C, int R) {
   switch (C) {
@@ -176,7 +223,7 @@ int launch_split_fused_v(Setup<T>* s, const cpx<T>* src, cpx<T>* dst, long long 
   const long long cap = (long long)s->sm_count * per_sm;
   if (ctas > cap) ctas = cap;
   kern<<<(int)ctas, 16 * C, smem, st>>>(reinterpret_cast<const T*>(src), reinterpret_cast<T*>(dst), batch,
-                                         s->tw_fast, s->tw_fast + K2<C>::NC, s->tw);
+                                         s->tw_fast, s->tw_fast + K2<C>::NC, s->tw_fast + cta_table_cpx(K2<C>::NC));
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
   return 0;
@@ -202,7 +249,8 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   // input that already IS the dense complex core (complex canonical, or real time samples read as pairs)
   const bool direct_in = dense_io && p.in_limit < 0 && (LM == L_C_ORD || LM == L_R_TIME) && vec_aligned<T>(p.in);
   const bool direct_out = dense_io && (SM == S_C_ORD || (SM == S_R_TIME && p.out_count >= s->N)) && vec_aligned<T>(p.out);
-  const bool need_scratch = !direct_in || !direct_out || !s->split_fused;
+  const bool one_kernel = s->split_fused || s->split_cluster > 0;
+  const bool need_scratch = !direct_in || !direct_out || !one_kernel;
   std::unique_lock<std::mutex> lock(s->scratch_mu, std::defer_lock);
   if (need_scratch) {
     lock.lock();
@@ -217,7 +265,13 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   }
   // (the fused kernel reads a whole transform before it writes it, so src == dst is fine)
   cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
-  if (s->split_fused) {
+  if (s->split_cluster > 0) {
+    int rc = (int)cudaErrorInvalidValue;
+    if constexpr (sizeof(T) == 4)
+      rc = cluster_launch_float(s->split_cluster, s->split_Q, s->split_scatter, SIGN, src, dst, p.batch, s->tw_fast,
+                                s->tw_fast + s->split_N2, s->tw_fast + cta_table_cpx(s->split_N2), st);
+    if (rc) return rc;
+  } else if (s->split_fused) {
     const int rc = launch_split_fused<T, SIGN>(s, src, dst, p.batch, st);
     if (rc) return rc;
   } else {
@@ -258,12 +312,12 @@ template <typename T> struct CtaOnlyHooks {
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
     const int n2 = rows_size(N, transform);
-    return n2 ? cta_table_cpx(n2) : cta_table_cpx(Nc);
+    return n2 ? split_table_cpx(Nc, n2) : cta_table_cpx(Nc);
   }
   static void fill_extra_table(int N, int transform, T* dst) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
     const int n2 = rows_size(N, transform);
-    cta_fill_tables<T>(n2 ? n2 : Nc, dst);
+    if (n2) split_fill_tables<T>(Nc, n2, dst); else cta_fill_tables<T>(Nc, dst);
   }
   static bool plan(Setup<T>* s) {
     int R = 0, N2 = 0;

@@ -355,12 +355,13 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
 // already multiplied by W_Nc^{n1 k}, in shared memory, and finishes with radix-R register DFTs across the rows:
 //     X[k2 + N2*k1] = sum_n1 W_R^{n1 k1} * ( W_Nc^{n1 k2} * Y_n1[k2] )
 // One HBM read and one HBM write per transform instead of the two round trips of the split (rows + combine) plan.
+// twP[n1*N2 + k] = exp(-2 pi i n1 k / Nc) is the row-major copy of the combine twiddles (unit-stride reads per row).
 // Shared memory: (R + 1) * N2 complex words.  Complex canonical in and out only (other layouts wrap it).
 // ---------------------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 template <typename T, int C, int R, int SIGN, int MINB>
 __global__ void __launch_bounds__(16 * C, MINB)
-k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T>* tw2, const cpx<T>* twN) {
+k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T>* tw2, const cpx<T>* twP) {
   using K = K2<C>;
   constexpr int N2 = K::NC;
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
@@ -368,7 +369,7 @@ k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T
   cpx<T>* rows = tile + N2;                                   // [R][N2]
   const int t = threadIdx.x;
   for (long long tr = blockIdx.x; tr < batch; tr += gridDim.x) {
-    asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twN));
+    asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twP));
     const cpx<T>* src = reinterpret_cast<const cpx<T>*>(in) + tr * (long long)(R * N2);
     cpx<T>* dst = reinterpret_cast<cpx<T>*>(out) + tr * (long long)(R * N2);
 #pragma unroll 1
@@ -384,7 +385,7 @@ k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T
 #pragma unroll
         for (int kc = 0; kc < C; ++kc) {
           const int k = k2_out_index<C>(t, r, kc);
-          rows[n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], ldtab(twN + (long long)n1 * k));
+          rows[n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], ldtab(twP + n1 * N2 + k));
         }
       __syncthreads();                                        // tile free for the next row; row n1 complete
     }

@@ -244,3 +244,88 @@ extern "C" int emu_wmixed(int N, int dir, const float* in, float* out, long long
 #undef WM
   return -1;
 }
+
+// ---- cluster kernel (cluster_kernels.cuh): the CL CTAs of one cluster stepped phase by phase, barriers = phase ends
+#include "../../pffft_b200/csrc/cluster_kernels.cuh"
+#include "../../pffft_b200/csrc/cta_hooks.cuh"   // split_fill_tables
+struct EmuRemote { pf::cf* const* bases; PF_HD pf::cf* operator()(int owner) const { return bases[owner]; } };
+template <int C, int CL, int Q, bool SCATTER, int SIGN>
+static void emu_cluster_run(const float* in, float* out) {
+  using namespace pf;
+  using K = K2<C>; using G = KCL<C, CL, Q>;
+  std::vector<float> tab(2 * split_table_cpx(G::NC, G::N2));
+  split_fill_tables<float>(G::NC, G::N2, tab.data());
+  const cf* tw1 = reinterpret_cast<const cf*>(tab.data());
+  const cf* tw2 = tw1 + G::N2;
+  const cf* twP = tw1 + cta_table_cpx(G::N2);
+  std::vector<std::vector<cf>> tile(CL, std::vector<cf>(G::N2)), park(CL, std::vector<cf>((size_t)Q * G::N2));
+  cf* bases[CL];
+  for (int c = 0; c < CL; ++c) bases[c] = park[c].data();
+  const EmuRemote remote{bases};
+  const cf* src = reinterpret_cast<const cf*>(in);
+  cf* dst = reinterpret_cast<cf*>(out);
+  std::vector<cf> U((size_t)CL * K::T * 16);
+  auto u_of = [&](int c, int t) -> cf (&)[16] { return *reinterpret_cast<cf(*)[16]>(&U[((size_t)c * K::T + t) * 16]); };
+  if (SCATTER) {
+    for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) cl_scatter<C, CL, float>(t, c, src, remote);
+    for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) k2_pass1_smem<C, SIGN, float>(t, park[c].data(), tw1, tile[c].data());
+    for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, tw2, tile[c].data());
+    for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) k2_pass3<C, SIGN, float>(t, tile[c].data(), u_of(c, t));
+    for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) cl_park<C, CL, Q, SIGN, float>(t, c, u_of(c, t), twP, remote);
+  } else {
+    for (int q = 0; q < Q; ++q)
+      for (int c = 0; c < CL; ++c) {
+        const int n1 = c + CL * q;
+        for (int t = 0; t < K::T; ++t)
+          k2_pass1<C, L_C_ORD, SIGN, false, float>(t, reinterpret_cast<const float*>(src + n1), G::N2, nullptr, -1, true, tw1, tile[c].data(), G::R);
+        for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, tw2, tile[c].data());
+        for (int t = 0; t < K::T; ++t) { k2_pass3<C, SIGN, float>(t, tile[c].data(), u_of(c, t)); cl_park<C, CL, Q, SIGN, float>(t, n1, u_of(c, t), twP, remote); }
+      }
+  }
+  for (int c = 0; c < CL; ++c) for (int t = 0; t < K::T; ++t) cl_combine<C, CL, Q, SIGN, float>(t, c, park[c].data(), dst);
+}
+extern "C" int emu_cluster(int CL, int Q, int scatter, int dir, const float* in, float* out) {
+#define CLX(cl, q, sc) if (CL == cl && Q == q && (scatter != 0) == sc) { if (dir == 0) emu_cluster_run<16, cl, q, sc, -1>(in, out); else emu_cluster_run<16, cl, q, sc, +1>(in, out); return 0; }
+  CLX(2, 1, false) CLX(2, 1, true) CLX(4, 1, false) CLX(4, 1, true) CLX(8, 1, false) CLX(8, 1, true) CLX(8, 2, false) CLX(16, 1, false) CLX(16, 1, true)
+#undef CLX
+  return -1;
+}
+// single-CTA two-level kernel (k_cta_split) with the row-major twiddle table
+template <int C, int R, int SIGN>
+static void emu_cta_split_run(const float* in, float* out) {
+  using namespace pf;
+  using K = K2<C>;
+  constexpr int N2 = K::NC, Nc = R * N2;
+  std::vector<float> tab(2 * split_table_cpx(Nc, N2));
+  split_fill_tables<float>(Nc, N2, tab.data());
+  const cf* tw1 = reinterpret_cast<const cf*>(tab.data());
+  const cf* tw2 = tw1 + N2;
+  const cf* twP = tw1 + cta_table_cpx(N2);
+  std::vector<cf> tile(N2), rows((size_t)R * N2);
+  const cf* src = reinterpret_cast<const cf*>(in);
+  cf* dst = reinterpret_cast<cf*>(out);
+  for (int n1 = 0; n1 < R; ++n1) {
+    for (int t = 0; t < K::T; ++t) k2_pass1<C, L_C_ORD, SIGN, false, float>(t, reinterpret_cast<const float*>(src + n1), N2, nullptr, -1, true, tw1, tile.data(), R);
+    for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, tw2, tile.data());
+    for (int t = 0; t < K::T; ++t) {
+      cf u[16];
+      k2_pass3<C, SIGN, float>(t, tile.data(), u);
+      for (int r = 0; r < 16 / C; ++r) for (int kc = 0; kc < C; ++kc) {
+        const int k = k2_out_index<C>(t, r, kc);
+        rows[(size_t)n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], twP[n1 * N2 + k]);
+      }
+    }
+  }
+  for (int k2 = 0; k2 < N2; ++k2) {
+    cf v[R];
+    for (int n1 = 0; n1 < R; ++n1) v[n1] = rows[(size_t)n1 * N2 + k2];
+    dft_small<R, SIGN>(v);
+    for (int k1 = 0; k1 < R; ++k1) dst[k2 + N2 * k1] = v[k1];
+  }
+}
+extern "C" int emu_cta_split(int C, int R, int dir, const float* in, float* out) {
+#define CSX(c, r) if (C == c && R == r) { if (dir == 0) emu_cta_split_run<c, r, -1>(in, out); else emu_cta_split_run<c, r, +1>(in, out); return 0; }
+  CSX(16, 2) CSX(8, 3) CSX(4, 9) CSX(2, 15) CSX(8, 6)
+#undef CSX
+  return -1;
+}
