@@ -37,6 +37,47 @@ template <int C, int CL, int Q> struct KCL {
   static constexpr int COLS_PER_THREAD = S / K::T;
 };
 
+// ---- pass 1 in two halves, so that the loads of the NEXT row are in flight while the current one is parked and combined.
+// cl_row_issue: thread m copies its 16 points x[n1 + R*(m + 16C*n_a)] with 8-byte cp.async (LDGSTS, no registers held)
+// into the 16 tile slots it will itself overwrite in pass 1 -- thread-private slots, so no barrier is needed between the
+// copy and its consumption, only cp.async.wait_all.  Register p of the radix-16 network holds point n_a = brev4(p).
+template <int C, int R, typename T>
+PF_HD void cl_row_issue(int m, const cpx<T>* row /* x + n1 */, cpx<T>* tile) {
+  using K = K2<C>;
+  const int jb = m / C, jc = m % C;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const cpx<T>* g = row + (long long)(m + K::BC * brev4(p)) * R;
+    cpx<T>* d = tile + K::idx(p, jb, jc);
+#ifdef __CUDA_ARCH__
+    if constexpr (sizeof(cpx<T>) == 8)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(d)), "l"(g) : "memory");
+    else
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(d)), "l"(g) : "memory");
+#else
+    *d = *g;
+#endif
+  }
+}
+PF_HD void cl_row_landed() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+// cl_row_pass1: radix-16 over n_a of the staged points, * W_N2^{m k_a}, back into the same slots (== k2_pass1 after its loads)
+template <int C, int SIGN, typename T>
+PF_HD void cl_row_pass1(int m, const cpx<T>* tw1, cpx<T>* tile) {
+  using K = K2<C>;
+  const int jb = m / C, jc = m % C;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = tile[K::idx(p, jb, jc)];
+  reg_fft<16, SIGN>(v);
+  tile[K::idx(0, jb, jc)] = v[0];
+#pragma unroll
+  for (int ka = 1; ka < 16; ++ka) tile[K::idx(ka, jb, jc)] = cmul_dir<SIGN>(v[ka], ldtab(tw1 + ka * K::BC + m));
+}
+
 // ---- park: thread t of the CTA that just transformed row n1 holds u[r*C + kc] = Y_n1[k2_out_index(t, r, kc)]
 // remote(owner) -> base of the park buffer [R][S] of CTA `owner`
 // twP: row-major twiddle table twP[n1*N2 + k2] = exp(-2 pi i n1 k2 / Nc): consecutive threads read consecutive entries
@@ -101,7 +142,12 @@ PF_HD void cl_scatter(int t, int rank, const cpx<T>* src, Remote remote) {
 }
 
 #ifdef __CUDACC__
+// release: the DSMEM stores issued before it are visible to the peers after their wait.  The fence behind it also
+// waits for every other outstanding store of the thread (the combine's global stores: ncu showed it as the second
+// largest stall), so barriers that only announce "I have finished READING" use the relaxed form -- the loads they
+// cover have returned, their values were consumed by the stores issued before the arrive.
 PF_D void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+PF_D void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 PF_D void cluster_wait()   { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 PF_D unsigned cluster_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // generic address of `p` (a shared-memory variable of this CTA) in the shared memory of CTA `rank` of the cluster
@@ -138,7 +184,9 @@ k_cluster_fft(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx
   const int rank = (int)cluster_cta_rank();
   const long long nclusters = gridDim.x / CL, cid = blockIdx.x / CL;
   const ClusterRemote<T> remote{park};
-  cluster_arrive();                                             // "park buffers free", phase 0
+  cluster_arrive_relaxed();                                     // "park buffers free", phase 0
+  if (!SCATTER && cid < batch)
+    cl_row_issue<C, G::R, T>(t, reinterpret_cast<const cpx<T>*>(in) + cid * (long long)G::NC + rank, tile);
   for (long long tr = cid; tr < batch; tr += nclusters) {
     asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twP));         // keep table reads in the loop (see cta_kernels.cuh)
     const cpx<T>* src = reinterpret_cast<const cpx<T>*>(in) + tr * (long long)G::NC;
@@ -149,7 +197,7 @@ k_cluster_fft(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx
       cluster_arrive(); cluster_wait();                         // rows complete in every CTA
       k2_pass1_smem<C, SIGN, T>(t, park, tw1, tile);
       __syncthreads();
-      cluster_arrive();                                         // this CTA no longer reads its staging buffer
+      cluster_arrive_relaxed();                                 // this CTA no longer reads its staging buffer
       k2_pass2<C, SIGN, T>(t, tw2, tile);
       __syncthreads();
       cpx<T> u[16];
@@ -160,20 +208,23 @@ k_cluster_fft(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx
 #pragma unroll 1
       for (int q = 0; q < Q; ++q) {
         const int n1 = rank + CL * q;
-        k2_pass1<C, L_C_ORD, SIGN, false, T>(t, reinterpret_cast<const T*>(src + n1), G::N2, nullptr, -1, true, tw1, tile, G::R);
+        cl_row_landed();                                        // own 16 points are in own tile slots
+        cl_row_pass1<C, SIGN, T>(t, tw1, tile);
         __syncthreads();
         k2_pass2<C, SIGN, T>(t, tw2, tile);
         __syncthreads();
         cpx<T> u[16];
         k2_pass3<C, SIGN, T>(t, tile, u);
+        __syncthreads();                                        // every pass-3 read done: the tile can take the next row
+        if (q + 1 < Q) cl_row_issue<C, G::R, T>(t, src + n1 + CL, tile);
+        else if (tr + nclusters < batch) cl_row_issue<C, G::R, T>(t, src + nclusters * (long long)G::NC + rank, tile);
         if (q == 0) cluster_wait();                             // every CTA finished its previous combine: park free
         cl_park<C, CL, Q, SIGN, T>(t, n1, u, twP, remote);
-        if (q + 1 < Q) __syncthreads();                         // pass-3 reads of the tile done before the next pass 1
       }
     }
     cluster_arrive(); cluster_wait();                           // all rows parked (release/acquire orders the DSMEM stores)
     cl_combine<C, CL, Q, SIGN, T>(t, rank, park, dst);
-    cluster_arrive();                                           // "park buffers free" for the next transform
+    cluster_arrive_relaxed();                                   // "park buffers free" for the next transform
   }
   cluster_wait();                                               // no CTA exits while a peer may still address its memory
 }

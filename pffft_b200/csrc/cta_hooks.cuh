@@ -151,20 +151,25 @@ bool cluster_shape_exists(int CL, int Q, bool scatter);
 int cluster_max_active_float(int CL, int Q, bool scatter);      // co-resident clusters on the current device (0: unusable)
 int cluster_launch_float(int CL, int Q, bool scatter, int sign, const cpx<float>* src, cpx<float>* dst, long long batch,
                          const cpx<float>* tw1, const cpx<float>* tw2, const cpx<float>* twP, cudaStream_t st);
-// cluster shape for a float plan R x N2 (0 = none).  PFFFT_B200_CLUSTER=0 disables, PFFFT_B200_CLUSTER_SCATTER=0/1 picks
-// the row distribution (strided L2 reads / DSMEM scatter), PFFFT_B200_CLUSTER_R16=16 runs 65536 on 16-CTA clusters,
-// PFFFT_B200_CLUSTER_8192=1 also moves 2 x 4096 from the single-CTA kernel to a 2-CTA cluster.
+// cluster shape for a float plan R x N2 (false = none).  Measured on B200 (profiles/r01b_cluster.md): only 4 x 4096 beats
+// the two-pass plan (0.41 vs 0.38 of HBM peak), so it is the one default; the other shapes stay selectable:
+//   PFFFT_B200_CLUSTER=0 none, =all every shape that exists (8 x 4096 on 8 CTAs, 16 x 4096 on 8 CTAs x 2 rows);
+//   PFFFT_B200_CLUSTER_SCATTER=1 rows distributed through DSMEM instead of strided L2 reads (one row per CTA only);
+//   PFFFT_B200_CLUSTER_R16=16 runs 16 x 4096 on 16-CTA clusters; PFFFT_B200_CLUSTER_8192=1 moves 2 x 4096 from the
+//   single-CTA kernel to a 2-CTA cluster.
 inline bool cluster_choose(int R, int N2, int* CL, int* Q, bool* scatter) {
   if (N2 != 4096) return false;
-  if (const char* e = getenv("PFFFT_B200_CLUSTER")) if (atoi(e) == 0) return false;
-  bool sc = true;
+  bool all = false;
+  if (const char* e = getenv("PFFFT_B200_CLUSTER")) { if (!strcmp(e, "0")) return false; all = !strcmp(e, "all") || !strcmp(e, "1"); }
+  bool sc = false;
   if (const char* e = getenv("PFFFT_B200_CLUSTER_SCATTER")) sc = atoi(e) != 0;
   int cl = 0, q = 1;
   switch (R) {
     case 2: if (getenv("PFFFT_B200_CLUSTER_8192") && atoi(getenv("PFFFT_B200_CLUSTER_8192"))) cl = 2; break;
     case 4: cl = 4; break;
-    case 8: cl = 8; break;
+    case 8: if (all) cl = 8; break;
     case 16:
+      if (!all) break;
       if (getenv("PFFFT_B200_CLUSTER_R16") && atoi(getenv("PFFFT_B200_CLUSTER_R16")) == 16) cl = 16;
       else { cl = 8; q = 2; }
       break;

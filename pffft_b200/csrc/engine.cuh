@@ -319,32 +319,31 @@ int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device
   if (chunk > batch) chunk = batch;
   int rc = ensure_slots(s, (size_t)chunk * per);
   if (rc) return rc;
-  // Chunk schedule: sizes double from chunk/32 up to `chunk` at the head and mirror back down at the tail, so the
-  // un-overlapped first H2D copy and last D2H copy (pipeline fill and drain) are ~1 MiB instead of a whole 32 MiB chunk
-  // (at 2^16 transforms of 8 KiB per call, fill + drain of full-size chunks cost 11 % of the call).
-  const long long c0 = chunk / 32 > 0 ? chunk / 32 : 1;
-  int ramp_steps = 0;
-  long long ramp = 0;
-  static const bool ramp_on = getenv("PFFFT_B200_RAMP") ? atoi(getenv("PFFFT_B200_RAMP")) != 0 : true;     // A/B switch
-  while (ramp_on && (c0 << ramp_steps) < chunk && 2 * (ramp + (c0 << ramp_steps)) <= batch) { ramp += c0 << ramp_steps; ++ramp_steps; }
+  // (a ramped schedule -- 1 MiB first/last chunks doubling up to 32 MiB to shorten pipeline fill and drain -- was
+  //  measured SLOWER on the B200 box: 4.73 M vs 5.12 M FFT/s at 2^16 transforms per call; fixed 32 MiB chunks stay)
+  // Output side: when `out` is page-locked AND mapped (pffft_aligned_malloc, cudaHostAlloc, cudaHostRegister) the kernels
+  // can store straight into it over PCIe (posted writes, whole 128-byte lines) -- no device staging buffer and no D2H
+  // copy; the input keeps coming through the copy engine (SM reads over PCIe are latency bound).  PFFFT_B200_ZC_OUT=1.
+  static const bool zc_out = getenv("PFFFT_B200_ZC_OUT") ? atoi(getenv("PFFFT_B200_ZC_OUT")) != 0 : false;
+  T* out_alias = nullptr;
+  if (zc_out) { void* d = nullptr; if (host_mapped_pointer(out, &d)) out_alias = (T*)d; }
   int i = 0;
   long long b0 = 0;
   auto submit = [&](long long nb) -> int {
     Slot& sl = s->slot[i];
     PF_CUDA_OK(cudaMemcpyAsync(sl.d_in, in + (size_t)b0 * per, (size_t)nb * per * sizeof(T), cudaMemcpyHostToDevice, sl.stream));
-    const int r = device_op((const T*)sl.d_in, (T*)sl.d_out, nb, sl.stream);
-    if (r) return r;
-    PF_CUDA_OK(cudaMemcpyAsync(out + (size_t)b0 * per, sl.d_out, (size_t)nb * per * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+    if (out_alias) {
+      const int r = device_op((const T*)sl.d_in, out_alias + (size_t)b0 * per, nb, sl.stream);
+      if (r) return r;
+    } else {
+      const int r = device_op((const T*)sl.d_in, (T*)sl.d_out, nb, sl.stream);
+      if (r) return r;
+      PF_CUDA_OK(cudaMemcpyAsync(out + (size_t)b0 * per, sl.d_out, (size_t)nb * per * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+    }
     b0 += nb; i = (i + 1) % 3;
     return 0;
   };
-  for (int j = 0; j < ramp_steps; ++j) { rc = submit(c0 << j); if (rc) return rc; }
-  for (long long mid = batch - 2 * ramp; mid > 0; ) {
-    const long long nb = mid < chunk ? mid : chunk;
-    rc = submit(nb); if (rc) return rc;
-    mid -= nb;
-  }
-  for (int j = ramp_steps - 1; j >= 0; --j) { rc = submit(c0 << j); if (rc) return rc; }
+  while (b0 < batch) { rc = submit((batch - b0 < chunk) ? (batch - b0) : chunk); if (rc) return rc; }
   for (int k = 0; k < 3; ++k) PF_CUDA_OK(cudaStreamSynchronize(s->slot[k].stream));
   if (cur != s->device) cudaSetDevice(cur);
   return 0;

@@ -33,6 +33,10 @@ struct PFFASTCONV_Setup {
   float* d_spec = nullptr; size_t spec_elems = 0;
   float* d_x = nullptr;    size_t x_elems = 0;     // host input staging / planar split
   float* d_y = nullptr;    size_t y_elems = 0;     // host output staging / planar split
+  // host-pointer calls: the stream is cut into pieces that move through three internal streams, so the H2D copy of
+  // piece c+1, the kernel of piece c and the D2H copy of piece c-1 overlap (PCIe is full duplex)
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t h2d_done[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -196,6 +200,7 @@ PFFASTCONV_EXPORT void pffastconv_destroy_setup(PFFASTCONV_Setup* s) {
   if (s->d_spec) cudaFree(s->d_spec);
   if (s->d_x) cudaFree(s->d_x);
   if (s->d_y) cudaFree(s->d_y);
+  for (int k = 0; k < 3; ++k) { if (s->hs[k]) cudaStreamDestroy(s->hs[k]); if (s->h2d_done[k]) cudaEventDestroy(s->h2d_done[k]); }
   pffft_destroy_setup(s->st);
   delete s;
 }
@@ -227,6 +232,53 @@ PFFASTCONV_EXPORT int pffastconv_apply(PFFASTCONV_Setup* s, const float* input, 
   if ((rc = grow(&s->d_y, &s->y_elems, need_y + 8))) return 0;
   float* x_planes = s->d_x;
   float* y_planes = s->d_y;
+  if (!din && !two_planes && s->d_Hc && s->tabs.C && getenv("PFFFT_B200_CONV_NO_PIPELINE") == nullptr) {
+    // ---- pipelined host path (fused kernel only: it needs no per-call scratch, so pieces may overlap freely)
+    float* hx = s->d_x; float* hy = s->d_y;
+    hx += (4 - ((uintptr_t)hx / sizeof(float)) % 4) % 4;
+    hy += (4 - ((uintptr_t)hy / sizeof(float)) % 4) % 4;
+    for (int k = 0; k < 3; ++k) {
+      if (!s->hs[k] && cudaStreamCreateWithFlags(&s->hs[k], cudaStreamNonBlocking) != cudaSuccess) { pf::set_error("pffastconv_apply: stream", cudaGetLastError()); return 0; }
+      if (!s->h2d_done[k] && cudaEventCreateWithFlags(&s->h2d_done[k], cudaEventDisableTiming) != cudaSuccess) { pf::set_error("pffastconv_apply: event", cudaGetLastError()); return 0; }
+    }
+    const long long nblk = bp.n_full + (bp.tail_off >= 0 ? 1 : 0);
+    size_t piece_bytes = (size_t)8 << 20;                      // ~8 MiB of new input per piece (PFFFT_B200_CONV_PIECE_KB overrides)
+    if (const char* e = getenv("PFFFT_B200_CONV_PIECE_KB")) { const long kb = atol(e); if (kb > 0) piece_bytes = (size_t)kb << 10; }
+    long long per_piece = (long long)(piece_bytes / ((size_t)bp.stride * sizeof(float)));
+    if (per_piece < 1) per_piece = 1;
+    long long copied = 0;                                      // input floats already on their way to the device
+    int k = 0;
+    bool okp = true;
+    for (long long b0 = 0; b0 < nblk && okp; b0 += per_piece, k = (k + 1) % 3) {
+      const long long b1 = (b0 + per_piece < nblk) ? b0 + per_piece : nblk;
+      const long long off0 = b0 * bp.stride;
+      long long in_end = (b1 - 1) * bp.stride + s->Nfft;       // last sample the piece reads (window of its last block)
+      if (in_end > inputLen) in_end = inputLen;
+      cudaStream_t ps = s->hs[k];
+      if (in_end > copied) {
+        okp = cudaMemcpyAsync(hx + copied, input + copied, (size_t)(in_end - copied) * sizeof(float), cudaMemcpyHostToDevice, ps) == cudaSuccess;
+        copied = in_end;
+      }
+      okp = okp && cudaEventRecord(s->h2d_done[k], ps) == cudaSuccess;
+      // the head of this piece's first window was copied by the previous piece, on another stream
+      if (b0 > 0) {
+        okp = okp && cudaStreamWaitEvent(ps, s->h2d_done[(k + 2) % 3], 0) == cudaSuccess;
+        okp = okp && cudaStreamWaitEvent(ps, s->h2d_done[(k + 1) % 3], 0) == cudaSuccess;   // (one-block pieces of huge Nfft)
+      }
+      BlockPlan sub;
+      sub.stride = bp.stride;
+      const bool has_tail = bp.tail_off >= 0 && b1 == nblk;
+      sub.n_full = (b1 - b0) - (has_tail ? 1 : 0);
+      sub.tail_off = has_tail ? bp.tail_off - off0 : -1;
+      sub.tail_out = has_tail ? bp.tail_out : 0;
+      const long long out_count = sub.n_full * bp.stride + sub.tail_out;
+      okp = okp && conv_stream(s, hx + off0, inputLen - off0, hy + off0, sub, ps) == 0;
+      okp = okp && cudaMemcpyAsync(output + off0, hy + off0, (size_t)out_count * sizeof(float), cudaMemcpyDeviceToHost, ps) == cudaSuccess;
+    }
+    for (int q = 0; q < 3; ++q) okp = (cudaStreamSynchronize(s->hs[q]) == cudaSuccess) && okp;
+    if (!okp) { pf::set_error("pffastconv_apply: pipelined host path", cudaGetLastError()); return 0; }
+    return (int)(bp.produced / cplxFactor);
+  }
   if (!din) {
     float* hx = s->d_x + (two_planes ? 2 * (size_t)cplxInputLen : 0);
     float* hy = s->d_y + (two_planes ? 2 * (size_t)bp.produced : 0);

@@ -276,8 +276,8 @@ static void emu_cluster_run(const float* in, float* out) {
     for (int q = 0; q < Q; ++q)
       for (int c = 0; c < CL; ++c) {
         const int n1 = c + CL * q;
-        for (int t = 0; t < K::T; ++t)
-          k2_pass1<C, L_C_ORD, SIGN, false, float>(t, reinterpret_cast<const float*>(src + n1), G::N2, nullptr, -1, true, tw1, tile[c].data(), G::R);
+        for (int t = 0; t < K::T; ++t) cl_row_issue<C, G::R, float>(t, src + n1, tile[c].data());
+        for (int t = 0; t < K::T; ++t) cl_row_pass1<C, SIGN, float>(t, tw1, tile[c].data());
         for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, tw2, tile[c].data());
         for (int t = 0; t < K::T; ++t) { k2_pass3<C, SIGN, float>(t, tile[c].data(), u_of(c, t)); cl_park<C, CL, Q, SIGN, float>(t, n1, u_of(c, t), twP, remote); }
       }

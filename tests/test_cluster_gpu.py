@@ -15,11 +15,11 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [
     (16384, {"PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster4_4x4096_dsmem_rows"),
     (16384, {"PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster4_4x4096"),
-    (32768, {"PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster8_8x4096_dsmem_rows"),
-    (32768, {"PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster8_8x4096"),
-    (65536, {}, "cluster8_16x4096"),
-    (65536, {"PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster16_16x4096_dsmem_rows"),
-    (65536, {"PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster16_16x4096"),
+    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster8_8x4096_dsmem_rows"),
+    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster8_8x4096"),
+    (65536, {"PFFFT_B200_CLUSTER": "all"}, "cluster8_16x4096"),
+    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster16_16x4096_dsmem_rows"),
+    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster16_16x4096"),
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster2_2x4096_dsmem_rows"),
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster2_2x4096"),
 ]
@@ -117,7 +117,7 @@ def test_cluster_persistent_loop_position_independent(pf, N, env, name):
 def test_real_and_zdomain_wrap_the_cluster_kernel(pf, ref, R, N):
     """real N = 2 x Nc and the z-domain layouts run the cluster kernel between the generic load / store passes"""
     import torch
-    s = make_setup(pf, N, 0, {}, "cluster")
+    s = make_setup(pf, N, 0, {"PFFFT_B200_CLUSTER": "all"}, "cluster")
     try:
         rng = np.random.default_rng(N)
         x = uniform(rng, 2 * N).reshape(2, N)

@@ -134,3 +134,28 @@ def test_c4_config_sampled(pf):
         worst = max(worst, abs(float(y[p]) - want))
     assert worst <= lim, (worst, lim)
     assert worst <= 4 * float(np.spacing(np.float32(np.abs(y).max()))), worst   # and in fact within a few ulp
+
+
+@pytest.mark.parametrize("flags_name", ["real", "cplx_single"])
+@pytest.mark.parametrize("flush", [0, 1])
+def test_host_pointer_pipeline_equals_device_call(pf, flags_name, flush):
+    """host-pointer calls cut the stream into pieces that overlap H2D / kernel / D2H on three streams; every piece size
+    (one block per piece up to the whole stream) must give exactly the samples of the one-launch device-pointer call"""
+    flags = 0 if flags_name == "real" else (pf.PFFASTCONV_CPLX_INP_OUT | pf.PFFASTCONV_CPLX_SINGLE_FFT)
+    taps = 301
+    n = 70000 + 37                                      # real samples / complex samples
+    x, h = inputs(n * (2 if flags else 1), taps)
+    want, n_dev, bl = gpu_conv(pf, h, x, 1024, flags, flush, device_ptrs=True)
+    assert n_dev > 0
+    old = os.environ.get("PFFFT_B200_CONV_PIECE_KB")
+    try:
+        for kb in ("1", "4", "24", "100", "100000"):    # 1 KiB -> one block per piece
+            os.environ["PFFFT_B200_CONV_PIECE_KB"] = kb
+            got, n_host, _ = gpu_conv(pf, h, x, 1024, flags, flush, device_ptrs=False)
+            assert n_host == n_dev, (kb, n_host, n_dev)
+            assert np.array_equal(got, want), kb
+    finally:
+        if old is None:
+            os.environ.pop("PFFFT_B200_CONV_PIECE_KB", None)
+        else:
+            os.environ["PFFFT_B200_CONV_PIECE_KB"] = old

@@ -366,6 +366,8 @@ def test_kernel_selection_reports_tuned_kernel(pf):
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "split_16x4096"
+    with pf.Setup(16384, 1) as s:
+        assert s.kernel in ("cluster4_4x4096", "split_4x4096")      # 4-CTA clusters where the device schedules them
     with pf.Setup(1 << 20, 1) as s:
         assert s.kernel == "global_stockham"
     with pf.Setup(256, 1) as s:
