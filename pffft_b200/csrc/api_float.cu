@@ -214,10 +214,10 @@ template <> struct FastHooks<float> {
         s->split_R = R; s->split_N2 = N2;
         s->split_fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_fused_ok<float>(R, N2);
         s->fast_variant = 300;
-        int CL = 0, Q = 1; bool scatter = false;
-        if (cluster_choose(R, N2, &CL, &Q, &scatter)) {
-          s->split_cluster = CL; s->split_Q = Q; s->split_scatter = scatter; s->split_fused = false;
-          snprintf(s->name_buf, sizeof(s->name_buf), "cluster%d_%dx%d%s", CL, R, N2, scatter ? "_dsmem_rows" : "");
+        int CL = 0, Q = 1, mode = 0;
+        if (cluster_choose(R, N2, &CL, &Q, &mode)) {
+          s->split_cluster = CL; s->split_Q = Q; s->split_mode = mode; s->split_fused = false;
+          snprintf(s->name_buf, sizeof(s->name_buf), "cluster%d_%dx%d%s", CL, R, N2, mode == 1 ? "_dsmem_rows" : "");
         } else
         snprintf(s->name_buf, sizeof(s->name_buf), s->split_fused ? "cta_split_%dx%d" : "split_%dx%d", R, N2);
         s->kernel_name = s->name_buf;

@@ -8,14 +8,15 @@
 namespace pf {
 namespace {
 
-template <int C, int CL, int Q, int SIGN, bool SCATTER> struct ClusterLaunch {
+// MODE 0: rows read with element stride R; 1: rows distributed through DSMEM
+template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
   using G = KCL<C, CL, Q>;
   static constexpr size_t kSmem = (size_t)(1 + Q) * G::N2 * sizeof(cpx<float>);
   // CTAs per SM the register budget is sized for: what the shared memory admits (227 KB per SM), at most 1024 threads
   static constexpr int kBySmem = (int)((227 * 1024) / (kSmem + 1024));
   static constexpr int kByThreads = 1024 / (16 * C);
   static constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kByThreads ? kBySmem : kByThreads);
-  static auto kernel() { return k_cluster_fft<float, C, CL, Q, SIGN, SCATTER, MINB>; }
+  static auto kernel() { return k_cluster_fft<float, C, CL, Q, SIGN, MODE == 1, MINB>; }
 
   static int prepare(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, cudaStream_t st) {
     static thread_local bool configured = false;
@@ -59,28 +60,27 @@ template <int C, int CL, int Q, int SIGN, bool SCATTER> struct ClusterLaunch {
   }
 };
 
-// (CL, Q, scatter) shapes that exist; every one is built for both directions
-#define PF_CLUSTER_SHAPES(X) X(2, 1, false) X(2, 1, true) X(4, 1, false) X(4, 1, true) X(8, 1, false) X(8, 1, true) \
-                             X(8, 2, false) X(16, 1, false) X(16, 1, true)
+// (CL, Q, mode) shapes that exist; every one is built for both directions
+#define PF_CLUSTER_SHAPES(X) X(2, 1, 0) X(2, 1, 1) X(4, 1, 0) X(4, 1, 1) X(8, 1, 0) X(8, 1, 1) X(8, 2, 0) X(16, 1, 0) X(16, 1, 1)
 
 }  // namespace
 
-bool cluster_shape_exists(int CL, int Q, bool scatter) {
-#define X(cl, q, sc) if (CL == cl && Q == q && scatter == sc) return true;
+bool cluster_shape_exists(int CL, int Q, int mode) {
+#define X(cl, q, sc) if (CL == cl && Q == q && mode == sc) return true;
   PF_CLUSTER_SHAPES(X)
 #undef X
   return false;
 }
-int cluster_max_active_float(int CL, int Q, bool scatter) {
-#define X(cl, q, sc) if (CL == cl && Q == q && scatter == sc) return ClusterLaunch<16, cl, q, -1, sc>::max_active();
+int cluster_max_active_float(int CL, int Q, int mode) {
+#define X(cl, q, sc) if (CL == cl && Q == q && mode == sc) return ClusterLaunch<16, cl, q, -1, sc>::max_active();
   PF_CLUSTER_SHAPES(X)
 #undef X
   return 0;
 }
-int cluster_launch_float(int CL, int Q, bool scatter, int sign, const cf* src, cf* dst, long long batch,
+int cluster_launch_float(int CL, int Q, int mode, int sign, const cf* src, cf* dst, long long batch,
                          const cf* tw1, const cf* tw2, const cf* twP, cudaStream_t st) {
 #define X(cl, q, sc)                                                                                         \
-  if (CL == cl && Q == q && scatter == sc)                                                                   \
+  if (CL == cl && Q == q && mode == sc)                                                                   \
     return sign < 0 ? ClusterLaunch<16, cl, q, -1, sc>::launch(src, dst, batch, tw1, tw2, twP, st)           \
                     : ClusterLaunch<16, cl, q, +1, sc>::launch(src, dst, batch, tw1, tw2, twP, st);
   PF_CLUSTER_SHAPES(X)

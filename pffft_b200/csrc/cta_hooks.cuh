@@ -145,24 +145,29 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
   return 0;
 }
 
+// (A decimation-in-frequency order -- dense radix-R pre-pass, then rows whose STORES carry the element stride R -- was
+//  built and measured: 0.25 / 0.22 / 0.17 of HBM peak at 16384 / 32768 / 65536 against 0.38 / 0.34 / 0.24 for this
+//  order.  Partial-sector stores cost more than the strided loads they replace; stores stay dense.)
+
 // ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked
 // in the distributed shared memory of a CL-CTA cluster -> one HBM round trip for 16384 .. 65536 points
-bool cluster_shape_exists(int CL, int Q, bool scatter);
-int cluster_max_active_float(int CL, int Q, bool scatter);      // co-resident clusters on the current device (0: unusable)
-int cluster_launch_float(int CL, int Q, bool scatter, int sign, const cpx<float>* src, cpx<float>* dst, long long batch,
+// mode 0: rows read with element stride R; 1: rows distributed through DSMEM
+bool cluster_shape_exists(int CL, int Q, int mode);
+int cluster_max_active_float(int CL, int Q, int mode);          // co-resident clusters on the current device (0: unusable)
+int cluster_launch_float(int CL, int Q, int mode, int sign, const cpx<float>* src, cpx<float>* dst, long long batch,
                          const cpx<float>* tw1, const cpx<float>* tw2, const cpx<float>* twP, cudaStream_t st);
 // cluster shape for a float plan R x N2 (false = none).  Measured on B200 (profiles/r01b_cluster.md): only 4 x 4096 beats
 // the two-pass plan (0.41 vs 0.38 of HBM peak), so it is the one default; the other shapes stay selectable:
 //   PFFFT_B200_CLUSTER=0 none, =all every shape that exists (8 x 4096 on 8 CTAs, 16 x 4096 on 8 CTAs x 2 rows);
-//   PFFFT_B200_CLUSTER_SCATTER=1 rows distributed through DSMEM instead of strided L2 reads (one row per CTA only);
+//   PFFFT_B200_CLUSTER_MODE=0 strided row reads, =1 rows distributed through DSMEM (one row per CTA only);
 //   PFFFT_B200_CLUSTER_R16=16 runs 16 x 4096 on 16-CTA clusters; PFFFT_B200_CLUSTER_8192=1 moves 2 x 4096 from the
 //   single-CTA kernel to a 2-CTA cluster.
-inline bool cluster_choose(int R, int N2, int* CL, int* Q, bool* scatter) {
+inline bool cluster_choose(int R, int N2, int* CL, int* Q, int* mode) {
   if (N2 != 4096) return false;
   bool all = false;
   if (const char* e = getenv("PFFFT_B200_CLUSTER")) { if (!strcmp(e, "0")) return false; all = !strcmp(e, "all") || !strcmp(e, "1"); }
-  bool sc = false;
-  if (const char* e = getenv("PFFFT_B200_CLUSTER_SCATTER")) sc = atoi(e) != 0;
+  int sc = 0;
+  if (const char* e = getenv("PFFFT_B200_CLUSTER_MODE")) { sc = atoi(e); if (sc < 0 || sc > 1) sc = 0; }
   int cl = 0, q = 1;
   switch (R) {
     case 2: if (getenv("PFFFT_B200_CLUSTER_8192") && atoi(getenv("PFFFT_B200_CLUSTER_8192"))) cl = 2; break;
@@ -175,10 +180,10 @@ inline bool cluster_choose(int R, int N2, int* CL, int* Q, bool* scatter) {
       break;
   }
   if (!cl) return false;
-  if (q > 1) sc = false;
+  if (q > 1) sc = 0;
   if (!cluster_shape_exists(cl, q, sc)) return false;
   if (cluster_max_active_float(cl, q, sc) <= 0) return false;
-  *CL = cl; *Q = q; *scatter = sc;
+  *CL = cl; *Q = q; *mode = sc;
   return true;
 }
 
@@ -273,7 +278,7 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   if (s->split_cluster > 0) {
     int rc = (int)cudaErrorInvalidValue;
     if constexpr (sizeof(T) == 4)
-      rc = cluster_launch_float(s->split_cluster, s->split_Q, s->split_scatter, SIGN, src, dst, p.batch, s->tw_fast,
+      rc = cluster_launch_float(s->split_cluster, s->split_Q, s->split_mode, SIGN, src, dst, p.batch, s->tw_fast,
                                 s->tw_fast + s->split_N2, s->tw_fast + cta_table_cpx(s->split_N2), st);
     if (rc) return rc;
   } else if (s->split_fused) {

@@ -66,7 +66,7 @@ template <typename T> struct Setup {
   int split_R = 0, split_N2 = 0;          // Nc = split_R x split_N2 two-level plans (rows on a tuned kernel + radix-R combine)
   bool split_fused = false;               // ... small enough for ONE kernel (rows parked in shared memory): one HBM round trip
   int split_cluster = 0, split_Q = 1;     // ... or ONE kernel on clusters of split_cluster CTAs (rows parked in DSMEM), split_Q rows per CTA
-  bool split_scatter = false;             //     rows distributed through DSMEM (dense HBM reads) instead of strided L2 reads
+  int split_mode = 0;                     //     0 strided row reads, 1 rows distributed through DSMEM
   char name_buf[40] = {0};
   int tpc = 1;                            // transforms resident per CTA (shared-memory kernel), a power of two
   int log2_tpt = 8;                       // log2(threads per transform) = log2(256 / tpc)

@@ -13,17 +13,17 @@ pytestmark = pytest.mark.gpu
 
 # (N complex, env overrides, expected kernel-name prefix)
 VARIANTS = [
-    (16384, {"PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster4_4x4096_dsmem_rows"),
-    (16384, {"PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster4_4x4096"),
-    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster8_8x4096_dsmem_rows"),
-    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster8_8x4096"),
+    (16384, {"PFFFT_B200_CLUSTER_MODE": "1"}, "cluster4_4x4096_dsmem_rows"),
+    (16384, {"PFFFT_B200_CLUSTER_MODE": "0"}, "cluster4_4x4096"),
+    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster8_8x4096_dsmem_rows"),
+    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster8_8x4096"),
     (65536, {"PFFFT_B200_CLUSTER": "all"}, "cluster8_16x4096"),
-    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster16_16x4096_dsmem_rows"),
-    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster16_16x4096"),
-    (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_SCATTER": "1"}, "cluster2_2x4096_dsmem_rows"),
-    (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_SCATTER": "0"}, "cluster2_2x4096"),
+    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster16_16x4096_dsmem_rows"),
+    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster16_16x4096"),
+    (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster2_2x4096_dsmem_rows"),
+    (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster2_2x4096"),
 ]
-ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_SCATTER", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192")
+ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192")
 
 
 class env_set:
@@ -137,14 +137,22 @@ def test_real_and_zdomain_wrap_the_cluster_kernel(pf, ref, R, N):
         s.close()
 
 
-def test_cluster_switch_off_falls_back_to_two_pass(pf, ref, R):
+@pytest.mark.parametrize("N", [16384, 36864, 65536])
+def test_cluster_switch_off_falls_back_to_two_pass(pf, ref, R, N):
     import torch
     with env_set({"PFFFT_B200_CLUSTER": "0"}):
-        s = pf.Setup(16384, 1)
-    try:
-        assert s.kernel.startswith("split_"), s.kernel
-        x = uniform(np.random.default_rng(5), 2 * 16384)[None, :]
-        y = s.transform_batch(torch.from_numpy(x).cuda(), 0, True).cpu().numpy()
-        assert R.relmax(y[0], ref.transform_batch(16384, 1, x, 0, True)[0]) <= 1e-5
-    finally:
-        s.close()
+        s = pf.Setup(N, 1)
+        try:
+            assert s.kernel.startswith("split_"), s.kernel
+            x = uniform(np.random.default_rng(5), 3 * 2 * N).reshape(3, 2 * N)
+            xd = torch.from_numpy(x).cuda()
+            y = s.transform_batch(xd, 0, True)
+            want = ref.transform_batch(N, 1, x[:1], 0, True)
+            assert R.relmax(y[0].cpu().numpy(), want[0]) <= 1e-5
+            z = s.transform_batch(y, 1, True)
+            assert float(((z / N - xd) ** 2).sum(dim=1).max()) <= N * 1e-7
+            xi = xd.clone()
+            s.transform_batch(xi, 0, True, out=xi)
+            assert torch.equal(xi, y)
+        finally:
+            s.close()
