@@ -8,7 +8,7 @@
 namespace pf {
 namespace {
 
-// MODE 0: rows read with element stride R; 1: rows distributed through DSMEM
+// MODE 0: strided rows staged by cp.async; 1: rows distributed through DSMEM
 template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
   using G = KCL<C, CL, Q>;
   static constexpr size_t kSmem = (size_t)(1 + Q) * G::N2 * sizeof(cpx<float>);
@@ -16,7 +16,7 @@ template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
   static constexpr int kBySmem = (int)((227 * 1024) / (kSmem + 1024));
   static constexpr int kByThreads = 1024 / (16 * C);
   static constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kByThreads ? kBySmem : kByThreads);
-  static auto kernel() { return k_cluster_fft<float, C, CL, Q, SIGN, MODE == 1, MINB>; }
+  static auto kernel() { return k_cluster_fft<float, C, CL, Q, SIGN, MODE, MINB>; }
 
   static int prepare(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, cudaStream_t st) {
     static thread_local bool configured = false;
@@ -61,7 +61,8 @@ template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
 };
 
 // (CL, Q, mode) shapes that exist; every one is built for both directions
-#define PF_CLUSTER_SHAPES(X) X(2, 1, 0) X(2, 1, 1) X(4, 1, 0) X(4, 1, 1) X(8, 1, 0) X(8, 1, 1) X(8, 2, 0) X(16, 1, 0) X(16, 1, 1)
+#define PF_CLUSTER_SHAPES(X) X(2, 1, 0) X(2, 1, 1) X(4, 1, 0) X(4, 1, 1) X(8, 1, 0) X(8, 1, 1) X(8, 2, 0) X(16, 1, 0) X(16, 1, 1) \
+                             X(4, 2, 0) X(4, 4, 0)
 
 }  // namespace
 

@@ -175,11 +175,15 @@ template <typename T> struct ClusterRemote {
 
 // gridDim.x = (#clusters) * CL, cluster dimension CL (launch attribute), blockDim.x = 16*C.
 // shared memory: tile [N2] + park [Q*N2] complex words (SCATTER: the park buffer doubles as the row staging buffer).
-template <typename T, int C, int CL, int Q, int SIGN, bool SCATTER, int MINB>
+// MODE 0: next row staged by cp.async (LDGSTS) into the thread's own tile slots;  1: rows distributed through DSMEM (SCATTER).
+// (Measured and dropped: plain loads inside pass 1 with the next row only prefetched into L2 by prefetch.global.L2 --
+//  0.38 / 0.27 / 0.16 of HBM peak at 16384 / 32768 / 65536 against 0.41 / 0.33 / 0.23 for the cp.async staging.)
+template <typename T, int C, int CL, int Q, int SIGN, int MODE, int MINB>
 __global__ void __launch_bounds__(16 * C, MINB)
 k_cluster_fft(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T>* tw2, const cpx<T>* twP) {
   using K = K2<C>;
   using G = KCL<C, CL, Q>;
+  constexpr bool SCATTER = MODE == 1;
   static_assert(!SCATTER || Q == 1, "the staging buffer aliases the park buffer: one row per CTA");
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);

@@ -134,11 +134,18 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
   const long long work = batch * N2;
   long long g = (work + 255) / 256; const long long cap = (long long)s->sm_count * 16;
   if (g > cap) g = cap; if (g < 1) g = 1;
+  // combine twiddles W_Nc^{n1 k2}: row-major copy (unit-stride reads) when the plan carries one (CTA-core rows), else the
+  // natural table exp(-2 pi i k / Nc) read at n1*k2
+  const bool rm = cta_C_for(N2) != 0;
+  const cpx<T>* tw = rm ? s->tw_fast + cta_table_cpx(N2) : s->tw;
   switch (R) {
-#define PF_CMB(r) case r: k_split_combine_any<T, r, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+#define PF_CMB(r) case r: if (rm) k_split_combine_any<T, r, SIGN, true><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, tw); \
+                          else k_split_combine_any<T, r, SIGN, false><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, tw); break;
     PF_CMB(2) PF_CMB(3) PF_CMB(4) PF_CMB(5) PF_CMB(6) PF_CMB(8) PF_CMB(9) PF_CMB(10) PF_CMB(12) PF_CMB(15)
 #undef PF_CMB
-    default: k_split_combine<T, 16, SIGN><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, s->tw); break;
+    default: if (rm) k_split_combine<T, 16, SIGN, true><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, tw);
+             else k_split_combine<T, 16, SIGN, false><<<(int)g, 256, 0, st>>>(rows, dst, batch, N2, tw);
+             break;
   }
   count_launch();
   PF_CUDA_OK(cudaGetLastError());
@@ -151,7 +158,7 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 
 // ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked
 // in the distributed shared memory of a CL-CTA cluster -> one HBM round trip for 16384 .. 65536 points
-// mode 0: rows read with element stride R; 1: rows distributed through DSMEM
+// mode 0: strided rows staged by cp.async; 1: rows distributed through DSMEM
 bool cluster_shape_exists(int CL, int Q, int mode);
 int cluster_max_active_float(int CL, int Q, int mode);          // co-resident clusters on the current device (0: unusable)
 int cluster_launch_float(int CL, int Q, int mode, int sign, const cpx<float>* src, cpx<float>* dst, long long batch,
@@ -159,7 +166,8 @@ int cluster_launch_float(int CL, int Q, int mode, int sign, const cpx<float>* sr
 // cluster shape for a float plan R x N2 (false = none).  Measured on B200 (profiles/r01b_cluster.md): only 4 x 4096 beats
 // the two-pass plan (0.41 vs 0.38 of HBM peak), so it is the one default; the other shapes stay selectable:
 //   PFFFT_B200_CLUSTER=0 none, =all every shape that exists (8 x 4096 on 8 CTAs, 16 x 4096 on 8 CTAs x 2 rows);
-//   PFFFT_B200_CLUSTER_MODE=0 strided row reads, =1 rows distributed through DSMEM (one row per CTA only);
+//   PFFFT_B200_CLUSTER_MODE=0 strided rows staged by cp.async, =1 rows distributed through DSMEM (one row per CTA only);
+//   PFFFT_B200_CLUSTER_SHAPE=CLxQ picks the cluster size and rows per CTA for R = CL*Q (4x2, 4x4, 8x2, 16x1 ...);
 //   PFFFT_B200_CLUSTER_R16=16 runs 16 x 4096 on 16-CTA clusters; PFFFT_B200_CLUSTER_8192=1 moves 2 x 4096 from the
 //   single-CTA kernel to a 2-CTA cluster.
 inline bool cluster_choose(int R, int N2, int* CL, int* Q, int* mode) {
@@ -178,6 +186,10 @@ inline bool cluster_choose(int R, int N2, int* CL, int* Q, int* mode) {
       if (getenv("PFFFT_B200_CLUSTER_R16") && atoi(getenv("PFFFT_B200_CLUSTER_R16")) == 16) cl = 16;
       else { cl = 8; q = 2; }
       break;
+  }
+  if (const char* e = getenv("PFFFT_B200_CLUSTER_SHAPE")) {       // "CLxQ", e.g. 4x2: 8 rows on 4-CTA clusters, 2 rows per CTA
+    int a = 0, b = 0;
+    if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b == R) { cl = a; q = b; }
   }
   if (!cl) return false;
   if (q > 1) sc = 0;

@@ -358,7 +358,40 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
 // twP[n1*N2 + k] = exp(-2 pi i n1 k / Nc) is the row-major copy of the combine twiddles (unit-stride reads per row).
 // Shared memory: (R + 1) * N2 complex words.  Complex canonical in and out only (other layouts wrap it).
 // ---------------------------------------------------------------------------------------------------------------
+// park one finished row: thread t holds u[r*C + kc] = Y_n1[k] (k = k2_out_index); slot of (n1, k) is rows[n1*RS + k*KS]
+// (row-major: RS = N2, KS = 1)
+template <int C, int R, int SIGN, int RS, int KS, typename T>
+PF_HD void split_park(int t, int n1, const cpx<T> (&u)[16], const cpx<T>* twP, cpx<T>* rows) {
+  constexpr int N2 = K2<C>::NC;
+#pragma unroll
+  for (int r = 0; r < 16 / C; ++r)
+#pragma unroll
+    for (int kc = 0; kc < C; ++kc) {
+      const int k = k2_out_index<C>(t, r, kc);
+      rows[n1 * RS + k * KS] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], ldtab(twP + n1 * N2 + k));
+    }
+}
+template <int C, int R, int SIGN, int RS, int KS, typename T>
+PF_HD void split_combine_cols(int t, const cpx<T>* rows, cpx<T>* dst) {
+  using K = K2<C>;
+  constexpr int N2 = K::NC;
+#pragma unroll 2
+  for (int j = 0; j < 16; ++j) {
+    const int k2 = t + K::T * j;
+    cpx<T> v[R];
+#pragma unroll
+    for (int n1 = 0; n1 < R; ++n1) v[n1] = rows[n1 * RS + k2 * KS];
+    dft_small<R, SIGN>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) dst[k2 + N2 * k1] = v[k1];
+  }
+}
+
 #ifdef __CUDACC__
+// (Measured and dropped: copying the whole transform into shared memory with dense 128-bit loads first and parking the
+//  rows in place over that copy -- HBM/L2 then see no strided reads -- was SLOWER for every size but one: 8192: 0.47 vs
+//  0.57, 3072: 0.49 vs 0.73, 9216: 0.32 vs 0.43 of HBM peak.  L2 absorbs the strided row reads; the extra shared-memory
+//  round trip and barrier do not pay.)
 template <typename T, int C, int R, int SIGN, int MINB>
 __global__ void __launch_bounds__(16 * C, MINB)
 k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T>* tw2, const cpx<T>* twP) {
@@ -380,25 +413,10 @@ k_cta_split(const T* in, T* out, long long batch, const cpx<T>* tw1, const cpx<T
       __syncthreads();
       cpx<T> u[16];
       k2_pass3<C, SIGN, T>(t, tile, u);
-#pragma unroll
-      for (int r = 0; r < 16 / C; ++r)
-#pragma unroll
-        for (int kc = 0; kc < C; ++kc) {
-          const int k = k2_out_index<C>(t, r, kc);
-          rows[n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], ldtab(twP + n1 * N2 + k));
-        }
+      split_park<C, R, SIGN, N2, 1, T>(t, n1, u, twP, rows);
       __syncthreads();                                        // tile free for the next row; row n1 complete
     }
-#pragma unroll 2
-    for (int j = 0; j < 16; ++j) {
-      const int k2 = t + K::T * j;
-      cpx<T> v[R];
-#pragma unroll
-      for (int n1 = 0; n1 < R; ++n1) v[n1] = rows[n1 * N2 + k2];
-      dft_small<R, SIGN>(v);
-#pragma unroll
-      for (int k1 = 0; k1 < R; ++k1) dst[k2 + N2 * k1] = v[k1];
-    }
+    split_combine_cols<C, R, SIGN, N2, 1, T>(t, rows, dst);
     __syncthreads();                                          // rows are rewritten by the next transform
   }
 }

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256) k_glob_store(const XformParams<T> p, cons
 // Nc = R * N2.  The R decimated sub-sequences x[n1 + R*n2] were transformed by the CTA kernel into Y[n1][k2]
 // (rows of N2); this kernel finishes with   X[k2 + N2*k1] = sum_n1 W_R^{n1 k1} * (W_Nc^{n1 k2} Y[n1][k2]).
 // One thread per (transform, k2): R coalesced reads, R coalesced writes.  tw = exp(-2 pi i k / Nc).
-template <typename T, int R, int SIGN>
+// ROWMAJOR: tw[n1*N2 + k2] (unit-stride reads) instead of the natural table read at n1*k2
+template <typename T, int R, int SIGN, bool ROWMAJOR = false>
 __global__ void __launch_bounds__(256) k_split_combine(const cpx<T>* __restrict__ Y, cpx<T>* __restrict__ X, long long batch,
                                                        int N2, const cpx<T>* __restrict__ tw) {
   const long long total = batch * N2;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256) k_split_combine(const cpx<T>* __restrict_
     for (int p = 0; p < R; ++p) {
       const int n1 = ct::bitrev(p, bits);
       const cpx<T> a = y[(long long)n1 * N2];
-      v[p] = (n1 == 0) ? a : cmul_dir<SIGN>(a, tw[(long long)n1 * k2]);
+      v[p] = (n1 == 0) ? a : cmul_dir<SIGN>(a, ROWMAJOR ? tw[(long long)n1 * N2 + k2] : tw[(long long)n1 * k2]);
     }
     reg_fft<R, SIGN>(v);
     cpx<T>* x = X + t * (long long)R * N2 + k2;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(256) k_split_combine(const cpx<T>* __restrict_
 }
 
 // same, for any radix the register DFT library offers (3,5,6,9,10,12,15 ... natural order in and out)
-template <typename T, int R, int SIGN>
+template <typename T, int R, int SIGN, bool ROWMAJOR = false>
 __global__ void __launch_bounds__(256) k_split_combine_any(const cpx<T>* __restrict__ Y, cpx<T>* __restrict__ X, long long batch,
                                                            int N2, const cpx<T>* __restrict__ tw) {
   const long long total = batch * N2;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(256) k_split_combine_any(const cpx<T>* __restr
 #pragma unroll
     for (int n1 = 0; n1 < R; ++n1) {
       const cpx<T> a = y[(long long)n1 * N2];
-      v[n1] = (n1 == 0) ? a : cmul_dir<SIGN>(a, tw[(long long)n1 * k2]);
+      v[n1] = (n1 == 0) ? a : cmul_dir<SIGN>(a, ROWMAJOR ? tw[(long long)n1 * N2 + k2] : tw[(long long)n1 * k2]);
     }
     dft_small<R, SIGN>(v);
     cpx<T>* x = X + t * (long long)R * N2 + k2;

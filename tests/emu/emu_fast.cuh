@@ -286,7 +286,7 @@ static void emu_cluster_run(const float* in, float* out) {
 }
 extern "C" int emu_cluster(int CL, int Q, int scatter, int dir, const float* in, float* out) {
 #define CLX(cl, q, sc) if (CL == cl && Q == q && (scatter != 0) == sc) { if (dir == 0) emu_cluster_run<16, cl, q, sc, -1>(in, out); else emu_cluster_run<16, cl, q, sc, +1>(in, out); return 0; }
-  CLX(2, 1, false) CLX(2, 1, true) CLX(4, 1, false) CLX(4, 1, true) CLX(8, 1, false) CLX(8, 1, true) CLX(8, 2, false) CLX(16, 1, false) CLX(16, 1, true)
+  CLX(2, 1, false) CLX(2, 1, true) CLX(4, 1, false) CLX(4, 1, true) CLX(8, 1, false) CLX(8, 1, true) CLX(8, 2, false) CLX(16, 1, false) CLX(16, 1, true) CLX(4, 2, false) CLX(4, 4, false)
 #undef CLX
   return -1;
 }
@@ -307,21 +307,11 @@ static void emu_cta_split_run(const float* in, float* out) {
   for (int n1 = 0; n1 < R; ++n1) {
     for (int t = 0; t < K::T; ++t) k2_pass1<C, L_C_ORD, SIGN, false, float>(t, reinterpret_cast<const float*>(src + n1), N2, nullptr, -1, true, tw1, tile.data(), R);
     for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, tw2, tile.data());
-    for (int t = 0; t < K::T; ++t) {
-      cf u[16];
-      k2_pass3<C, SIGN, float>(t, tile.data(), u);
-      for (int r = 0; r < 16 / C; ++r) for (int kc = 0; kc < C; ++kc) {
-        const int k = k2_out_index<C>(t, r, kc);
-        rows[(size_t)n1 * N2 + k] = (n1 == 0) ? u[r * C + kc] : cmul_dir<SIGN>(u[r * C + kc], twP[n1 * N2 + k]);
-      }
-    }
+    std::vector<cf> U((size_t)K::T * 16);
+    for (int t = 0; t < K::T; ++t) k2_pass3<C, SIGN, float>(t, tile.data(), *reinterpret_cast<cf(*)[16]>(&U[(size_t)t * 16]));
+    for (int t = 0; t < K::T; ++t) split_park<C, R, SIGN, N2, 1, float>(t, n1, *reinterpret_cast<cf(*)[16]>(&U[(size_t)t * 16]), twP, rows.data());
   }
-  for (int k2 = 0; k2 < N2; ++k2) {
-    cf v[R];
-    for (int n1 = 0; n1 < R; ++n1) v[n1] = rows[(size_t)n1 * N2 + k2];
-    dft_small<R, SIGN>(v);
-    for (int k1 = 0; k1 < R; ++k1) dst[k2 + N2 * k1] = v[k1];
-  }
+  for (int t = 0; t < K::T; ++t) split_combine_cols<C, R, SIGN, N2, 1, float>(t, rows.data(), dst);
 }
 extern "C" int emu_cta_split(int C, int R, int dir, const float* in, float* out) {
 #define CSX(c, r) if (C == c && R == r) { if (dir == 0) emu_cta_split_run<c, r, -1>(in, out); else emu_cta_split_run<c, r, +1>(in, out); return 0; }

@@ -18,12 +18,14 @@ VARIANTS = [
     (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster8_8x4096_dsmem_rows"),
     (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster8_8x4096"),
     (65536, {"PFFFT_B200_CLUSTER": "all"}, "cluster8_16x4096"),
+    (32768, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SHAPE": "4x2"}, "cluster4_8x4096"),
+    (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_SHAPE": "4x4"}, "cluster4_16x4096"),
     (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster16_16x4096_dsmem_rows"),
     (65536, {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_CLUSTER_R16": "16", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster16_16x4096"),
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster2_2x4096_dsmem_rows"),
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster2_2x4096"),
 ]
-ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192")
+ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192", "PFFFT_B200_CLUSTER_SHAPE")
 
 
 class env_set:
