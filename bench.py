@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="transforms per GPU per pass (default 2^20)")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 16, help="transforms per e2e step (host buffers)")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 17, help="transforms per e2e step (host buffers)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
