@@ -170,3 +170,34 @@ def test_mixed_radix_warp_kernel_phases(emu, ref, R):
                 got = o[: batch * 2 * N].reshape(batch, 2 * N)
                 assert max(R.relmax(got[i], w[i]) for i in range(batch)) <= 2e-6, (N, batch, d)
                 assert np.all(np.isnan(o[batch * 2 * N:])), "wrote beyond the batch"
+
+
+def test_cluster_kernel_phases(emu, ref, R):
+    """cluster plans (cluster_kernels.cuh): the CTAs of one cluster stepped phase by phase on the CPU, cluster barriers =
+    phase boundaries, DSMEM = the peers' buffers.  Every shape / row mode that is instantiated, against the reference."""
+    emu.emu_cluster.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2
+    rng = np.random.default_rng(11)
+    for CL, Q, scatter in [(2, 1, 0), (4, 1, 0), (4, 1, 1), (8, 1, 1), (8, 2, 0), (4, 4, 0), (16, 1, 0), (16, 1, 1)]:
+        N = CL * Q * 4096
+        x = (rng.random(2 * N) * 2 - 1).astype(np.float32)
+        want = ref.transform(N, 1, x, 0, True)
+        for d in ((0, 1) if CL == 4 else (0,)):
+            o = np.zeros(2 * N, np.float32)
+            src = x if d == 0 else want
+            assert emu.emu_cluster(CL, Q, scatter, d, src.ctypes.data, o.ctypes.data) == 0
+            if d == 0:
+                assert R.relmax(o, want) <= 2e-6, (CL, Q, scatter)
+            else:
+                assert R.relmax(o / N, x) <= 2e-6, (CL, Q, scatter)
+
+
+def test_single_cta_two_level_kernel_phases(emu, ref, R):
+    """k_cta_split with the row-major combine twiddles: (C, R) = rows of 256*C points x radix-R finish"""
+    emu.emu_cta_split.argtypes = [C.c_int] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(12)
+    for c, r in [(16, 2), (8, 3), (4, 9), (2, 15), (8, 6)]:
+        N = r * 256 * c
+        x = (rng.random(2 * N) * 2 - 1).astype(np.float32)
+        o = np.zeros(2 * N, np.float32)
+        assert emu.emu_cta_split(c, r, 0, x.ctypes.data, o.ctypes.data) == 0
+        assert R.relmax(o, ref.transform(N, 1, x, 0, True)) <= 2e-6, (c, r)
