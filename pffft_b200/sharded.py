@@ -15,7 +15,8 @@ tests/test_pffastconv.c:685).  No other inter-GPU traffic exists; the filter spe
 taps (deterministic, so bit-identical everywhere).
 
 This module is host-side orchestration only (torch.distributed for the halo message, the C-ABI for the compute).  The
-`conv` callable is injectable so the world_size-2 gloo test can run the algebra on CPU with the oracle as the worker.
+`conv(taps, x, y, length, block_len, flush) -> produced` callable is injectable so the world_size-2 gloo test can run the
+algebra on CPU with the oracle as the worker.
 """
 import numpy as np
 
@@ -31,6 +32,7 @@ class ShardedStreamConv:
     rank r:  buf = alloc()                      # len_r + halo floats; fill buf[:len_r] with its samples
              exchange_halo(buf)                 # one send (to r-1) / one recv (from r+1)
              n = apply(buf, out)                # out[:n] = outputs [lo_r, lo_r + n)
+         or  n = exchange_and_apply(buf, out)   # same samples, message overlapped with the blocks that do not need it
     """
 
     def __init__(self, taps, total_len, rank, world, block_len=0, group=None, conv=None):
@@ -59,35 +61,58 @@ class ShardedStreamConv:
         return buf[: self.hi - self.lo]
 
     # ---- the one exchange step of the path ------------------------------------------------------------------------
-    def exchange_halo(self, buf):
-        """rank r+1 -> rank r: first F-1 samples.  NCCL send/recv (NVLink) on CUDA tensors, gloo on CPU tensors."""
+    def exchange_halo_begin(self, buf):
+        """rank r+1 -> rank r: first F-1 samples.  NCCL send/recv (NVLink) on CUDA tensors, gloo on CPU tensors.
+        Returns the pending requests; `exchange_halo_end` makes the current stream (or the host, on CPU) wait for them."""
         if self.world == 1 or self.halo == 0:
-            return
+            return []
         import torch.distributed as dist
         ops = []
         if self.rank > 0:
             ops.append(dist.P2POp(dist.isend, buf[: self.halo].contiguous(), self.rank - 1, self.group))
         if self.rank + 1 < self.world:
             ops.append(dist.P2POp(dist.irecv, buf[self.hi - self.lo:], self.rank + 1, self.group))
-        for w in dist.batch_isend_irecv(ops):
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def exchange_halo_end(reqs):
+        for w in reqs:
             w.wait()
 
+    def exchange_halo(self, buf):
+        self.exchange_halo_end(self.exchange_halo_begin(buf))
+
     # ---- compute: the ordinary single-GPU call ---------------------------------------------------------------------
+    def _call(self, x, y, length, flush):
+        if self._conv is not None:
+            return self._conv(self.taps, x, y, length, self.block_len, flush)
+        import pffft_b200 as pf
+        if self._fc is None:
+            self._fc = pf.FastConv(self.taps, self.block_len, 0)
+            if not self._fc.handle:
+                raise RuntimeError("pffastconv_new_setup failed: " + pf.last_error())
+        return self._fc.apply(x, y, length, flush)
+
     def apply(self, buf, out):
-        """out[:n] <- outputs [lo, lo+n) of the global convolution; returns n (== self.out_len)"""
+        """out[:n] <- outputs [lo, lo+n) of the global convolution; returns n (== self.out_len).  Call after exchange_halo."""
         if self.feed_len < self.F:
             return 0
-        if self._conv is not None:
-            n = self._conv(self.taps, buf, out, self.feed_len, self.block_len)
-        else:
-            import pffft_b200 as pf
-            if self._fc is None:
-                self._fc = pf.FastConv(self.taps, self.block_len, 0)
-                if not self._fc.handle:
-                    raise RuntimeError("pffastconv_new_setup failed: " + pf.last_error())
-            n = self._fc.apply(buf, out, self.feed_len, 1)
+        n = self._call(buf, out, self.feed_len, 1)
         assert n == self.out_len, (n, self.out_len)
         return n
+
+    def exchange_and_apply(self, buf, out):
+        """the same result with the halo message HIDDEN behind the blocks that do not need it: every whole block inside
+        this rank's own samples is convolved (applyFlush = 0) while the message is in flight; the remaining tail -- the
+        only part that reads the halo -- follows with applyFlush = 1 at the block boundary the first call stopped at,
+        i.e. with the same block phase, so the samples are those of `exchange_halo` + `apply` bit for bit."""
+        own = self.hi - self.lo
+        reqs = self.exchange_halo_begin(buf)
+        n0 = self._call(buf, out, own, 0) if own >= self.F else 0
+        self.exchange_halo_end(reqs)
+        n1 = self._call(buf[n0:], out[n0:], self.feed_len - n0, 1) if self.feed_len - n0 >= self.F else 0
+        assert n0 + n1 == self.out_len, (n0, n1, self.out_len)
+        return n0 + n1
 
     def close(self):
         if self._fc is not None:

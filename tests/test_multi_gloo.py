@@ -84,8 +84,8 @@ def _conv_worker(rank, world, port, q, total_len, ntaps):
         from pffft_b200.sharded import ShardedStreamConv
         checker = R.ref() if R.have_ref() else R.oracle()
 
-        def cpu_conv(taps, buf, out, feed_len, block_len):     # the CPU checker stands in for the GPU call (no GPU here)
-            y, n, _ = checker.fastconv(taps, buf.numpy()[:feed_len], block_len, 0, 1)
+        def cpu_conv(taps, buf, out, feed_len, block_len, flush):   # the CPU checker stands in for the GPU call (no GPU here)
+            y, n, _ = checker.fastconv(taps, buf.numpy()[:feed_len], block_len, 0, flush)
             out[:n] = torch.from_numpy(y)
             return n
 
@@ -98,7 +98,13 @@ def _conv_worker(rank, world, port, q, total_len, ntaps):
         halo_ok = bool(np.array_equal(buf.numpy(), x[sc.lo:sc.lo + sc.feed_len]))
         out = torch.full((sc.feed_len + 8,), float("nan"))
         n = sc.apply(buf, out)
-        q.put((rank, sc.lo, n, halo_ok, out[:n].numpy().copy(), bool(torch.isnan(out[n:]).all())))
+        # the overlapped form (whole own blocks while the message is in flight, tail after it) gives the same samples
+        buf2 = sc.alloc(device="cpu")
+        sc.local(buf2)[:] = torch.from_numpy(x[sc.lo:sc.hi])
+        out2 = torch.full((sc.feed_len + 8,), float("nan"))
+        n2 = sc.exchange_and_apply(buf2, out2)
+        same = n2 == n and bool(torch.equal(out2[:n], out[:n])) and bool(torch.isnan(out2[n:]).all())
+        q.put((rank, sc.lo, n, halo_ok and same, out[:n].numpy().copy(), bool(torch.isnan(out[n:]).all())))
     finally:
         dist.destroy_process_group()
 
