@@ -149,7 +149,7 @@ template <> struct FastHooks<float> {
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
     { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
-      if (!cta_C_for(Nc) && float_split_for(N, transform, &R, &N2)) return cta_C_for(N2) ? split_table_cpx(Nc, N2) : (size_t)N2; }
+      if (!cta_C_for(Nc) && float_split_for(N, transform, &R, &N2)) return cta_C_for(N2) ? split_table_cpx(Nc, N2) + t2d_table_cpx(Nc) : (size_t)N2; }
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
@@ -174,7 +174,11 @@ template <> struct FastHooks<float> {
     }
     { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
       if (!cta_C_for(Nc) && float_split_for(N, transform, &R, &N2)) {
-        if (cta_C_for(N2)) { split_fill_tables<float>(Nc, N2, dst); return; }
+        if (cta_C_for(N2)) {
+          split_fill_tables<float>(Nc, N2, dst);
+          if (t2d_table_cpx(Nc)) t2d_fill_tables_float(Nc, dst + 2 * split_table_cpx(Nc, N2));
+          return;
+        }
         const int R2 = wmixed_complex_R2(N2);                 // warp rows: tw[k2*32 + l] = exp(-2 pi i l k2 / N2)
         for (int k2 = 0; k2 < R2; ++k2)
           for (int l = 0; l < 32; ++l) {
@@ -214,8 +218,11 @@ template <> struct FastHooks<float> {
         s->split_R = R; s->split_N2 = N2;
         s->split_fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_fused_ok<float>(R, N2);
         s->fast_variant = 300;
-        int CL = 0, Q = 1, mode = 0;
-        if (cluster_choose(R, N2, &CL, &Q, &mode)) {
+        int CL = 0, Q = 1, mode = 0, a1 = 0, a2 = 0;
+        if (t2d_enabled() && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {
+          s->split_t2d = true; s->split_fused = false;
+          snprintf(s->name_buf, sizeof(s->name_buf), "tiled2d_%dx%d", 16 * a1, 16 * a2);
+        } else if (cluster_choose(R, N2, &CL, &Q, &mode)) {
           s->split_cluster = CL; s->split_Q = Q; s->split_mode = mode; s->split_fused = false;
           snprintf(s->name_buf, sizeof(s->name_buf), "cluster%d_%dx%d%s", CL, R, N2, mode == 1 ? "_dsmem_rows" : "");
         } else

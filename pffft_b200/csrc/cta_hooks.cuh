@@ -156,6 +156,15 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 //  built and measured: 0.25 / 0.22 / 0.17 of HBM peak at 16384 / 32768 / 65536 against 0.38 / 0.34 / 0.24 for this
 //  order.  Partial-sector stores cost more than the strided loads they replace; stores stay dense.)
 
+// ---- tiled two-dimensional plan (tiled2d_kernels.cuh, instantiated in tiled2d.cu): float complex cores 16384 / 32768 / 65536
+// as N1 x N2 with 128-byte runs in both passes.  Opt-in (PFFFT_B200_TILED2D=1): verified by CPU stepping, not yet on hardware.
+bool t2d_shape_for(int Nc, int* A1, int* A2);
+size_t t2d_table_cpx(int Nc);                                   // [twA: N2][twC: N1][tw2d: Nc], 0 when the size has no tiled plan
+void t2d_fill_tables_float(int Nc, float* dst);
+int t2d_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* S, cpx<float>* X, long long batch,
+                     const cpx<float>* tables, int sm_count, cudaStream_t st);
+inline bool t2d_enabled() { const char* e = getenv("PFFFT_B200_TILED2D"); return e && atoi(e) != 0; }
+
 // ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked
 // in the distributed shared memory of a CL-CTA cluster -> one HBM round trip for 16384 .. 65536 points
 // mode 0: strided rows staged by cp.async; 1: rows distributed through DSMEM
@@ -287,7 +296,13 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   }
   // (the fused kernel reads a whole transform before it writes it, so src == dst is fine)
   cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
-  if (s->split_cluster > 0) {
+  if (s->split_t2d) {
+    int rc = (int)cudaErrorInvalidValue;
+    if constexpr (sizeof(T) == 4)
+      rc = t2d_launch_float(s->Nc, SIGN, src, s->d_scratch[1], dst, p.batch,
+                            s->tw_fast + split_table_cpx(s->Nc, s->split_N2), s->sm_count, st);
+    if (rc) return rc;
+  } else if (s->split_cluster > 0) {
     int rc = (int)cudaErrorInvalidValue;
     if constexpr (sizeof(T) == 4)
       rc = cluster_launch_float(s->split_cluster, s->split_Q, s->split_mode, SIGN, src, dst, p.batch, s->tw_fast,

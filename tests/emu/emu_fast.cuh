@@ -319,3 +319,53 @@ extern "C" int emu_cta_split(int C, int R, int dir, const float* in, float* out)
 #undef CSX
   return -1;
 }
+
+// ---- tiled two-dimensional large-N plan (tiled2d_kernels.cuh): pass A tiles then pass C tiles, thread by thread
+#include "../../pffft_b200/csrc/tiled2d_kernels.cuh"
+template <int A1, int A2, int SIGN>
+static void emu_t2d_run(const float* in, float* out) {
+  using namespace pf;
+  using G = T2D<A1, A2>;
+  std::vector<float> tab(2 * ((size_t)G::N1 + G::N2 + G::NC));
+  t2d_fill_tables<float, A1, A2>(tab.data());
+  const cf* twA = reinterpret_cast<const cf*>(tab.data());
+  const cf* twC = twA + G::N2;
+  const cf* tw2d = twC + G::N1;
+  std::vector<cf> S(G::NC), tileA(16 * G::N2), tileC(16 * G::N1);
+  const cf* x = reinterpret_cast<const cf*>(in);
+  cf* X = reinterpret_cast<cf*>(out);
+  for (int c = 0; c < G::N1 / 16; ++c) {
+    for (int t = 0; t < G::TA; ++t) t2d_A1<A1, A2, SIGN, float>(t, x + 16 * c, twA, tileA.data());
+    for (int t = 0; t < G::TA; ++t) t2d_A2<A1, A2, SIGN, float>(t, c, tileA.data(), tw2d, S.data());
+  }
+  for (int d = 0; d < G::N2 / 16; ++d) {
+    for (int t = 0; t < G::TC; ++t) t2d_C1<A1, A2, SIGN, float>(t, S.data() + (size_t)16 * d * G::N1, twC, tileC.data());
+    for (int t = 0; t < G::TC; ++t) t2d_C2<A1, A2, SIGN, float>(t, tileC.data(), X + 16 * d);
+  }
+}
+extern "C" int emu_t2d(int A1, int A2, int dir, const float* in, float* out) {
+#define T2X(a1, a2) if (A1 == a1 && A2 == a2) { if (dir == 0) emu_t2d_run<a1, a2, -1>(in, out); else emu_t2d_run<a1, a2, +1>(in, out); return 0; }
+  T2X(8, 8) T2X(16, 8) T2X(8, 16) T2X(16, 16)
+#undef T2X
+  return -1;
+}
+// worst number of lanes of a half-warp that hit the same 8-byte bank pair in the exchange tiles (1 = conflict free)
+template <int A1, int A2> static int emu_t2d_conflicts_c() {
+  using namespace pf;
+  int worst = 1;
+  auto audit = [&](auto addr, int nthreads) {
+    for (int h = 0; h < nthreads; h += 16) { int cnt[16] = {0}; for (int l = 0; l < 16; ++l) cnt[addr(h + l) & 15]++; for (int b = 0; b < 16; ++b) if (cnt[b] > worst) worst = cnt[b]; }
+  };
+  for (int ka = 0; ka < 16; ++ka) audit([&](int t) { return (ka * A2 + (t >> 4)) * 16 + (t & 15); }, 16 * A2);                       // A1 writes
+  for (int q = 0; q < A2; ++q) audit([&](int t) { return (((t >> 4)) * A2 + q) * 16 + (t & 15); }, 16 * A2);                          // A2 reads
+  for (int ka = 0; ka < 16; ++ka) audit([&](int t) { return (ka * A1 + t % A1) * 16 + ((t / A1) ^ t2d_swz<A1>(t % A1)); }, 16 * A1); // C1 writes
+  for (int qq = 0; qq < A1; ++qq) audit([&](int t) { return (((t >> 4)) * A1 + qq) * 16 + ((t & 15) ^ t2d_swz<A1>(qq)); }, 16 * A1);  // C2 reads
+  return worst;
+}
+extern "C" int emu_t2d_conflicts(int A1, int A2) {
+  if (A1 == 8 && A2 == 8) return emu_t2d_conflicts_c<8, 8>();
+  if (A1 == 16 && A2 == 8) return emu_t2d_conflicts_c<16, 8>();
+  if (A1 == 8 && A2 == 16) return emu_t2d_conflicts_c<8, 16>();
+  if (A1 == 16 && A2 == 16) return emu_t2d_conflicts_c<16, 16>();
+  return -1;
+}

@@ -201,3 +201,20 @@ def test_single_cta_two_level_kernel_phases(emu, ref, R):
         o = np.zeros(2 * N, np.float32)
         assert emu.emu_cta_split(c, r, 0, x.ctypes.data, o.ctypes.data) == 0
         assert R.relmax(o, ref.transform(N, 1, x, 0, True)) <= 2e-6, (c, r)
+
+
+def test_tiled_2d_large_n_phases(emu, ref, R):
+    """tiled two-dimensional plan (tiled2d_kernels.cuh, opt-in): pass A tiles then pass C tiles stepped thread by thread;
+    both exchange tiles must be bank-conflict free for every shape"""
+    emu.emu_t2d.argtypes = [C.c_int] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(13)
+    for a1, a2 in [(8, 8), (16, 8), (8, 16), (16, 16)]:
+        assert emu.emu_t2d_conflicts(a1, a2) == 1
+        N = 256 * a1 * a2
+        x = (rng.random(2 * N) * 2 - 1).astype(np.float32)
+        want = ref.transform(N, 1, x, 0, True)
+        o = np.zeros(2 * N, np.float32)
+        assert emu.emu_t2d(a1, a2, 0, x.ctypes.data, o.ctypes.data) == 0
+        assert R.relmax(o, want) <= 2e-6, (a1, a2)
+        assert emu.emu_t2d(a1, a2, 1, want.ctypes.data, o.ctypes.data) == 0
+        assert R.relmax(o / N, x) <= 2e-6, (a1, a2)

@@ -1,0 +1,55 @@
+"""GPU tests of the tiled two-dimensional large-N plan (pffft_b200/csrc/tiled2d_kernels.cuh).
+
+The plan was written at the end of round 1 after the GPU budget was spent: its index algebra is verified by CPU stepping
+(tests/test_host_logic.py::test_tiled_2d_large_n_phases) but it has NOT run on hardware yet, so it is opt-in in the
+library (PFFFT_B200_TILED2D=1) and these tests only run with PFFFT_B200_TEST_TILED2D=1 (first thing to do next round)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import uniform
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_TILED2D") != "1",
+                                 reason="opt-in: tiled2d kernels not yet run on hardware (set PFFFT_B200_TEST_TILED2D=1)")]
+
+
+@pytest.mark.parametrize("tr", [1, 0])
+@pytest.mark.parametrize("Nc", [16384, 32768, 65536])
+def test_tiled2d_vs_reference(pf, ref, R, Nc, tr):
+    import torch
+    N = Nc if tr == 1 else 2 * Nc
+    old = os.environ.get("PFFFT_B200_TILED2D")
+    os.environ["PFFFT_B200_TILED2D"] = "1"
+    try:
+        s = pf.Setup(N, tr)
+    finally:
+        if old is None:
+            os.environ.pop("PFFFT_B200_TILED2D", None)
+        else:
+            os.environ["PFFFT_B200_TILED2D"] = old
+    try:
+        assert s.kernel.startswith("tiled2d_"), s.kernel
+        per = N if tr == 0 else 2 * N
+        batch = 5
+        x = uniform(np.random.default_rng(Nc + tr), batch * per).reshape(batch, per)
+        xd = torch.from_numpy(x).cuda()
+        y = s.transform_batch(xd, pf.PFFFT_FORWARD, True)
+        z = s.transform_batch(y, pf.PFFFT_BACKWARD, True)
+        torch.cuda.synchronize()
+        want = ref.transform_batch(N, tr, x[:2], 0, True)
+        for b in range(2):
+            assert R.relmax(y[b].cpu().numpy(), want[b]) <= 1e-5
+        assert float(((z / N - xd) ** 2).sum(dim=1).max()) <= N * 1e-7
+        xi = xd.clone()
+        s.transform_batch(xi, pf.PFFFT_FORWARD, True, out=xi)
+        torch.cuda.synchronize()
+        assert torch.equal(xi, y)                                   # in place == out of place
+        big = max(8, (64 << 20) // (8 * Nc))                         # more tiles than resident CTAs: the grid-stride loop
+        xb = xd[:1].repeat(big, 1).contiguous()
+        yb = s.transform_batch(xb, pf.PFFFT_FORWARD, True)
+        torch.cuda.synchronize()
+        assert torch.equal(yb[-1], y[0]) and torch.equal(yb[big // 2], y[0])
+    finally:
+        s.close()
