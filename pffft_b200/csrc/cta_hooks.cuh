@@ -157,13 +157,19 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 //  order.  Partial-sector stores cost more than the strided loads they replace; stores stay dense.)
 
 // ---- tiled two-dimensional plan (tiled2d_kernels.cuh, instantiated in tiled2d.cu): float complex cores 16384 / 32768 / 65536
-// as N1 x N2 with 128-byte runs in both passes.  Opt-in (PFFFT_B200_TILED2D=1): verified by CPU stepping, not yet on hardware.
+// as N1 x N2 with 128-byte runs in both passes.  Measured (profiles/r01b_large_n.md): 32768: 0.42, 65536: 0.41-0.44 of HBM
+// peak against 0.34 / 0.26 for the split plan -> the default there; 16384: 0.39 against 0.41 for the 4-CTA cluster kernel
+// -> only with PFFFT_B200_TILED2D=1.  PFFFT_B200_TILED2D=0 switches the plan off.
 bool t2d_shape_for(int Nc, int* A1, int* A2);
 size_t t2d_table_cpx(int Nc);                                   // [twA: N2][twC: N1][tw2d: Nc], 0 when the size has no tiled plan
 void t2d_fill_tables_float(int Nc, float* dst);
 int t2d_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* S, cpx<float>* X, long long batch,
                      const cpx<float>* tables, int sm_count, cudaStream_t st);
-inline bool t2d_enabled() { const char* e = getenv("PFFFT_B200_TILED2D"); return e && atoi(e) != 0; }
+inline bool t2d_enabled(int Nc) {
+  const char* e = getenv("PFFFT_B200_TILED2D");
+  if (e) return atoi(e) != 0;
+  return Nc == 32768 || Nc == 65536;
+}
 
 // ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked
 // in the distributed shared memory of a CL-CTA cluster -> one HBM round trip for 16384 .. 65536 points

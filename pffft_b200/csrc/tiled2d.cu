@@ -1,5 +1,5 @@
 // tiled2d.cu -- instantiations and launchers of the tiled two-dimensional large-N plan (tiled2d_kernels.cuh), float.
-// Own translation unit so the C-ABI units stay small.  Opt-in (PFFFT_B200_TILED2D=1): see the STATUS note in the header.
+// Own translation unit so the C-ABI units stay small.  Default plan for 32768 and 65536 (PFFFT_B200_TILED2D=0|1 overrides).
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include "internal_api.h"

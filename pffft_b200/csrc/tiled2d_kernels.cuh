@@ -14,8 +14,9 @@
 // R: one 32-byte sector per 8 useful bytes, LSU bound at R = 16 -- profiles/r01b_large_n.md).  Two HBM round trips
 // (ceiling 0.5 of the roofline); the same two phase pairs are what a cluster version exchanges through DSMEM instead of S.
 //
-// STATUS (end of round 1): index algebra and arithmetic verified by CPU stepping (tests/test_host_logic.py via tests/emu);
-// NOT YET RUN ON HARDWARE -- the plan is opt-in (PFFFT_B200_TILED2D=1) and no default path reaches these kernels.
+// Measured on B200 (first hardware run, untuned; profiles/r01b_large_n.md): 16384: 0.39, 32768: 0.42, 65536: 0.41 forward /
+// 0.44 backward of the HBM peak (split plan: 0.38 / 0.34 / 0.26).  Index algebra also verified by CPU stepping
+// (tests/test_host_logic.py via tests/emu).  80 registers (a 64-register build spills 16-24 of them): tuning left for round 2.
 //
 // Replaces, for these sizes, the cfftf1_ps sweeps + finalize + zreorder of the reference (src/pffft_priv_impl.h:1004-1048,
 // :122-251, :1195-1237, :1158-1193).

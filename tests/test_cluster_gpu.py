@@ -25,7 +25,8 @@ VARIANTS = [
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "1"}, "cluster2_2x4096_dsmem_rows"),
     (8192, {"PFFFT_B200_CLUSTER_8192": "1", "PFFFT_B200_CLUSTER_MODE": "0"}, "cluster2_2x4096"),
 ]
-ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192", "PFFFT_B200_CLUSTER_SHAPE")
+ENV_KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192", "PFFFT_B200_CLUSTER_SHAPE",
+            "PFFFT_B200_TILED2D")
 
 
 class env_set:
@@ -36,6 +37,7 @@ class env_set:
         self.old = {k: os.environ.get(k) for k in ENV_KEYS}
         for k in ENV_KEYS:
             os.environ.pop(k, None)
+        os.environ["PFFFT_B200_TILED2D"] = "0"          # these tests address the cluster / split plans of the same sizes
         os.environ.update(self.kv)
 
     def __exit__(self, *a):

@@ -365,7 +365,9 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(144, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
-        assert s.kernel == "split_16x4096"
+        assert s.kernel == "tiled2d_256x256"
+    with pf.Setup(36864, 1) as s:
+        assert s.kernel == "split_9x4096"
     with pf.Setup(16384, 1) as s:
         assert s.kernel in ("cluster4_4x4096", "split_4x4096")      # 4-CTA clusters where the device schedules them
     with pf.Setup(1 << 20, 1) as s:

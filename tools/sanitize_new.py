@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pffft_b200 as pf
 rng = np.random.default_rng(0)
-KEYS = ("PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_SHAPE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192")
+KEYS = ("PFFFT_B200_TILED2D", "PFFFT_B200_CLUSTER", "PFFFT_B200_CLUSTER_MODE", "PFFFT_B200_CLUSTER_SHAPE", "PFFFT_B200_CLUSTER_R16", "PFFFT_B200_CLUSTER_8192")
 def run(N, tr, env, batch=3):
     for k in KEYS: os.environ.pop(k, None)
     os.environ.update(env)
@@ -19,11 +19,11 @@ def run(N, tr, env, batch=3):
         torch.cuda.synchronize()
         print("%-6d %-5s %-30s roundtrip %.1e reorder %s" % (N, "real" if tr == 0 else "cplx", s.kernel, float((b / N - x).abs().max()),
                                                               bool(torch.equal(z, z2))), flush=True)
-A = {"PFFFT_B200_CLUSTER": "all"}
+A = {"PFFFT_B200_CLUSTER": "all", "PFFFT_B200_TILED2D": "0"}
 run(16384, 1, {}); run(16384, 1, {"PFFFT_B200_CLUSTER_MODE": "1"}); run(32768, 0, {})
 run(32768, 1, A); run(32768, 1, dict(A, PFFFT_B200_CLUSTER_MODE="1")); run(32768, 1, dict(A, PFFFT_B200_CLUSTER_SHAPE="4x2"))
 run(65536, 1, A); run(65536, 1, dict(A, PFFFT_B200_CLUSTER_R16="16")); run(65536, 1, dict(A, PFFFT_B200_CLUSTER_R16="16", PFFFT_B200_CLUSTER_MODE="1"))
-run(8192, 1, {"PFFFT_B200_CLUSTER_8192": "1"}); run(65536, 1, {"PFFFT_B200_CLUSTER": "0"}); run(9216, 1, {}); run(36864, 1, {})
+run(8192, 1, {"PFFFT_B200_CLUSTER_8192": "1"}); run(65536, 1, {"PFFFT_B200_CLUSTER": "0", "PFFFT_B200_TILED2D": "0"}); run(65536, 1, {}); run(32768, 1, {}); run(16384, 1, {"PFFFT_B200_TILED2D": "1"}); run(9216, 1, {}); run(36864, 1, {})
 run(1024, 1, {}); run(4096, 0, {}); run(96, 0, {})
 os.environ["PFFFT_B200_CONV_PIECE_KB"] = "16"
 n, taps = 50000, 301
