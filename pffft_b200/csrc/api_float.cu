@@ -221,7 +221,8 @@ template <> struct FastHooks<float> {
         int CL = 0, Q = 1, mode = 0, a1 = 0, a2 = 0;
         if (t2d_enabled(s->Nc) && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {
           s->split_t2d = true; s->split_fused = false;
-          snprintf(s->name_buf, sizeof(s->name_buf), "tiled2d_%dx%d", 16 * a1, 16 * a2);
+          s->split_t2d_cluster = t2d_cluster_requested() && t2d_cluster_max_active_float(s->Nc) > 0;
+          snprintf(s->name_buf, sizeof(s->name_buf), s->split_t2d_cluster ? "tiled2d_cluster8_%dx%d" : "tiled2d_%dx%d", 16 * a1, 16 * a2);
         } else if (cluster_choose(R, N2, &CL, &Q, &mode)) {
           s->split_cluster = CL; s->split_Q = Q; s->split_mode = mode; s->split_fused = false;
           snprintf(s->name_buf, sizeof(s->name_buf), "cluster%d_%dx%d%s", CL, R, N2, mode == 1 ? "_dsmem_rows" : "");

@@ -66,7 +66,8 @@ template <typename T> struct Setup {
   int split_R = 0, split_N2 = 0;          // Nc = split_R x split_N2 two-level plans (rows on a tuned kernel + radix-R combine)
   bool split_fused = false;               // ... small enough for ONE kernel (rows parked in shared memory): one HBM round trip
   int split_cluster = 0, split_Q = 1;     // ... or ONE kernel on clusters of split_cluster CTAs (rows parked in DSMEM), split_Q rows per CTA
-  bool split_t2d = false;                 // ... or the tiled two-dimensional plan (two dense passes, opt-in)
+  bool split_t2d = false;                 // ... or the tiled two-dimensional plan (two dense passes)
+  bool split_t2d_cluster = false;         //     its cluster-fused form (pass A -> pass C through DSMEM; opt-in)
   int split_mode = 0;                     //     0 strided row reads, 1 rows distributed through DSMEM
   char name_buf[40] = {0};
   int tpc = 1;                            // transforms resident per CTA (shared-memory kernel), a power of two

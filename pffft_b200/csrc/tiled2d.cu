@@ -39,6 +39,57 @@ template <int A1, int A2, int SIGN> struct T2DLaunch {
   }
 };
 
+// cluster-fused form (one HBM round trip); NOT YET RUN ON HARDWARE, reached only with PFFFT_B200_TILED2D=2
+template <int A1, int A2, int CL, int SIGN> struct T2DClusterLaunch {
+  using G = T2D<A1, A2>;
+  using K = T2DC<A1, A2, CL>;
+  static constexpr size_t kSmem = K::kSmem * sizeof(cf);
+  static constexpr int kBySmem = (int)((227 * 1024) / (kSmem + 1024));
+  static constexpr int kByRegs = 768 / K::NT;                       // 80 registers per thread
+  static constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kByRegs ? kBySmem : kByRegs);
+  static auto kernel() { return k_t2d_cluster<float, A1, A2, CL, SIGN, MINB>; }
+  static int prepare(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, cudaStream_t st) {
+    static thread_local bool configured = false;
+    if (!configured) {
+      if (kSmem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      if (CL > 8) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      configured = true;
+    }
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)(nclusters * CL), 1, 1);
+    cfg->blockDim = dim3(K::NT, 1, 1);
+    cfg->dynamicSmemBytes = kSmem;
+    cfg->stream = st;
+    cfg->attrs = attr; cfg->numAttrs = 1;
+    return 0;
+  }
+  static int max_active() {
+    static thread_local int cached = -1;
+    if (cached >= 0) return cached;
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    if (prepare(&cfg, attr, 1, nullptr)) { cached = 0; return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel(), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cached = n;
+    return n;
+  }
+  static int run(const cf* x, cf* X, long long batch, const cf* tables, cudaStream_t st) {
+    const int cap = max_active();
+    if (cap <= 0) { set_error_msg("tiled2d cluster kernel: cluster shape not schedulable on this device"); return (int)cudaErrorInvalidConfiguration; }
+    const int ncl = (int)(batch < (long long)cap ? batch : (long long)cap);
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    { const int rc = prepare(&cfg, attr, ncl, st); if (rc) return rc; }
+    const cf* twA = tables;
+    const cf* twC = twA + G::N2;
+    const cf* tw2d = twC + G::N1;
+    PF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel(), x, X, batch, twA, twC, tw2d));
+    count_launch();
+    return 0;
+  }
+};
+
 }  // namespace
 
 // (A1, A2) for a complex core, 0 when the size has no tiled plan
@@ -70,4 +121,24 @@ int t2d_launch_float(int Nc, int sign, const cf* x, cf* S, cf* X, long long batc
   return (int)cudaErrorInvalidValue;
 }
 
+}  // namespace pf
+
+namespace pf {
+// cluster-fused form: 8-CTA clusters for every size
+int t2d_cluster_max_active_float(int Nc) {
+  switch (Nc) {
+    case 16384: return T2DClusterLaunch<8, 8, 8, -1>::max_active();
+    case 32768: return T2DClusterLaunch<16, 8, 8, -1>::max_active();
+    case 65536: return T2DClusterLaunch<16, 16, 8, -1>::max_active();
+  }
+  return 0;
+}
+int t2d_cluster_launch_float(int Nc, int sign, const cf* x, cf* X, long long batch, const cf* tables, cudaStream_t st) {
+#define PF_T2C(nc, a1, a2) if (Nc == nc) return sign < 0 ? T2DClusterLaunch<a1, a2, 8, -1>::run(x, X, batch, tables, st) \
+                                                         : T2DClusterLaunch<a1, a2, 8, +1>::run(x, X, batch, tables, st);
+  PF_T2C(16384, 8, 8) PF_T2C(32768, 16, 8) PF_T2C(65536, 16, 16)
+#undef PF_T2C
+  set_error_msg("tiled2d cluster: size not instantiated");
+  return (int)cudaErrorInvalidValue;
+}
 }  // namespace pf

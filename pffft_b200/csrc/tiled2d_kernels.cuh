@@ -24,6 +24,7 @@
 #include "butterfly.cuh"
 #include "cta_kernels.cuh"   // brev4, ldtab
 #include "plan.h"          // unit_root (host table fill)
+#include "cluster_kernels.cuh"   // cluster_arrive / cluster_wait / ClusterRemote (cluster-fused form)
 
 namespace pf {
 
@@ -61,8 +62,13 @@ PF_HD void t2d_A1(int t, const cpx<T>* cols /* x + 16c */, const cpx<T>* twA, cp
 }
 // ---- pass A, second half: thread t = j + 16*g finishes k_a = g + A2*r (r < 16/A2): radix A2 over q -> k_b,
 //      k2 = k_a + 16*k_b, * W_Nc^{n1 k2}, to the transposed scratch S[k2*N1 + 16c + j]
-template <int A1, int A2, int SIGN, typename T>
-PF_HD void t2d_A2(int t, int c, const cpx<T>* tile, const cpx<T>* tw2d, cpx<T>* S /* S of this transform */) {
+// Sink: row(k2) -> where row k2 of the transposed intermediate lives (element n1 at row(k2)[n1])
+template <typename T, int N1> struct T2DScratchSink {           // the two-pass plan: S[k2][n1] in global memory
+  cpx<T>* S;
+  PF_HD cpx<T>* row(int k2) const { return S + (long long)k2 * N1; }
+};
+template <int A1, int A2, int SIGN, typename T, typename Sink>
+PF_HD void t2d_A2(int t, int c, const cpx<T>* tile, const cpx<T>* tw2d, Sink sink) {
   using G = T2D<A1, A2>;
   const int j = t & 15, g = t >> 4;
   cpx<T> u[16];
@@ -77,7 +83,7 @@ PF_HD void t2d_A2(int t, int c, const cpx<T>* tile, const cpx<T>* tw2d, cpx<T>* 
     for (int kb = 0; kb < A2; ++kb) {
       const int ka = g + A2 * r, k2 = ka + 16 * kb;
       const cpx<T> w = ldtab(tw2d + G::idx2d(c, ka, kb, j));
-      S[k2 * G::N1 + 16 * c + j] = cmul_dir<SIGN>(u[r * A2 + kb], w);
+      sink.row(k2)[16 * c + j] = cmul_dir<SIGN>(u[r * A2 + kb], w);
     }
 }
 // ---- pass C, first half: thread t = q1 + A1*k2' loads row k2 = 16d + k2' at n1 = q1 + A1*i (i < 16), radix 16 over i -> k1a,
@@ -134,7 +140,7 @@ k_t2d_A(const cpx<T>* __restrict__ x, cpx<T>* __restrict__ S, long long batch, c
     const int c = (int)(w - b * CB);
     t2d_A1<A1, A2, SIGN, T>(t, x + b * (long long)G::NC + 16 * c, twA, tile);
     __syncthreads();
-    t2d_A2<A1, A2, SIGN, T>(t, c, tile, tw2d, S + b * (long long)G::NC);
+    t2d_A2<A1, A2, SIGN, T>(t, c, tile, tw2d, T2DScratchSink<T, G::N1>{S + b * (long long)G::NC});
     __syncthreads();
   }
 }
@@ -156,6 +162,80 @@ k_t2d_C(const cpx<T>* __restrict__ S, cpx<T>* __restrict__ X, long long batch, c
     t2d_C2<A1, A2, SIGN, T>(t, tile, X + b * (long long)G::NC + 16 * d);
     __syncthreads();
   }
+}
+#endif  // __CUDACC__
+
+// =====================================================================================================================
+// CLUSTER-FUSED form: the same two phase pairs, but pass A hands its rows to the CTA that runs pass C through DISTRIBUTED
+// SHARED MEMORY instead of the scratch array -- one HBM read and one HBM write per transform (ceiling 1.0 instead of 0.5).
+//   cluster of CL CTAs per transform; column blocks c = rank + CL*qa (qa < QA = N1/16/CL) are transformed one after the
+//   other; value (n1, k2) goes to row block db = k2/16, owned by CTA db % CL as its block number db / CL:
+//        park[(db / CL)][k2 % 16][n1]          (lanes j -> 128-byte runs, as in the scratch version)
+//   one cluster barrier; then every CTA runs pass C for its QC = N2/16/CL row blocks from LOCAL shared memory.
+//   Barrier protocol as in cluster_kernels.cuh: "parks free" (relaxed arrive after the last pass-C1 read, wait before the
+//   first remote store of the next transform) and "parks full" (release / acquire).
+// STATUS (end of round 1): arithmetic and index algebra verified by CPU stepping (tests/test_host_logic.py); NOT YET RUN ON
+// HARDWARE.  Opt-in only (PFFFT_B200_TILED2D=2); its GPU tests are gated (PFFFT_B200_TEST_T2D_CLUSTER=1).
+// =====================================================================================================================
+template <int A1, int A2, int CL> struct T2DC {
+  using G = T2D<A1, A2>;
+  static constexpr int CB = G::N1 / 16, RB = G::N2 / 16;       // column blocks (pass A) / row blocks (pass C) per transform
+  static_assert(CB % CL == 0 && RB % CL == 0, "blocks divide evenly over the cluster");
+  static constexpr int QA = CB / CL, QC = RB / CL;
+  static constexpr int NT = G::TA > G::TC ? G::TA : G::TC;       // threads per CTA
+  static constexpr int TILE = 16 * (G::N1 > G::N2 ? G::N1 : G::N2);
+  static constexpr int PARK_BLOCK = 16 * G::N1;                  // words of one row block [16][N1]
+  static constexpr size_t kSmem = (size_t)(TILE + QC * PARK_BLOCK);   // in complex words
+};
+// Remote: rank -> base of that CTA's park buffer
+template <typename T, int A1, int A2, int CL, typename Remote> struct T2DClusterSink {
+  Remote remote;
+  PF_HD cpx<T>* row(int k2) const {
+    const int db = k2 >> 4;
+    return remote(db % CL) + (db / CL) * T2DC<A1, A2, CL>::PARK_BLOCK + (k2 & 15) * T2D<A1, A2>::N1;
+  }
+};
+
+#ifdef __CUDACC__
+template <typename T, int A1, int A2, int CL, int SIGN, int MINB>
+__global__ void __launch_bounds__((T2DC<A1, A2, CL>::NT), MINB)
+k_t2d_cluster(const cpx<T>* __restrict__ x, cpx<T>* __restrict__ X, long long batch,
+              const cpx<T>* twA, const cpx<T>* twC, const cpx<T>* tw2d) {
+  using G = T2D<A1, A2>;
+  using K = T2DC<A1, A2, CL>;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
+  cpx<T>* park = tile + K::TILE;                                // [QC][16][N1]
+  const int t = threadIdx.x;
+  const int rank = (int)cluster_cta_rank();
+  const long long nclusters = gridDim.x / CL, cid = blockIdx.x / CL;
+  const T2DClusterSink<T, A1, A2, CL, ClusterRemote<T>> sink{ClusterRemote<T>{park}};
+  cluster_arrive_relaxed();                                     // "parks free", phase 0
+  for (long long tr = cid; tr < batch; tr += nclusters) {
+    asm volatile("" : "+l"(twA), "+l"(twC), "+l"(tw2d));
+    const cpx<T>* src = x + tr * (long long)G::NC;
+    cpx<T>* dst = X + tr * (long long)G::NC;
+#pragma unroll 1
+    for (int qa = 0; qa < K::QA; ++qa) {
+      const int c = rank + CL * qa;
+      if (t < G::TA) t2d_A1<A1, A2, SIGN, T>(t, src + 16 * c, twA, tile);
+      __syncthreads();
+      if (qa == 0) cluster_wait();                              // every CTA has finished reading its parks
+      if (t < G::TA) t2d_A2<A1, A2, SIGN, T>(t, c, tile, tw2d, sink);
+      __syncthreads();                                          // tile free for the next column block / pass C
+    }
+    cluster_arrive(); cluster_wait();                           // parks full (release / acquire orders the DSMEM stores)
+#pragma unroll 1
+    for (int qc = 0; qc < K::QC; ++qc) {
+      const int d = rank + CL * qc;
+      if (t < G::TC) t2d_C1<A1, A2, SIGN, T>(t, park + qc * K::PARK_BLOCK, twC, tile);
+      __syncthreads();
+      if (qc == K::QC - 1) cluster_arrive_relaxed();            // last read of this CTA's parks is done
+      if (t < G::TC) t2d_C2<A1, A2, SIGN, T>(t, tile, dst + 16 * d);
+      __syncthreads();
+    }
+  }
+  cluster_wait();                                               // no CTA exits while a peer may still address its memory
 }
 #endif  // __CUDACC__
 

@@ -336,7 +336,7 @@ static void emu_t2d_run(const float* in, float* out) {
   cf* X = reinterpret_cast<cf*>(out);
   for (int c = 0; c < G::N1 / 16; ++c) {
     for (int t = 0; t < G::TA; ++t) t2d_A1<A1, A2, SIGN, float>(t, x + 16 * c, twA, tileA.data());
-    for (int t = 0; t < G::TA; ++t) t2d_A2<A1, A2, SIGN, float>(t, c, tileA.data(), tw2d, S.data());
+    for (int t = 0; t < G::TA; ++t) t2d_A2<A1, A2, SIGN, float>(t, c, tileA.data(), tw2d, T2DScratchSink<float, G::N1>{S.data()});
   }
   for (int d = 0; d < G::N2 / 16; ++d) {
     for (int t = 0; t < G::TC; ++t) t2d_C1<A1, A2, SIGN, float>(t, S.data() + (size_t)16 * d * G::N1, twC, tileC.data());
@@ -367,5 +367,41 @@ extern "C" int emu_t2d_conflicts(int A1, int A2) {
   if (A1 == 16 && A2 == 8) return emu_t2d_conflicts_c<16, 8>();
   if (A1 == 8 && A2 == 16) return emu_t2d_conflicts_c<8, 16>();
   if (A1 == 16 && A2 == 16) return emu_t2d_conflicts_c<16, 16>();
+  return -1;
+}
+
+// ---- cluster-fused tiled 2-D plan: the CL CTAs of one cluster stepped phase by phase (barriers = phase ends)
+template <int A1, int A2, int CL, int SIGN>
+static void emu_t2d_cluster_run(const float* in, float* out) {
+  using namespace pf;
+  using G = T2D<A1, A2>; using K = T2DC<A1, A2, CL>;
+  std::vector<float> tab(2 * ((size_t)G::N1 + G::N2 + G::NC));
+  t2d_fill_tables<float, A1, A2>(tab.data());
+  const cf* twA = reinterpret_cast<const cf*>(tab.data());
+  const cf* twC = twA + G::N2;
+  const cf* tw2d = twC + G::N1;
+  std::vector<std::vector<cf>> tile(CL, std::vector<cf>(K::TILE)), park(CL, std::vector<cf>((size_t)K::QC * K::PARK_BLOCK));
+  cf* bases[CL];
+  for (int c = 0; c < CL; ++c) bases[c] = park[c].data();
+  const T2DClusterSink<float, A1, A2, CL, EmuRemote> sink{EmuRemote{bases}};
+  const cf* x = reinterpret_cast<const cf*>(in);
+  cf* X = reinterpret_cast<cf*>(out);
+  for (int qa = 0; qa < K::QA; ++qa)
+    for (int rank = 0; rank < CL; ++rank) {
+      const int c = rank + CL * qa;
+      for (int t = 0; t < G::TA; ++t) t2d_A1<A1, A2, SIGN, float>(t, x + 16 * c, twA, tile[rank].data());
+      for (int t = 0; t < G::TA; ++t) t2d_A2<A1, A2, SIGN, float>(t, c, tile[rank].data(), tw2d, sink);
+    }
+  for (int qc = 0; qc < K::QC; ++qc)
+    for (int rank = 0; rank < CL; ++rank) {
+      const int d = rank + CL * qc;
+      for (int t = 0; t < G::TC; ++t) t2d_C1<A1, A2, SIGN, float>(t, park[rank].data() + (size_t)qc * K::PARK_BLOCK, twC, tile[rank].data());
+      for (int t = 0; t < G::TC; ++t) t2d_C2<A1, A2, SIGN, float>(t, tile[rank].data(), X + 16 * d);
+    }
+}
+extern "C" int emu_t2d_cluster(int A1, int A2, int CL, int dir, const float* in, float* out) {
+#define T2C(a1, a2, cl) if (A1 == a1 && A2 == a2 && CL == cl) { if (dir == 0) emu_t2d_cluster_run<a1, a2, cl, -1>(in, out); else emu_t2d_cluster_run<a1, a2, cl, +1>(in, out); return 0; }
+  T2C(8, 8, 8) T2C(8, 8, 4) T2C(16, 8, 8) T2C(16, 16, 8) T2C(16, 16, 16)
+#undef T2C
   return -1;
 }

@@ -218,3 +218,19 @@ def test_tiled_2d_large_n_phases(emu, ref, R):
         assert R.relmax(o, want) <= 2e-6, (a1, a2)
         assert emu.emu_t2d(a1, a2, 1, want.ctypes.data, o.ctypes.data) == 0
         assert R.relmax(o / N, x) <= 2e-6, (a1, a2)
+
+
+def test_tiled_2d_cluster_fused_phases(emu, ref, R):
+    """cluster-fused form of the tiled plan (pass A -> pass C through the peers' shared memory): every cluster shape"""
+    emu.emu_t2d_cluster.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2
+    rng = np.random.default_rng(14)
+    for a1, a2, cl in [(8, 8, 8), (8, 8, 4), (16, 8, 8), (16, 16, 8), (16, 16, 16)]:
+        N = 256 * a1 * a2
+        x = (rng.random(2 * N) * 2 - 1).astype(np.float32)
+        want = ref.transform(N, 1, x, 0, True)
+        o = np.zeros(2 * N, np.float32)
+        assert emu.emu_t2d_cluster(a1, a2, cl, 0, x.ctypes.data, o.ctypes.data) == 0
+        assert R.relmax(o, want) <= 2e-6, (a1, a2, cl)
+        if cl == 8:
+            assert emu.emu_t2d_cluster(a1, a2, cl, 1, want.ctypes.data, o.ctypes.data) == 0
+            assert R.relmax(o / N, x) <= 2e-6, (a1, a2, cl)

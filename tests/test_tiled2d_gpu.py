@@ -49,3 +49,37 @@ def test_tiled2d_vs_reference(pf, ref, R, Nc, tr):
         assert torch.equal(yb[-1], y[0]) and torch.equal(yb[big // 2], y[0])
     finally:
         s.close()
+
+
+@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_CLUSTER") != "1",
+                    reason="opt-in: the cluster-fused tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_CLUSTER=1)")
+@pytest.mark.parametrize("Nc", [16384, 32768, 65536])
+def test_tiled2d_cluster_fused_vs_reference(pf, ref, R, Nc):
+    """PFFFT_B200_TILED2D=2: pass A hands its rows to pass C through DSMEM (8-CTA clusters).  Written after the GPU budget
+    of round 1 was spent: verified by CPU stepping only (tests/test_host_logic.py), first thing to run next round."""
+    import torch
+    old = os.environ.get("PFFFT_B200_TILED2D")
+    os.environ["PFFFT_B200_TILED2D"] = "2"
+    try:
+        s = pf.Setup(Nc, 1)
+    finally:
+        if old is None:
+            os.environ.pop("PFFFT_B200_TILED2D", None)
+        else:
+            os.environ["PFFFT_B200_TILED2D"] = old
+    try:
+        if not s.kernel.startswith("tiled2d_cluster8_"):
+            pytest.skip("cluster shape not schedulable: " + s.kernel)
+        batch = max(8, (64 << 20) // (8 * Nc)) + 3
+        x = uniform(np.random.default_rng(Nc), 5 * 2 * Nc).reshape(5, 2 * Nc)
+        xd = torch.from_numpy(x).cuda().repeat((batch + 4) // 5, 1)[:batch].contiguous()
+        y = s.transform_batch(xd, pf.PFFFT_FORWARD, True)
+        z = s.transform_batch(y, pf.PFFFT_BACKWARD, True)
+        torch.cuda.synchronize()
+        want = ref.transform_batch(Nc, 1, x[:2], 0, True)
+        for b in range(2):
+            assert R.relmax(y[b].cpu().numpy(), want[b]) <= 1e-5
+        assert torch.equal(y[5:10], y[0:5]) and torch.equal(y[batch - batch % 5 - 5:batch - batch % 5], y[0:5])
+        assert float(((z / Nc - xd) ** 2).sum(dim=1).max()) <= Nc * 1e-7
+    finally:
+        s.close()
