@@ -219,7 +219,10 @@ template <> struct FastHooks<float> {
         s->split_fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_fused_ok<float>(R, N2);
         s->fast_variant = 300;
         int CL = 0, Q = 1, mode = 0, a1 = 0, a2 = 0;
-        if (t2d_enabled(s->Nc) && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {
+        if (t2dg_requested() && t2dg_shape_for(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_float(s->Nc)) != nullptr) {
+          s->split_fused = false;
+          snprintf(s->name_buf, sizeof(s->name_buf), "tiled2dg_%dx%d", 16 * a1, 16 * a2);
+        } else if (t2d_enabled(s->Nc) && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {
           s->split_t2d = true; s->split_fused = false;
           s->split_t2d_cluster = t2d_cluster_requested() && t2d_cluster_max_active_float(s->Nc) > 0;
           snprintf(s->name_buf, sizeof(s->name_buf), s->split_t2d_cluster ? "tiled2d_cluster8_%dx%d" : "tiled2d_%dx%d", 16 * a1, 16 * a2);

@@ -165,6 +165,14 @@ size_t t2d_table_cpx(int Nc);                                   // [twA: N2][twC
 void t2d_fill_tables_float(int Nc, float* dst);
 int t2d_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* S, cpx<float>* X, long long batch,
                      const cpx<float>* tables, int sm_count, cudaStream_t st);
+// general-radix form (Nc = 256*A1*A2: 7680, 9216, 12288, 20480, 24576, 36864, 40960, 49152, 61440 ...; tiled2d_general.cu):
+// verified by CPU stepping, NOT YET RUN ON HARDWARE -> only with PFFFT_B200_TILED2D_GENERAL=1.  Its tables are a separate
+// allocation made when the plan is chosen, so plans without the switch are byte-for-byte what they were.
+bool t2dg_shape_for(int Nc, int* A1, int* A2);
+cpx<float>* t2dg_make_tables_float(int Nc);
+int t2dg_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* S, cpx<float>* X, long long batch,
+                      const cpx<float>* tables, int sm_count, cudaStream_t st);
+inline bool t2dg_requested() { const char* e = getenv("PFFFT_B200_TILED2D_GENERAL"); return e && atoi(e) != 0; }
 // cluster-fused form of the same plan (8-CTA clusters, pass A -> pass C through DSMEM, one HBM round trip): verified by CPU
 // stepping, NOT YET RUN ON HARDWARE -> only with PFFFT_B200_TILED2D=2
 int t2d_cluster_max_active_float(int Nc);
@@ -292,7 +300,7 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   // input that already IS the dense complex core (complex canonical, or real time samples read as pairs)
   const bool direct_in = dense_io && p.in_limit < 0 && (LM == L_C_ORD || LM == L_R_TIME) && vec_aligned<T>(p.in);
   const bool direct_out = dense_io && (SM == S_C_ORD || (SM == S_R_TIME && p.out_count >= s->N)) && vec_aligned<T>(p.out);
-  const bool one_kernel = s->split_fused || s->split_cluster > 0 || (s->split_t2d && s->split_t2d_cluster);
+  const bool one_kernel = !s->d_aux_tables && (s->split_fused || s->split_cluster > 0 || (s->split_t2d && s->split_t2d_cluster));
   const bool need_scratch = !direct_in || !direct_out || !one_kernel;
   std::unique_lock<std::mutex> lock(s->scratch_mu, std::defer_lock);
   if (need_scratch) {
@@ -308,7 +316,12 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
   }
   // (the fused kernel reads a whole transform before it writes it, so src == dst is fine)
   cpx<T>* dst = direct_out ? reinterpret_cast<cpx<T>*>(p.out) : s->d_scratch[0];
-  if (s->split_t2d && s->split_t2d_cluster) {
+  if (s->d_aux_tables) {                                          // general-radix tiled plan (opt-in)
+    int rc = (int)cudaErrorInvalidValue;
+    if constexpr (sizeof(T) == 4)
+      rc = t2dg_launch_float(s->Nc, SIGN, src, s->d_scratch[1], dst, p.batch, reinterpret_cast<const cpx<float>*>(s->d_aux_tables), s->sm_count, st);
+    if (rc) return rc;
+  } else if (s->split_t2d && s->split_t2d_cluster) {
     int rc = (int)cudaErrorInvalidValue;
     if constexpr (sizeof(T) == 4)
       rc = t2d_cluster_launch_float(s->Nc, SIGN, src, dst, p.batch, s->tw_fast + split_table_cpx(s->Nc, s->split_N2), st);

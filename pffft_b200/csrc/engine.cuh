@@ -68,6 +68,7 @@ template <typename T> struct Setup {
   int split_cluster = 0, split_Q = 1;     // ... or ONE kernel on clusters of split_cluster CTAs (rows parked in DSMEM), split_Q rows per CTA
   bool split_t2d = false;                 // ... or the tiled two-dimensional plan (two dense passes)
   bool split_t2d_cluster = false;         //     its cluster-fused form (pass A -> pass C through DSMEM; opt-in)
+  void* d_aux_tables = nullptr;           //     tables of the general-radix tiled plan (opt-in; own allocation, freed with the plan)
   int split_mode = 0;                     //     0 strided row reads, 1 rows distributed through DSMEM
   char name_buf[40] = {0};
   int tpc = 1;                            // transforms resident per CTA (shared-memory kernel), a power of two
@@ -185,6 +186,7 @@ template <typename T, typename S> void engine_destroy_setup(S* s) {
   for (int i = 0; i < 2; ++i) if (s->d_scratch[i]) cudaFree(s->d_scratch[i]);
   if (s->scratch_done) cudaEventDestroy(s->scratch_done);
   if (s->d_tables) cudaFree(s->d_tables);
+  if (s->d_aux_tables) cudaFree(s->d_aux_tables);
   if (cur != s->device) cudaSetDevice(cur);
   delete s;
 }

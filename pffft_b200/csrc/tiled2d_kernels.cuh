@@ -239,6 +239,95 @@ k_t2d_cluster(const cpx<T>* __restrict__ x, cpx<T>* __restrict__ X, long long ba
 }
 #endif  // __CUDACC__
 
+// =====================================================================================================================
+// GENERAL radices: N1 = 16*A1, N2 = 16*A2 with A1, A2 any size of the register DFT library (2,3,4,5,6,8,9,10,12,15,16), i.e.
+// Nc = 256*A1*A2: 7680 = 96 x 80, 9216 = 96 x 96, 12288 = 128 x 96, 20480 = 160 x 128, 24576 = 192 x 128, 36864 = 192 x 192,
+// 40960 = 256 x 160, 49152 = 256 x 192, 61440 = 256 x 240 ...  Same passes and tables; 256 threads per CTA:
+//   first halves: 16*A threads hold 16 points each (pass C pads its rows to 16 lanes so the XOR swizzle stays conflict free);
+//   second halves: every thread finishes ONE (column, k_a) pair with a radix-A register DFT (natural order in and out).
+// STATUS (end of round 1): verified by CPU stepping for every shape below; NOT YET RUN ON HARDWARE.  Opt-in only
+// (PFFFT_B200_TILED2D_GENERAL=1), GPU tests gated (PFFFT_B200_TEST_T2D_GENERAL=1).
+// =====================================================================================================================
+template <int A1, int A2, int SIGN, typename T, typename Sink>
+PF_HD void t2dg_A2(int t, int c, const cpx<T>* tile, const cpx<T>* tw2d, Sink sink) {   // t < 256: j = t & 15, k_a = t >> 4
+  using G = T2D<A1, A2>;
+  const int j = t & 15, ka = t >> 4;
+  cpx<T> u[A2];
+#pragma unroll
+  for (int q = 0; q < A2; ++q) u[q] = tile[(ka * A2 + q) * 16 + j];
+  dft_small<A2, SIGN>(u);
+#pragma unroll
+  for (int kb = 0; kb < A2; ++kb)
+    sink.row(ka + 16 * kb)[16 * c + j] = cmul_dir<SIGN>(u[kb], ldtab(tw2d + G::idx2d(c, ka, kb, j)));
+}
+// pass C, first half with rows padded to 16 lanes: thread t = q1 + 16*k2' works when q1 < A1
+template <int A1, int A2, int SIGN, typename T>
+PF_HD void t2dg_C1(int t, const cpx<T>* rows, const cpx<T>* twC, cpx<T>* tile) {
+  using G = T2D<A1, A2>;
+  const int q1 = t & 15, k2p = t >> 4;
+  if (q1 >= A1) return;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = rows[k2p * G::N1 + q1 + A1 * brev4(p)];
+  reg_fft<16, SIGN>(v);
+  const int col = k2p ^ q1;
+  tile[(0 * A1 + q1) * 16 + col] = v[0];
+#pragma unroll
+  for (int ka = 1; ka < 16; ++ka) tile[(ka * A1 + q1) * 16 + col] = cmul_dir<SIGN>(v[ka], ldtab(twC + ka * A1 + q1));
+}
+template <int A1, int A2, int SIGN, typename T>
+PF_HD void t2dg_C2(int t, const cpx<T>* tile, cpx<T>* xblk) {        // t < 256: k2' = t & 15, k1a = t >> 4
+  using G = T2D<A1, A2>;
+  const int k2p = t & 15, ka = t >> 4;
+  cpx<T> u[A1];
+#pragma unroll
+  for (int q = 0; q < A1; ++q) u[q] = tile[(ka * A1 + q) * 16 + (k2p ^ q)];
+  dft_small<A1, SIGN>(u);
+#pragma unroll
+  for (int kb = 0; kb < A1; ++kb) xblk[k2p + (long long)G::N2 * (ka + 16 * kb)] = u[kb];
+}
+
+#ifdef __CUDACC__
+template <typename T, int A1, int A2, int SIGN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_t2dg_A(const cpx<T>* __restrict__ x, cpx<T>* __restrict__ S, long long batch, const cpx<T>* twA, const cpx<T>* tw2d) {
+  using G = T2D<A1, A2>;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);      // 16*N2 words
+  const int t = threadIdx.x;
+  constexpr int CB = G::N1 / 16;
+  const long long tiles = batch * CB;
+  for (long long w = blockIdx.x; w < tiles; w += gridDim.x) {
+    asm volatile("" : "+l"(twA), "+l"(tw2d));
+    const long long b = w / CB;
+    const int c = (int)(w - b * CB);
+    if (t < G::TA) t2d_A1<A1, A2, SIGN, T>(t, x + b * (long long)G::NC + 16 * c, twA, tile);
+    __syncthreads();
+    t2dg_A2<A1, A2, SIGN, T>(t, c, tile, tw2d, T2DScratchSink<T, G::N1>{S + b * (long long)G::NC});
+    __syncthreads();
+  }
+}
+template <typename T, int A1, int A2, int SIGN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_t2dg_C(const cpx<T>* __restrict__ S, cpx<T>* __restrict__ X, long long batch, const cpx<T>* twC) {
+  using G = T2D<A1, A2>;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);      // 16*N1 words
+  const int t = threadIdx.x;
+  constexpr int RB = G::N2 / 16;
+  const long long tiles = batch * RB;
+  for (long long w = blockIdx.x; w < tiles; w += gridDim.x) {
+    asm volatile("" : "+l"(twC));
+    const long long b = w / RB;
+    const int d = (int)(w - b * RB);
+    t2dg_C1<A1, A2, SIGN, T>(t, S + b * (long long)G::NC + (long long)16 * d * G::N1, twC, tile);
+    __syncthreads();
+    t2dg_C2<A1, A2, SIGN, T>(t, tile, X + b * (long long)G::NC + 16 * d);
+    __syncthreads();
+  }
+}
+#endif  // __CUDACC__
+
 // host: fill [twA: N2][twC: N1][tw2d: Nc]
 template <typename T, int A1, int A2> void t2d_fill_tables(T* dst) {
   using G = T2D<A1, A2>;

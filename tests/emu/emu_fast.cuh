@@ -405,3 +405,52 @@ extern "C" int emu_t2d_cluster(int A1, int A2, int CL, int dir, const float* in,
 #undef T2C
   return -1;
 }
+
+// ---- tiled 2-D plan, general radices (k_t2dg_A / k_t2dg_C): 256 threads per tile
+template <int A1, int A2, int SIGN>
+static void emu_t2dg_run(const float* in, float* out) {
+  using namespace pf;
+  using G = T2D<A1, A2>;
+  std::vector<float> tab(2 * ((size_t)G::N1 + G::N2 + G::NC));
+  t2d_fill_tables<float, A1, A2>(tab.data());
+  const cf* twA = reinterpret_cast<const cf*>(tab.data());
+  const cf* twC = twA + G::N2;
+  const cf* tw2d = twC + G::N1;
+  std::vector<cf> S(G::NC), tileA(16 * G::N2), tileC(16 * G::N1);
+  const cf* x = reinterpret_cast<const cf*>(in);
+  cf* X = reinterpret_cast<cf*>(out);
+  for (int c = 0; c < G::N1 / 16; ++c) {
+    for (int t = 0; t < G::TA; ++t) t2d_A1<A1, A2, SIGN, float>(t, x + 16 * c, twA, tileA.data());
+    for (int t = 0; t < 256; ++t) t2dg_A2<A1, A2, SIGN, float>(t, c, tileA.data(), tw2d, T2DScratchSink<float, G::N1>{S.data()});
+  }
+  for (int d = 0; d < G::N2 / 16; ++d) {
+    for (int t = 0; t < 256; ++t) t2dg_C1<A1, A2, SIGN, float>(t, S.data() + (size_t)16 * d * G::N1, twC, tileC.data());
+    for (int t = 0; t < 256; ++t) t2dg_C2<A1, A2, SIGN, float>(t, tileC.data(), X + 16 * d);
+  }
+}
+#define PF_T2DG_SHAPES(X) X(6, 5) X(6, 6) X(8, 6) X(10, 8) X(12, 8) X(12, 12) X(16, 10) X(16, 12) X(16, 15) X(8, 8) X(16, 8) X(16, 16)
+extern "C" int emu_t2dg(int A1, int A2, int dir, const float* in, float* out) {
+#define X(a1, a2) if (A1 == a1 && A2 == a2) { if (dir == 0) emu_t2dg_run<a1, a2, -1>(in, out); else emu_t2dg_run<a1, a2, +1>(in, out); return 0; }
+  PF_T2DG_SHAPES(X)
+#undef X
+  return -1;
+}
+// conflict audit of the padded pass-C tile and the pass-A tile for general A (1 = conflict free)
+template <int A1, int A2> static int emu_t2dg_conflicts_c() {
+  int worst = 1;
+  auto audit = [&](auto addr, auto active, int nthreads) {
+    for (int h = 0; h < nthreads; h += 16) { int cnt[16] = {0}; for (int l = 0; l < 16; ++l) if (active(h + l)) cnt[addr(h + l) & 15]++; for (int b = 0; b < 16; ++b) if (cnt[b] > worst) worst = cnt[b]; }
+  };
+  auto all = [](int) { return true; };
+  for (int ka = 0; ka < 16; ++ka) audit([&](int t) { return (ka * A2 + (t >> 4)) * 16 + (t & 15); }, all, 16 * A2);          // A1 writes
+  for (int q = 0; q < A2; ++q) audit([&](int t) { return ((t >> 4) * A2 + q) * 16 + (t & 15); }, all, 256);                    // A2 reads
+  for (int ka = 0; ka < 16; ++ka) audit([&](int t) { return (ka * A1 + (t & 15)) * 16 + ((t >> 4) ^ (t & 15)); }, [&](int t) { return (t & 15) < A1; }, 256);   // C1 writes
+  for (int q = 0; q < A1; ++q) audit([&](int t) { return ((t >> 4) * A1 + q) * 16 + ((t & 15) ^ q); }, all, 256);              // C2 reads
+  return worst;
+}
+extern "C" int emu_t2dg_conflicts(int A1, int A2) {
+#define X(a1, a2) if (A1 == a1 && A2 == a2) return emu_t2dg_conflicts_c<a1, a2>();
+  PF_T2DG_SHAPES(X)
+#undef X
+  return -1;
+}

@@ -234,3 +234,20 @@ def test_tiled_2d_cluster_fused_phases(emu, ref, R):
         if cl == 8:
             assert emu.emu_t2d_cluster(a1, a2, cl, 1, want.ctypes.data, o.ctypes.data) == 0
             assert R.relmax(o / N, x) <= 2e-6, (a1, a2, cl)
+
+
+def test_tiled_2d_general_radix_phases(emu, ref, R):
+    """general-radix tiled plan (Nc = 256*A1*A2, radix 3/5 factors included): every instantiated shape, conflict audit"""
+    emu.emu_t2dg.argtypes = [C.c_int] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(15)
+    for a1, a2 in [(6, 5), (6, 6), (8, 6), (10, 8), (12, 8), (12, 12), (16, 10), (16, 12), (16, 15), (8, 8), (16, 16)]:
+        assert emu.emu_t2dg_conflicts(a1, a2) == 1, (a1, a2)
+        N = 256 * a1 * a2
+        x = (rng.random(2 * N) * 2 - 1).astype(np.float32)
+        want = ref.transform(N, 1, x, 0, True)
+        o = np.zeros(2 * N, np.float32)
+        assert emu.emu_t2dg(a1, a2, 0, x.ctypes.data, o.ctypes.data) == 0
+        assert R.relmax(o, want) <= 2e-6, (a1, a2)
+        if a1 in (6, 12):
+            assert emu.emu_t2dg(a1, a2, 1, want.ctypes.data, o.ctypes.data) == 0
+            assert R.relmax(o / N, x) <= 2e-6, (a1, a2)

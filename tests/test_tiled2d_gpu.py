@@ -83,3 +83,32 @@ def test_tiled2d_cluster_fused_vs_reference(pf, ref, R, Nc):
         assert float(((z / Nc - xd) ** 2).sum(dim=1).max()) <= Nc * 1e-7
     finally:
         s.close()
+
+
+@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_GENERAL") != "1",
+                    reason="opt-in: the general-radix tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_GENERAL=1)")
+@pytest.mark.parametrize("Nc", [7680, 9216, 12288, 20480, 24576, 36864, 40960, 49152, 61440, 16384, 65536])
+def test_tiled2d_general_radix_vs_reference(pf, ref, R, Nc):
+    """PFFFT_B200_TILED2D_GENERAL=1: Nc = 256*A1*A2 with radix-3/5 factors.  CPU-stepped only so far."""
+    import torch
+    old = os.environ.get("PFFFT_B200_TILED2D_GENERAL")
+    os.environ["PFFFT_B200_TILED2D_GENERAL"] = "1"
+    try:
+        s = pf.Setup(Nc, 1)
+    finally:
+        if old is None:
+            os.environ.pop("PFFFT_B200_TILED2D_GENERAL", None)
+        else:
+            os.environ["PFFFT_B200_TILED2D_GENERAL"] = old
+    try:
+        assert s.kernel.startswith("tiled2dg_"), s.kernel
+        x = uniform(np.random.default_rng(Nc), 3 * 2 * Nc).reshape(3, 2 * Nc)
+        xd = torch.from_numpy(x).cuda()
+        y = s.transform_batch(xd, pf.PFFFT_FORWARD, True)
+        z = s.transform_batch(y, pf.PFFFT_BACKWARD, True)
+        torch.cuda.synchronize()
+        want = ref.transform_batch(Nc, 1, x[:1], 0, True)
+        assert R.relmax(y[0].cpu().numpy(), want[0]) <= 1e-5
+        assert float(((z / Nc - xd) ** 2).sum(dim=1).max()) <= Nc * 1e-7
+    finally:
+        s.close()
