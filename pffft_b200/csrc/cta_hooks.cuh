@@ -172,6 +172,10 @@ bool t2dg_shape_for(int Nc, int* A1, int* A2);
 cpx<float>* t2dg_make_tables_float(int Nc);
 int t2dg_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* S, cpx<float>* X, long long batch,
                       const cpx<float>* tables, int sm_count, cudaStream_t st);
+bool t2dg_shape_for_double(int Nc, int* A1, int* A2);            // double: the power-of-two shapes
+cpx<double>* t2dg_make_tables_double(int Nc);
+int t2dg_launch_double(int Nc, int sign, const cpx<double>* x, cpx<double>* S, cpx<double>* X, long long batch,
+                       const cpx<double>* tables, int sm_count, cudaStream_t st);
 inline bool t2dg_requested() { const char* e = getenv("PFFFT_B200_TILED2D_GENERAL"); return e && atoi(e) != 0; }
 // cluster-fused form of the same plan (8-CTA clusters, pass A -> pass C through DSMEM, one HBM round trip): verified by CPU
 // stepping, NOT YET RUN ON HARDWARE -> only with PFFFT_B200_TILED2D=2
@@ -320,6 +324,8 @@ int run_split_modes(Setup<T>* s, Rows rows_fn, const XformParams<T>& p, cudaStre
     int rc = (int)cudaErrorInvalidValue;
     if constexpr (sizeof(T) == 4)
       rc = t2dg_launch_float(s->Nc, SIGN, src, s->d_scratch[1], dst, p.batch, reinterpret_cast<const cpx<float>*>(s->d_aux_tables), s->sm_count, st);
+    else
+      rc = t2dg_launch_double(s->Nc, SIGN, src, s->d_scratch[1], dst, p.batch, reinterpret_cast<const cpx<double>*>(s->d_aux_tables), s->sm_count, st);
     if (rc) return rc;
   } else if (s->split_t2d && s->split_t2d_cluster) {
     int rc = (int)cudaErrorInvalidValue;
@@ -394,6 +400,13 @@ template <typename T> struct CtaOnlyHooks {
       s->split_R = R; s->split_N2 = N2; s->split_fused = fused;
       s->fast_variant = 300;
       snprintf(s->name_buf, sizeof(s->name_buf), fused ? "cta_split_%dx%d" : "split_%dx%d", R, N2);
+      if constexpr (sizeof(T) == 8) {                            // opt-in tiled plan for doubles (not yet run on hardware)
+        int a1 = 0, a2 = 0;
+        if (t2dg_requested() && t2dg_shape_for_double(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_double(s->Nc)) != nullptr) {
+          s->split_fused = false;
+          snprintf(s->name_buf, sizeof(s->name_buf), "tiled2dg_%dx%d", 16 * a1, 16 * a2);
+        }
+      }
       s->kernel_name = s->name_buf;
       return true;
     }

@@ -10,23 +10,26 @@
 namespace pf {
 namespace {
 
-template <int A1, int A2, int SIGN> struct T2DGLaunch {
+template <typename T, int A1, int A2, int SIGN> struct T2DGLaunch {
   using G = T2D<A1, A2>;
-  static constexpr int MINB = 3;                                                  // 80 registers per thread, 768 threads per SM
-  static constexpr size_t kSmemA = (size_t)16 * G::N2 * sizeof(cf), kSmemC = (size_t)16 * G::N1 * sizeof(cf);
-  static int run(const cf* x, cf* S, cf* X, long long batch, const cf* tables, int sm_count, cudaStream_t st) {
-    auto ka = k_t2dg_A<float, A1, A2, SIGN, MINB>;
-    auto kc = k_t2dg_C<float, A1, A2, SIGN, MINB>;
+  using cx = cpx<T>;
+  static constexpr int MINB = sizeof(T) == 4 ? 3 : 1;                             // float: 80 registers, 768 threads per SM
+  static constexpr size_t kSmemA = (size_t)16 * G::N2 * sizeof(cx), kSmemC = (size_t)16 * G::N1 * sizeof(cx);
+  static int run(const cx* x, cx* S, cx* X, long long batch, const cx* tables, int sm_count, cudaStream_t st) {
+    auto ka = k_t2dg_A<T, A1, A2, SIGN, MINB>;
+    auto kc = k_t2dg_C<T, A1, A2, SIGN, MINB>;
     static thread_local int per_sm_a = 0, per_sm_c = 0;
     if (per_sm_a == 0) {
+      if (kSmemA > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA));
+      if (kSmemC > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemC));
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ka, 256, kSmemA);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, kc, 256, kSmemC);
       if (per_sm_a < 1) per_sm_a = 1;
       if (per_sm_c < 1) per_sm_c = 1;
     }
-    const cf* twA = tables;
-    const cf* twC = twA + G::N2;
-    const cf* tw2d = twC + G::N1;
+    const cx* twA = tables;
+    const cx* twC = twA + G::N2;
+    const cx* tw2d = twC + G::N1;
     long long ga = batch * (G::N1 / 16), gc = batch * (G::N2 / 16);
     if (ga > (long long)sm_count * per_sm_a) ga = (long long)sm_count * per_sm_a;
     if (gc > (long long)sm_count * per_sm_c) gc = (long long)sm_count * per_sm_c;
@@ -70,11 +73,44 @@ cf* t2dg_make_tables_float(int Nc) {
   return reinterpret_cast<cf*>(d);
 }
 int t2dg_launch_float(int Nc, int sign, const cf* x, cf* S, cf* X, long long batch, const cf* tables, int sm_count, cudaStream_t st) {
-#define X(nc, a1, a2) if (Nc == nc) return sign < 0 ? T2DGLaunch<a1, a2, -1>::run(x, S, X, batch, tables, sm_count, st) \
-                                                    : T2DGLaunch<a1, a2, +1>::run(x, S, X, batch, tables, sm_count, st);
+#define X(nc, a1, a2) if (Nc == nc) return sign < 0 ? T2DGLaunch<float, a1, a2, -1>::run(x, S, X, batch, tables, sm_count, st) \
+                                                    : T2DGLaunch<float, a1, a2, +1>::run(x, S, X, batch, tables, sm_count, st);
   PF_T2DG_SIZES(X)
 #undef X
   set_error_msg("tiled2d general: size not instantiated");
+  return (int)cudaErrorInvalidValue;
+}
+
+// ---- double precision: the power-of-two shapes (PFFFT_B200_TILED2D_GENERAL=1 on a double plan)
+#define PF_T2DG_SIZES_D(X) X(16384, 8, 8) X(32768, 16, 8) X(65536, 16, 16)
+bool t2dg_shape_for_double(int Nc, int* A1, int* A2) {
+#define X(nc, a1, a2) if (Nc == nc) { *A1 = a1; *A2 = a2; return true; }
+  PF_T2DG_SIZES_D(X)
+#undef X
+  return false;
+}
+cd* t2dg_make_tables_double(int Nc) {
+  int a1 = 0, a2 = 0;
+  if (!t2dg_shape_for_double(Nc, &a1, &a2)) return nullptr;
+  std::vector<double> host(2 * ((size_t)16 * a1 + (size_t)16 * a2 + (size_t)Nc));
+#define X(nc, a1, a2) if (Nc == nc) t2d_fill_tables<double, a1, a2>(host.data());
+  PF_T2DG_SIZES_D(X)
+#undef X
+  void* d = nullptr;
+  if (cudaMalloc(&d, host.size() * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tiled2d general: table allocation", cudaGetLastError());
+    if (d) cudaFree(d);
+    return nullptr;
+  }
+  return reinterpret_cast<cd*>(d);
+}
+int t2dg_launch_double(int Nc, int sign, const cd* x, cd* S, cd* X, long long batch, const cd* tables, int sm_count, cudaStream_t st) {
+#define X(nc, a1, a2) if (Nc == nc) return sign < 0 ? T2DGLaunch<double, a1, a2, -1>::run(x, S, X, batch, tables, sm_count, st) \
+                                                    : T2DGLaunch<double, a1, a2, +1>::run(x, S, X, batch, tables, sm_count, st);
+  PF_T2DG_SIZES_D(X)
+#undef X
+  set_error_msg("tiled2d general (double): size not instantiated");
   return (int)cudaErrorInvalidValue;
 }
 

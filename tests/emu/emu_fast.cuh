@@ -454,3 +454,32 @@ extern "C" int emu_t2dg_conflicts(int A1, int A2) {
 #undef X
   return -1;
 }
+
+// ---- general tiled plan in double precision (the shapes the double launcher instantiates)
+template <int A1, int A2, int SIGN>
+static void emu_t2dg_run_d(const double* in, double* out) {
+  using namespace pf;
+  using G = T2D<A1, A2>;
+  std::vector<double> tab(2 * ((size_t)G::N1 + G::N2 + G::NC));
+  t2d_fill_tables<double, A1, A2>(tab.data());
+  const cd* twA = reinterpret_cast<const cd*>(tab.data());
+  const cd* twC = twA + G::N2;
+  const cd* tw2d = twC + G::N1;
+  std::vector<cd> S(G::NC), tileA(16 * G::N2), tileC(16 * G::N1);
+  const cd* x = reinterpret_cast<const cd*>(in);
+  cd* X = reinterpret_cast<cd*>(out);
+  for (int c = 0; c < G::N1 / 16; ++c) {
+    for (int t = 0; t < G::TA; ++t) t2d_A1<A1, A2, SIGN, double>(t, x + 16 * c, twA, tileA.data());
+    for (int t = 0; t < 256; ++t) t2dg_A2<A1, A2, SIGN, double>(t, c, tileA.data(), tw2d, T2DScratchSink<double, G::N1>{S.data()});
+  }
+  for (int d = 0; d < G::N2 / 16; ++d) {
+    for (int t = 0; t < 256; ++t) t2dg_C1<A1, A2, SIGN, double>(t, S.data() + (size_t)16 * d * G::N1, twC, tileC.data());
+    for (int t = 0; t < 256; ++t) t2dg_C2<A1, A2, SIGN, double>(t, tileC.data(), X + 16 * d);
+  }
+}
+extern "C" int emu_t2dg_double(int A1, int A2, int dir, const double* in, double* out) {
+#define X(a1, a2) if (A1 == a1 && A2 == a2) { if (dir == 0) emu_t2dg_run_d<a1, a2, -1>(in, out); else emu_t2dg_run_d<a1, a2, +1>(in, out); return 0; }
+  X(8, 8) X(16, 8) X(16, 16)
+#undef X
+  return -1;
+}

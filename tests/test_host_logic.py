@@ -251,3 +251,16 @@ def test_tiled_2d_general_radix_phases(emu, ref, R):
         if a1 in (6, 12):
             assert emu.emu_t2dg(a1, a2, 1, want.ctypes.data, o.ctypes.data) == 0
             assert R.relmax(o / N, x) <= 2e-6, (a1, a2)
+
+
+def test_tiled_2d_double_phases(emu):
+    """the double-precision instantiations of the general tiled plan against numpy float64 (1e-13; north_star: 1e-12)"""
+    emu.emu_t2dg_double.argtypes = [C.c_int] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(16)
+    for a1, a2 in [(8, 8), (16, 8), (16, 16)]:
+        N = 256 * a1 * a2
+        x = rng.random(2 * N) * 2 - 1
+        o = np.zeros(2 * N)
+        assert emu.emu_t2dg_double(a1, a2, 0, x.ctypes.data, o.ctypes.data) == 0
+        want = np.fft.fft(x.view(np.complex128))
+        assert np.abs(o.view(np.complex128) - want).max() <= 1e-13 * np.abs(want).max(), (a1, a2)

@@ -112,3 +112,27 @@ def test_tiled2d_general_radix_vs_reference(pf, ref, R, Nc):
         assert float(((z / Nc - xd) ** 2).sum(dim=1).max()) <= Nc * 1e-7
     finally:
         s.close()
+
+
+@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_GENERAL") != "1",
+                    reason="opt-in: the double-precision tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_GENERAL=1)")
+@pytest.mark.parametrize("Nc", [16384, 32768, 65536])
+def test_tiled2d_double_vs_numpy(pf, Nc):
+    import torch
+    old = os.environ.get("PFFFT_B200_TILED2D_GENERAL")
+    os.environ["PFFFT_B200_TILED2D_GENERAL"] = "1"
+    try:
+        s = pf.Setup(Nc, 1, np.float64)
+    finally:
+        if old is None:
+            os.environ.pop("PFFFT_B200_TILED2D_GENERAL", None)
+        else:
+            os.environ["PFFFT_B200_TILED2D_GENERAL"] = old
+    try:
+        assert s.kernel.startswith("tiled2dg_"), s.kernel
+        x = uniform(np.random.default_rng(Nc), 2 * 2 * Nc, np.float64).reshape(2, 2 * Nc)
+        y = s.transform_batch(torch.from_numpy(x).cuda(), pf.PFFFT_FORWARD, True).cpu().numpy()
+        want = np.fft.fft(x[0].view(np.complex128))
+        assert np.abs(y[0].view(np.complex128) - want).max() <= 1e-12 * np.abs(want).max()
+    finally:
+        s.close()
