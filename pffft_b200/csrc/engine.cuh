@@ -221,7 +221,7 @@ int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
     int cur = 0, stride = 1;
     for (int f = 0; f < s->nfac; ++f) {
       const int r = s->fac[f];
-      k_glob_stage<T, SIGN><<<grid_for(total / r), thr, 0, st>>>(s->d_scratch[cur], s->d_scratch[cur ^ 1], p.batch, s->Nc, r, stride, stage_magic(stride), s->tw);
+      k_glob_stage<T, SIGN><<<grid_for(total / r), thr, 0, st>>>(s->d_scratch[cur], s->d_scratch[cur ^ 1], p.batch, s->Nc, r, stride, s->tw);
       count_launch();
       cur ^= 1; stride *= r;
     }

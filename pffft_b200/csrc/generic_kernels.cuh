@@ -132,10 +132,10 @@ PF_HD int div_by_stage(int b, int s, unsigned magic) {
 }
 inline unsigned stage_magic(int s) { return s == 1 ? 0u : (unsigned)(0xFFFFFFFFull / (unsigned)s + 1ull); }
 
+// core of one butterfly given sp = s * (b / s)
 template <int R, int SIGN, typename T>
-PF_HD void stockham_bfly(const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, unsigned magic, const cpx<T>* tw) {
+PF_HD void stockham_bfly_sp(const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, int sp, const cpx<T>* tw) {
   const int m = Nc / R;
-  const int sp = div_by_stage(b, s, magic) * s;     // s * p
   const int q = b - sp;
   cpx<T> a[R];
 #pragma unroll
@@ -151,13 +151,20 @@ PF_HD void stockham_bfly(const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, unsig
     for (int k = 1; k < R; ++k) y[o + s * k] = cmul_dir<SIGN>(a[k], tw[sp * k]);
   }
 }
+template <int R, int SIGN, typename T>
+PF_HD void stockham_bfly(const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, unsigned magic, const cpx<T>* tw) {
+  stockham_bfly_sp<R, SIGN>(x, y, b, Nc, s, div_by_stage(b, s, magic) * s, tw);   // shared-memory sizes: b*s < 2^32 holds
+}
+// global-memory stages (Nc up to 2^26): the 32-bit reciprocal is NOT exact there once s has a factor 3 or 5
+// (e.g. Nc = 589824, s = 196608, b = 196607), so these take the exact quotient
 template <int SIGN, typename T>
-PF_HD void stockham_any(int r, const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, unsigned magic, const cpx<T>* tw) {
+PF_HD void stockham_any(int r, const cpx<T>* x, cpx<T>* y, int b, int Nc, int s, const cpx<T>* tw) {
+  const int sp = (b / s) * s;
   switch (r) {
-    case 2: stockham_bfly<2, SIGN>(x, y, b, Nc, s, magic, tw); break;
-    case 3: stockham_bfly<3, SIGN>(x, y, b, Nc, s, magic, tw); break;
-    case 4: stockham_bfly<4, SIGN>(x, y, b, Nc, s, magic, tw); break;
-    default: stockham_bfly<5, SIGN>(x, y, b, Nc, s, magic, tw); break;
+    case 2: stockham_bfly_sp<2, SIGN>(x, y, b, Nc, s, sp, tw); break;
+    case 3: stockham_bfly_sp<3, SIGN>(x, y, b, Nc, s, sp, tw); break;
+    case 4: stockham_bfly_sp<4, SIGN>(x, y, b, Nc, s, sp, tw); break;
+    default: stockham_bfly_sp<5, SIGN>(x, y, b, Nc, s, sp, tw); break;
   }
 }
 // one whole stage of one transform for the threads li, li+tpt, ... (radix dispatch hoisted out of the loop)
@@ -256,13 +263,13 @@ __global__ void __launch_bounds__(256) k_glob_load(const XformParams<T> p, cpx<T
 }
 template <typename T, int SIGN>
 __global__ void __launch_bounds__(256) k_glob_stage(const cpx<T>* __restrict__ src, cpx<T>* __restrict__ dst,
-                                                    long long batch, int Nc, int r, int s, unsigned magic, const cpx<T>* __restrict__ tw) {
+                                                    long long batch, int Nc, int r, int s, const cpx<T>* __restrict__ tw) {
   const int m = Nc / r;
   const long long total = batch * m;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long t = idx / m;
     const int b = (int)(idx - t * m);
-    stockham_any<SIGN, T>(r, src + t * Nc, dst + t * Nc, b, Nc, s, magic, tw);
+    stockham_any<SIGN, T>(r, src + t * Nc, dst + t * Nc, b, Nc, s, tw);
   }
 }
 template <typename T, int SM>

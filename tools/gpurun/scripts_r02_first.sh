@@ -18,3 +18,4 @@ echo "== double: split (default) vs tiled"; $T 16384:1:0:1:d 32768:1:0:1:d 65536
 PFFFT_B200_TILED2D_GENERAL=1 $T 16384:1:0:1:d 32768:1:0:1:d 65536:1:0:1:d
 echo "== ncu: tiled passes at 65536"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_t2d -s 4 -c 2 -f -o gpurun_out/r02_t2d_65536 python tools/prof_case.py 65536 1 10 0 > gpurun_out/ncu_t2d.log 2>&1; tail -n 1 gpurun_out/ncu_t2d.log
+echo "== large N (global path, exact division fix)"; timeout 900 python -m pytest tests/test_large_n_gpu.py -x -q 2>&1 | tail -n 8
