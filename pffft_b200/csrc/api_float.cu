@@ -18,8 +18,8 @@ template <int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
 static int launch_ldg(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
   auto kern = k_c1024_ldg<SIGN, WARPS, MINB, ZIN, ZOUT>;
   const size_t smem = (1024 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
-  static thread_local bool attr = false;
-  if (!attr) { PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static PerDeviceInt attr;
+  { const int rc = ensure_dyn_smem(attr, s->device, kern, smem); if (rc) return rc; }
   long long ctas = (batch + WARPS - 1) / WARPS;
   const long long cap = (long long)s->sm_count * MINB;
   if (ctas > cap) ctas = cap;
@@ -32,8 +32,8 @@ template <int SIGN, int WARPS, int MINB, bool ZOUT>
 static int launch_bulk(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
   auto kern = k_c1024_bulk<SIGN, WARPS, MINB, ZOUT>;
   const size_t smem = (1024 + (size_t)WARPS * 2 * kW1024Tile) * sizeof(cf) + (size_t)WARPS * 2 * sizeof(uint64_t);
-  static thread_local bool attr = false;
-  if (!attr) { PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static PerDeviceInt attr;
+  { const int rc = ensure_dyn_smem(attr, s->device, kern, smem); if (rc) return rc; }
   long long ctas = (batch + WARPS - 1) / WARPS;
   const long long cap = (long long)s->sm_count * MINB;
   if (ctas > cap) ctas = cap;
@@ -146,6 +146,7 @@ static bool float_split_for(int N, int transform, int* R, int* N2) {
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N)) return 0;
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
     { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
@@ -153,6 +154,7 @@ template <> struct FastHooks<float> {
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N)) return;
     if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
       for (int k2 = 0; k2 < 32; ++k2)
         for (int n1 = 0; n1 < 32; ++n1) {
@@ -191,6 +193,7 @@ template <> struct FastHooks<float> {
     CtaOnlyHooks<float>::fill_extra_table(N, transform, dst);
   }
   static bool plan(Setup<float>* s) {
+    if (ts_wanted(s->Nc)) return ts_plan<float>(s);
     if (is_warp1024(s->N, s->transform)) {
       int v = V_LDG_4x4;
       if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
@@ -238,6 +241,7 @@ template <> struct FastHooks<float> {
   }
   static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
                  const XformOpts& o) {
+    if (s->fast_variant == 500) return ts_dispatch<float>(s, in, out, batch, direction, ordered, st, o);
     if (s->fast_variant < 100) {                            // warp-per-transform N=1024 complex: contiguous batches only
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
       if (!plain) return -1;

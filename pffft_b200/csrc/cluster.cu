@@ -18,13 +18,19 @@ template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
   static constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kByThreads ? kBySmem : kByThreads);
   static auto kernel() { return k_cluster_fft<float, C, CL, Q, SIGN, MODE, MINB>; }
 
+  static int configure() {                                          // function attributes: once per device
+    PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    if (CL > 8) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    return 0;
+  }
   static int prepare(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, cudaStream_t st) {
-    static thread_local bool configured = false;
-    if (!configured) {
-      PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-      if (CL > 8) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = true;
-    }
+    static PerDeviceInt configured;
+    int cfg_rc = 0;
+    configured.get(current_device(), [&]() -> int {
+      cfg_rc = configure();
+      return cfg_rc ? -1 : 1;
+    });
+    if (cfg_rc) return cfg_rc;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     *cfg = cudaLaunchConfig_t{};
@@ -37,14 +43,14 @@ template <int C, int CL, int Q, int SIGN, int MODE> struct ClusterLaunch {
   }
   // co-resident clusters of this kernel on the current device (0: the device cannot schedule the cluster shape)
   static int max_active() {
-    static thread_local int cached = -1;
-    if (cached >= 0) return cached;
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    if (prepare(&cfg, attr, 1, nullptr)) { cached = 0; return 0; }
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kernel(), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    cached = n;
-    return n;
+    static PerDeviceInt cached;
+    return cached.get(current_device(), [&]() -> int {
+      cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+      if (prepare(&cfg, attr, 1, nullptr)) return 0;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel(), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      return n;
+    });
   }
   static int launch(const cf* src, cf* dst, long long batch, const cf* tw1, const cf* tw2, const cf* twP, cudaStream_t st) {
     const int cap = max_active();

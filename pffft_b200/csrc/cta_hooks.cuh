@@ -39,12 +39,16 @@ int launch_cta_v(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
   // second buffer: TMA stage, gather staging of z-domain / backward-real inputs, or the z image of a C=16 real forward
   constexpr bool kSecond = STAGED || LM == L_C_Z || LM == L_R_Z || (SM == S_R_Z && C == 16);
   const size_t smem = (size_t)K2<C>::NC * sizeof(cpx<T>) * (kSecond ? 2 : 1) + (STAGED ? 16 : 0);
-  static thread_local int per_sm = 0;
-  if (per_sm == 0) {
-    if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * C, smem);
-    if (per_sm < 1) per_sm = 1;
-  }
+  static PerDeviceInt cache;                                   // resident CTAs per SM on each device (attribute set first)
+  int attr_rc = 0;
+  const int per_sm = cache.get(s->device, [&]() -> int {
+    if (smem > 48 * 1024) attr_rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr_rc) return -1;
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 16 * C, smem);
+    return n < 1 ? 1 : n;
+  });
+  if (attr_rc) { set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", (cudaError_t)attr_rc); return attr_rc; }
   long long ctas = p.batch;
   const long long cap = (long long)s->sm_count * per_sm;
   if (ctas > cap) ctas = cap;
@@ -155,6 +159,43 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 // (A decimation-in-frequency order -- dense radix-R pre-pass, then rows whose STORES carry the element stride R -- was
 //  built and measured: 0.25 / 0.22 / 0.17 of HBM peak at 16384 / 32768 / 65536 against 0.38 / 0.34 / 0.24 for this
 //  order.  Partial-sector stores cost more than the strided loads they replace; stores stay dense.)
+
+// ---- tiled Stockham pipeline (ts_kernels.cuh / ts.cu): complex cores that factor into 2-4 radices 16*A, one persistent
+// kernel, intermediates resident in L2.  PFFFT_B200_TS=0 never, =1 every factorisable core >= PFFFT_B200_TS_MIN (default
+// 8192); unset: the measured default range.
+inline bool ts_wanted(int Nc) {
+  int lo = 131072;                                                // default: everything the single-launch plans do not cover
+  if (const char* e = getenv("PFFFT_B200_TS")) {
+    if (atoi(e) == 0) return false;
+    lo = 8192;
+    if (const char* m = getenv("PFFFT_B200_TS_MIN")) lo = atoi(m);
+  }
+  if (Nc < lo) return false;
+  int P = 0, A[4];
+  return ts_factorize(Nc, &P, A);
+}
+// LoadMode / StoreMode of a dense call
+inline void ts_modes(int transform, int direction, int ordered, int* lm, int* sm) {
+  const bool fwd = direction == DIR_FORWARD;
+  if (transform == XF_COMPLEX) { *lm = (fwd || ordered) ? L_C_ORD : L_C_Z; *sm = (fwd && !ordered) ? S_C_Z : S_C_ORD; }
+  else if (fwd) { *lm = L_R_TIME; *sm = ordered ? S_R_ORD : S_R_Z; }
+  else { *lm = ordered ? L_R_ORD : L_R_Z; *sm = S_R_TIME; }
+}
+template <typename T> inline bool ts_plan(Setup<T>* s) {
+  s->ts = ts_create(s->N, s->Nc, sizeof(T) == 8, s->device, s->sm_count);
+  if (!s->ts) return false;
+  s->fast_variant = 500;
+  s->kernel_name = ts_name(s->ts);
+  return true;
+}
+template <typename T> inline int ts_dispatch(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered,
+                                             cudaStream_t st, const XformOpts& o) {
+  const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+  if (!plain || !vec_aligned<T>(in) || !vec_aligned<T>(out)) return -1;   // generic path
+  int lm = 0, sm = 0;
+  ts_modes(s->transform, direction, ordered, &lm, &sm);
+  return ts_run<T>(s->ts, in, out, batch, direction == DIR_FORWARD ? -1 : +1, lm, sm, s->tw, s->twr, st);
+}
 
 // ---- tiled two-dimensional plan (tiled2d_kernels.cuh, instantiated in tiled2d.cu): float complex cores 16384 / 32768 / 65536
 // as N1 x N2 with 128-byte runs in both passes.  Measured (profiles/r01b_large_n.md): 32768: 0.42, 65536: 0.41-0.44 of HBM
@@ -268,12 +309,16 @@ int launch_split_fused_v(Setup<T>* s, const cpx<T>* src, cpx<T>* dst, long long 
   constexpr int MINB = (cta_tpsm<T>() / (16 * C)) < 2 ? 1 : 2;
   auto kern = k_cta_split<T, C, R, SIGN, MINB>;
   const size_t smem = (size_t)(R + 1) * K2<C>::NC * sizeof(cpx<T>);
-  static thread_local int per_sm = 0;
-  if (per_sm == 0) {
-    if (smem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * C, smem);
-    if (per_sm < 1) per_sm = 1;
-  }
+  static PerDeviceInt cache;                                   // resident CTAs per SM on each device (attribute set first)
+  int attr_rc = 0;
+  const int per_sm = cache.get(s->device, [&]() -> int {
+    if (smem > 48 * 1024) attr_rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr_rc) return -1;
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 16 * C, smem);
+    return n < 1 ? 1 : n;
+  });
+  if (attr_rc) { set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", (cudaError_t)attr_rc); return attr_rc; }
   long long ctas = batch;
   const long long cap = (long long)s->sm_count * per_sm;
   if (ctas > cap) ctas = cap;
@@ -384,15 +429,18 @@ template <typename T> struct CtaOnlyHooks {
   }
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
+    if (ts_wanted(Nc)) return 0;
     const int n2 = rows_size(N, transform);
     return n2 ? split_table_cpx(Nc, n2) : cta_table_cpx(Nc);
   }
   static void fill_extra_table(int N, int transform, T* dst) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
+    if (ts_wanted(Nc)) return;
     const int n2 = rows_size(N, transform);
     if (n2) split_fill_tables<T>(Nc, n2, dst); else cta_fill_tables<T>(Nc, dst);
   }
   static bool plan(Setup<T>* s) {
+    if (ts_wanted(s->Nc)) return ts_plan<T>(s);
     int R = 0, N2 = 0;
     const bool fused = !cta_C_for(s->Nc) && !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_choose_fused<T>(s->Nc, &R, &N2);
     if (!cta_C_for(s->Nc) && (fused || split_choose(s->Nc, is_cta_row_size, &R, &N2))) {
@@ -417,6 +465,7 @@ template <typename T> struct CtaOnlyHooks {
     return true;
   }
   static int run(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered, cudaStream_t st, const XformOpts& o) {
+    if (s->fast_variant == 500) return ts_dispatch<T>(s, in, out, batch, direction, ordered, st, o);
     const XformParams<T> p = make_params(s, in, out, batch, o);
     if (s->fast_variant >= 300)
       return run_split<T>(s, split_rows_cta<T, -1>, split_rows_cta<T, +1>, p, direction, ordered, st);

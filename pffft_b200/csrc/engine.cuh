@@ -15,6 +15,7 @@
 #include <string.h>
 #include "generic_kernels.cuh"
 #include "plan.h"
+#include "ts.h"
 
 namespace pf {
 
@@ -31,6 +32,35 @@ bool zero_copy_enabled();
     cudaError_t _e = (call);                                    \
     if (_e != cudaSuccess) { ::pf::set_error(#call, _e); return (int)_e; } \
   } while (0)
+
+// One cached int per CUDA device for ONE kernel instantiation.  cudaFuncSetAttribute / occupancy results are per device and
+// process-wide (not per thread), so the cache is a plain function-local static indexed by the device ordinal; racing
+// first users compute the same value.  Values are stored +1 (0 = not computed on that device yet).
+struct PerDeviceInt {
+  enum { kMaxDevices = 64 };
+  std::atomic<int> v[kMaxDevices];
+  // compute() -> value >= 0, or < 0 for "failed, do not cache" (returned as is)
+  template <typename F> int get(int dev, F&& compute) {
+    if (dev < 0 || dev >= kMaxDevices) return compute();
+    const int c = v[dev].load(std::memory_order_acquire);
+    if (c) return c - 1;
+    const int r = compute();
+    if (r >= 0) v[dev].store(r + 1, std::memory_order_release);
+    return r;
+  }
+};
+inline int current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+// opt a kernel in to `smem` bytes of dynamic shared memory once per device (never lowered afterwards: callers pass the
+// largest size the instantiation can need)
+template <typename K> int ensure_dyn_smem(PerDeviceInt& flag, int dev, K kern, size_t smem) {
+  int rc = 0;
+  flag.get(dev, [&]() -> int {
+    if (smem > 48 * 1024) rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return rc ? -1 : 1;
+  });
+  if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", (cudaError_t)rc);
+  return rc;
+}
 
 enum KernelKind { KK_SMEM = 0, KK_GLOBAL = 1, KK_FAST = 2, KK_SPLIT = 3 };
 
@@ -51,6 +81,7 @@ struct Slot {                  // one lane of the host-pointer pipeline
 template <typename T> struct Setup {
   int N = 0, transform = 0, Nc = 0;
   int device = 0, sm_count = 0;
+  size_t smem_optin = 0;                  // device limit of dynamic shared memory per CTA
   int nfac = 0;
   int fac[PF_MAX_FACTORS];
   // device tables: [tw: Nc cpx][twr: N/2 cpx (real only)][fast-kernel tables]
@@ -62,6 +93,8 @@ template <typename T> struct Setup {
   cudaStream_t stream = nullptr;          // device-pointer calls are enqueued here (0 = legacy default stream)
   // kernel choice
   int kind = KK_SMEM;
+  int generic_kind = KK_SMEM;             // KK_SMEM / KK_GLOBAL: the always-available path behind a tuned plan's -1
+  TsPlanHost* ts = nullptr;               // tiled Stockham pipeline (large cores; ts.cu), owned by the plan
   int fast_variant = 0;
   int split_R = 0, split_N2 = 0;          // Nc = split_R x split_N2 two-level plans (rows on a tuned kernel + radix-R combine)
   bool split_fused = false;               // ... small enough for ONE kernel (rows parked in shared memory): one HBM round trip
@@ -114,7 +147,7 @@ S* engine_new_setup(int N, int transform) {
 
   S* s = new S();
   s->N = N; s->transform = transform; s->Nc = (transform == XF_REAL) ? N / 2 : N;
-  s->device = dev; s->sm_count = prop.multiProcessorCount;
+  s->device = dev; s->sm_count = prop.multiProcessorCount; s->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   std::vector<int> f = pfplan::factorize(s->Nc);
   s->nfac = (int)f.size();
   for (int i = 0; i < s->nfac; ++i) s->fac[i] = f[i];
@@ -152,6 +185,7 @@ S* engine_new_setup(int N, int transform) {
     s->kind = KK_GLOBAL;
     s->kernel_name = "global_stockham";
   }
+  s->generic_kind = s->kind;
   if (Hooks::plan(s)) s->kind = KK_FAST;
 
   // one transform's worth of staging so single host-pointer calls never allocate (README.md:269-271 of the reference)
@@ -164,7 +198,7 @@ S* engine_new_setup(int N, int transform) {
     ok = cudaMalloc(&s->slot[i].d_in, s->slot_elems * sizeof(T)) == cudaSuccess &&
          cudaMalloc(&s->slot[i].d_out, s->slot_elems * sizeof(T)) == cudaSuccess;
   }
-  if (ok && s->kind == KK_GLOBAL) {
+  if (ok && s->kind == KK_GLOBAL) {                                  // (tuned large-N plans allocate it on first fallback use)
     s->scratch_cpx = (size_t)s->Nc;
     ok = cudaMalloc((void**)&s->d_scratch[0], s->scratch_cpx * cbytes) == cudaSuccess &&
          cudaMalloc((void**)&s->d_scratch[1], s->scratch_cpx * cbytes) == cudaSuccess &&
@@ -187,6 +221,7 @@ template <typename T, typename S> void engine_destroy_setup(S* s) {
   if (s->scratch_done) cudaEventDestroy(s->scratch_done);
   if (s->d_tables) cudaFree(s->d_tables);
   if (s->d_aux_tables) cudaFree(s->d_aux_tables);
+  if (s->ts) ts_destroy(s->ts);
   if (cur != s->device) cudaSetDevice(cur);
   delete s;
 }
@@ -209,7 +244,7 @@ template <typename T> int scratch_acquire(Setup<T>* s, size_t need, cudaStream_t
 // ---------------------------------------------------------------- launches (device pointers)
 template <typename T, int LM, int SM, int SIGN>
 int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
-  if (s->kind == KK_GLOBAL) {
+  if (s->generic_kind == KK_GLOBAL) {
     // the ping-pong scratch is shared by every stream using this plan: serialise its users
     std::lock_guard<std::mutex> lock(s->scratch_mu);
     { const int rc = scratch_acquire(s, (size_t)p.batch * s->Nc, st); if (rc) return rc; }
@@ -233,11 +268,9 @@ int launch_generic(Setup<T>* s, const XformParams<T>& p, cudaStream_t st) {
   }
   // shared-memory kernel
   auto kern = k_smem_fft<T, LM, SM, SIGN>;
-  static thread_local size_t attr_set_for = 0;   // opt-in dynamic shared memory once per instantiation and size
-  if (s->smem_bytes > 48 * 1024 && attr_set_for < s->smem_bytes) {
-    PF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    attr_set_for = s->smem_bytes;
-  }
+  // plans of different sizes share this instantiation: opt in once per device to the device maximum, never lower it
+  static PerDeviceInt attr;
+  { const int rc = ensure_dyn_smem(attr, s->device, kern, s->smem_optin); if (rc) return rc; }
   constexpr int combo = (LM * 5 + SM) * 2 + (SIGN > 0 ? 1 : 0);
   int per_sm = s->occ_cache[combo];
   if (per_sm == 0) {

@@ -91,12 +91,22 @@ PF_HD cpx<T> load_core(const T* base, int i, int N, int Nc, const cpx<T>* twr, l
 }
 
 // store element k of the transform's OUTPUT given the complex core's natural-order result z[0..Nc)
-template <int SM, typename T>
+// CG: z was written by other SMs during this launch (ring buffers of the tiled Stockham pipeline): read it through L2 only
+template <bool CG, typename T> PF_HD cpx<T> core_get(const cpx<T>* p) {
+#ifdef __CUDA_ARCH__
+  if constexpr (CG) {
+    if constexpr (sizeof(T) == 4) { const float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
+    else { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
+  }
+#endif
+  return *p;
+}
+template <int SM, typename T, bool CG = false>
 PF_HD void store_core(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<T>* twr, int out_count, bool vec_ok) {
-  if (SM == S_C_ORD) { spec_put<false, false>(base, k, N, z[k]); return; }
-  if (SM == S_C_Z)   { spec_put<true, false>(base, k, N, z[k]); return; }
+  if (SM == S_C_ORD) { spec_put<false, false>(base, k, N, core_get<CG>(z + k)); return; }
+  if (SM == S_C_Z)   { spec_put<true, false>(base, k, N, core_get<CG>(z + k)); return; }
   if (SM == S_R_TIME) {
-    const cpx<T> v = z[k];
+    const cpx<T> v = core_get<CG>(z + k);
     const int e = 2 * k;
     if (vec_ok && e + 1 < out_count) { reinterpret_cast<cpx<T>*>(base)[k] = v; return; }
     if (e < out_count) base[e] = v.x;
@@ -106,12 +116,12 @@ PF_HD void store_core(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<
   // forward real: X[k] = (Z[k] + conj Z[M-k])/2 - (i/2) W^k (Z[k] - conj Z[M-k])
   constexpr bool Z = (SM == S_R_Z);
   if (k == 0) {
-    const cpx<T> z0 = z[0];
+    const cpx<T> z0 = core_get<CG>(z);
     spec_put<Z, true>(base, 0, N, mk<T>(z0.x + z0.y, z0.x - z0.y));
     return;
   }
-  const cpx<T> a = z[k];
-  const cpx<T> b = conj(z[Nc - k]);
+  const cpx<T> a = core_get<CG>(z + k);
+  const cpx<T> b = conj(core_get<CG>(z + (Nc - k)));
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, twr[k]);
   spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));

@@ -16,13 +16,10 @@ template <int A1, int A2, int SIGN> struct T2DLaunch {
   static int run(const cf* x, cf* S, cf* X, long long batch, const cf* tables, int sm_count, cudaStream_t st) {
     auto ka = k_t2d_A<float, A1, A2, SIGN, MINB_A>;
     auto kc = k_t2d_C<float, A1, A2, SIGN, MINB_C>;
-    static thread_local int per_sm_a = 0, per_sm_c = 0;
-    if (per_sm_a == 0) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ka, G::TA, kSmemA);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, kc, G::TC, kSmemC);
-      if (per_sm_a < 1) per_sm_a = 1;
-      if (per_sm_c < 1) per_sm_c = 1;
-    }
+    static PerDeviceInt occ_a, occ_c;
+    const int dev = current_device();
+    const int per_sm_a = occ_a.get(dev, [&]() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka, G::TA, kSmemA); return n < 1 ? 1 : n; });
+    const int per_sm_c = occ_c.get(dev, [&]() { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kc, G::TC, kSmemC); return n < 1 ? 1 : n; });
     const cf* twA = tables;
     const cf* twC = twA + G::N2;
     const cf* tw2d = twC + G::N1;
@@ -48,13 +45,19 @@ template <int A1, int A2, int CL, int SIGN> struct T2DClusterLaunch {
   static constexpr int kByRegs = 768 / K::NT;                       // 80 registers per thread
   static constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kByRegs ? kBySmem : kByRegs);
   static auto kernel() { return k_t2d_cluster<float, A1, A2, CL, SIGN, MINB>; }
+  static int configure() {                                          // function attributes: once per device
+    PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    if (CL > 8) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    return 0;
+  }
   static int prepare(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, cudaStream_t st) {
-    static thread_local bool configured = false;
-    if (!configured) {
-      if (kSmem > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-      if (CL > 8) PF_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = true;
-    }
+    static PerDeviceInt configured;
+    int cfg_rc = 0;
+    configured.get(current_device(), [&]() -> int {
+      cfg_rc = configure();
+      return cfg_rc ? -1 : 1;
+    });
+    if (cfg_rc) return cfg_rc;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     *cfg = cudaLaunchConfig_t{};
@@ -66,14 +69,14 @@ template <int A1, int A2, int CL, int SIGN> struct T2DClusterLaunch {
     return 0;
   }
   static int max_active() {
-    static thread_local int cached = -1;
-    if (cached >= 0) return cached;
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    if (prepare(&cfg, attr, 1, nullptr)) { cached = 0; return 0; }
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kernel(), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    cached = n;
-    return n;
+    static PerDeviceInt cached;
+    return cached.get(current_device(), [&]() -> int {
+      cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+      if (prepare(&cfg, attr, 1, nullptr)) return 0;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel(), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      return n;
+    });
   }
   static int run(const cf* x, cf* X, long long batch, const cf* tables, cudaStream_t st) {
     const int cap = max_active();

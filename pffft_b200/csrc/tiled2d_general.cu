@@ -18,15 +18,18 @@ template <typename T, int A1, int A2, int SIGN> struct T2DGLaunch {
   static int run(const cx* x, cx* S, cx* X, long long batch, const cx* tables, int sm_count, cudaStream_t st) {
     auto ka = k_t2dg_A<T, A1, A2, SIGN, MINB>;
     auto kc = k_t2dg_C<T, A1, A2, SIGN, MINB>;
-    static thread_local int per_sm_a = 0, per_sm_c = 0;
-    if (per_sm_a == 0) {
-      if (kSmemA > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA));
-      if (kSmemC > 48 * 1024) PF_CUDA_OK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemC));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ka, 256, kSmemA);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, kc, 256, kSmemC);
-      if (per_sm_a < 1) per_sm_a = 1;
-      if (per_sm_c < 1) per_sm_c = 1;
-    }
+    static PerDeviceInt occ_a, occ_c;
+    const int dev = current_device();
+    int arc = 0;
+    const int per_sm_a = occ_a.get(dev, [&]() -> int {
+      if (kSmemA > 48 * 1024) arc = (int)cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemA);
+      if (arc) return -1;
+      int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka, 256, kSmemA); return n < 1 ? 1 : n; });
+    const int per_sm_c = occ_c.get(dev, [&]() -> int {
+      if (kSmemC > 48 * 1024) arc = (int)cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemC);
+      if (arc) return -1;
+      int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kc, 256, kSmemC); return n < 1 ? 1 : n; });
+    if (arc) { set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", (cudaError_t)arc); return arc; }
     const cx* twA = tables;
     const cx* twC = twA + G::N2;
     const cx* tw2d = twC + G::N1;

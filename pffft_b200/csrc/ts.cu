@@ -1,0 +1,141 @@
+// ts.cu -- host side of the tiled Stockham pipeline (ts_kernels.cuh): factorisation of the core length into radices 16*A,
+// per-plan device resources (radix tables, L2-resident ring buffers, dependency counters) and the launcher.
+// Own translation unit so the C-ABI units stay small; float and double.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include "internal_api.h"
+#include "ts.h"
+#include "ts_kernels.cuh"
+#include "ts_plan.h"
+
+namespace pf {
+
+struct TsPlanHost {
+  int Nc = 0, N = 0, device = 0, sm_count = 0;
+  bool dbl = false;
+  int P = 0, A[4] = {0, 0, 0, 0}, tw_off[4] = {0, 0, 0, 0};
+  void* d_twR = nullptr;
+  void* d_ring[kTsMaxRings] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int nrings = 0;
+  unsigned* d_counters = nullptr;
+  size_t counter_bytes = 0;
+  int grid = 0, lag = 0, ring_slots = 1;
+  size_t smem = 0;
+  std::mutex mu;                       // rings and counters serve one launch at a time
+  cudaEvent_t done = nullptr;
+  char name[48] = {0};
+};
+
+template <typename T> struct TsKernels {
+  static constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
+  static auto fwd() { return k_ts_pipeline<T, -1, MINB>; }
+  static auto bwd() { return k_ts_pipeline<T, +1, MINB>; }
+};
+
+template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
+  static PerDeviceInt attr_f, attr_b;
+  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), 16 * 256 * sizeof(cpx<T>)); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), 16 * 256 * sizeof(cpx<T>)); if (rc) return rc; }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (n < 1) n = 1;
+  h->grid = n * h->sm_count;
+  return 0;
+}
+
+template <typename T> static bool ts_fill_radix_tables(TsPlanHost* h) {
+  const std::vector<T> host = ts_radix_tables<T>(h->P, h->A, h->tw_off);
+  if (cudaMalloc(&h->d_twR, host.size() * sizeof(T)) != cudaSuccess) return false;
+  return cudaMemcpy(h->d_twR, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+void ts_destroy(TsPlanHost* h) {
+  if (!h) return;
+  if (h->done) { cudaEventSynchronize(h->done); cudaEventDestroy(h->done); }
+  if (h->d_twR) cudaFree(h->d_twR);
+  for (int i = 0; i < kTsMaxRings; ++i) if (h->d_ring[i]) cudaFree(h->d_ring[i]);
+  if (h->d_counters) cudaFree(h->d_counters);
+  delete h;
+}
+
+TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
+  int P = 0, A[4];
+  if (!ts_factorize(Nc, &P, A)) return nullptr;
+  TsPlanHost* h = new TsPlanHost();
+  h->N = N; h->Nc = Nc; h->dbl = dbl; h->device = device; h->sm_count = sm_count; h->P = P;
+  memcpy(h->A, A, sizeof(int) * P);
+  const size_t csz = dbl ? sizeof(cpx<double>) : sizeof(cpx<float>);
+  int amax = 0; long long group = 0;
+  for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
+  (void)amax;
+  h->smem = (size_t)16 * 256 * csz;                             // one work item = up to 16 columns x 256 points (or G tiles of 16 x 16A)
+  bool ok = (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
+  ok = ok && (dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h));
+  // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
+  // so its input is complete (no spinning) and still in L2; rings hold 2*lag+1 transforms so a slot's previous occupant
+  // has long been consumed when it is overwritten.  Rings are capped at ~40 MB (they must stay L2 resident to pay).
+  h->nrings = P;                                                  // P-1 between the passes + one for a pre-/post-stage
+  const size_t tb = (size_t)Nc * csz;
+  long long lag = (3LL * h->grid / 2 + group - 1) / group;
+  if (lag < 1) lag = 1;
+  const size_t budget = (size_t)40 << 20;
+  if ((size_t)h->nrings * (size_t)(2 * lag + 1) * tb > budget) {
+    const long long fit = ((long long)(budget / ((size_t)h->nrings * tb)) - 1) / 2;
+    if (fit >= 1) lag = fit;
+    else lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
+  }
+  if (const char* e = getenv("PFFFT_B200_TS_LAG")) { const long long v = atoll(e); if (v >= 0 && v < 4096) lag = v; }
+  h->lag = (int)lag;
+  h->ring_slots = lag > 0 ? 2 * (int)lag + 1 : 1;
+  for (int i = 0; ok && i < h->nrings; ++i) ok = cudaMalloc(&h->d_ring[i], (size_t)h->ring_slots * tb) == cudaSuccess;
+  h->counter_bytes = sizeof(unsigned) * ((size_t)kTsCounterBase + (size_t)kTsMaxStages * h->ring_slots);
+  ok = ok && cudaMalloc((void**)&h->d_counters, h->counter_bytes) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { set_error("tiled Stockham plan: device resources", cudaGetLastError()); ts_destroy(h); return nullptr; }
+  int n = snprintf(h->name, sizeof(h->name), "ts");
+  for (int i = 0; i < P; ++i) n += snprintf(h->name + n, sizeof(h->name) - n, "%c%d", i ? 'x' : '_', ts_radix(A[i]));
+  return h;
+}
+const char* ts_name(const TsPlanHost* h) { return h->name; }
+
+template <typename T>
+int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm, int sm,
+           const cpx<T>* tw, const cpx<T>* twr, cudaStream_t st) {
+  if (batch <= 0) return 0;
+  TsParams<T> P;
+  memset(&P, 0, sizeof(P));
+  P.tw = tw; P.twr = twr; P.twR = reinterpret_cast<const cpx<T>*>(h->d_twR);
+  for (int i = 0; i < kTsMaxRings; ++i) P.ring[i] = reinterpret_cast<cpx<T>*>(h->d_ring[i]);
+  P.counters = h->d_counters;
+  P.N = h->N; P.Nc = h->Nc; P.lag = h->lag; P.ring_slots = h->ring_slots;
+  ts_build_stages<T>(P, h->Nc, h->P, h->A, h->tw_off, lm, sm);
+  const int ns = P.nstages;
+  const long long group = P.group_items;
+
+  std::lock_guard<std::mutex> lock(h->mu);
+  PF_CUDA_OK(cudaStreamWaitEvent(st, h->done, 0));
+  auto kern = sign < 0 ? TsKernels<T>::fwd() : TsKernels<T>::bwd();
+  // tickets are 32-bit: very long batches go in several launches
+  const long long max_groups = (long long)((0xFFFFFFFFull - 4ull * (unsigned long long)h->grid) / (unsigned long long)group);
+  const long long max_batch = max_groups - (long long)(ns - 1) * h->lag;
+  for (long long b0 = 0; b0 < batch; b0 += max_batch) {
+    const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
+    P.in = in + b0 * 2LL * h->Nc; P.out = out + b0 * 2LL * h->Nc; P.batch = nb;
+    const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
+    P.total_items = (unsigned)total;
+    PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
+    const long long g = total < h->grid ? total : h->grid;
+    kern<<<(int)g, kTsThreads, h->smem, st>>>(P);
+    count_launch();
+    PF_CUDA_OK(cudaGetLastError());
+  }
+  PF_CUDA_OK(cudaEventRecord(h->done, st));
+  return 0;
+}
+template int ts_run<float>(TsPlanHost*, const float*, float*, long long, int, int, int, const cpx<float>*, const cpx<float>*, cudaStream_t);
+template int ts_run<double>(TsPlanHost*, const double*, double*, long long, int, int, int, const cpx<double>*, const cpx<double>*, cudaStream_t);
+
+}  // namespace pf

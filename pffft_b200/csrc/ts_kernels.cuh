@@ -1,0 +1,312 @@
+// ts_kernels.cuh -- LARGE complex cores (Nc = 8192 .. 2^26) as a PIPELINE of tiled Stockham passes whose intermediates
+// live in the 126 MB L2 of the B200 instead of HBM.
+//
+// Plan: Nc = R_1 * R_2 * ... * R_P, every R_i = 16*A_i with A_i from the register DFT library (1,2,3,4,5,6,8,9,10,12,15,16).
+// Pass i is one autosort (Stockham, decimation in frequency) stage of radix R_i over the whole vector:
+//        y[q + s*(R*p + k)] = W_Nc^{s p k} * sum_n x[b + n*m] W_R^{n k},     b = q + s*p,  m = Nc/R,  s = R_1*...*R_{i-1}
+// and a WORK ITEM is a tile of 16 neighbouring columns b = 16*tile .. 16*tile+15 with all R points of each:
+//   phase 1: thread (j = column, q): loads x[b + m*(q + A*i)], i < 16 -- for every n the 16 columns are ONE 128-byte run --
+//            radix-16 register FFT over i -> k_a, * W_R^{q k_a}, into the CTA's exchange tile;
+//   phase 2: radix-A register DFT over q -> k_b, k = k_a + 16 k_b, * W_Nc^{s p k}, stored in 128-byte runs:
+//            first pass (s = 1): y[R*b + k] -- lanes run along k_a, the tile's output is one contiguous 16*R block;
+//            later passes (16 | s): y[q + s*(R*p + k)] -- lanes run along the column, p is uniform over the tile.
+//   The output is in natural order after the last pass: no transposes, no bit reversal, every HBM/L2 access a full line.
+//
+// ONE persistent kernel runs all passes (plus an element-wise pre-/post-rotation stage for real transforms and z-domain
+// layouts).  Work items are handed out by an atomic ticket in the order
+//        group g:  [pass 1 of transform g] [pass 2 of transform g - L] [pass 3 of transform g - 2L] ...
+// so pass i+1 of a transform is scheduled ~1.5 grid-fulls of tiles after pass i finished writing it: its input is still in
+// L2.  The intermediates are RINGS of 2L+1 transforms that are overwritten in place, so their dirty lines are re-written
+// in L2 before they are ever evicted: HBM sees one read of x and one write of X per transform (the two-launch tiled plan of
+// round 1 moved 2x that and sat at 0.42-0.45 of the HBM roofline with both launches at ~0.85 of HBM speed).
+// Dependencies (per ring slot, cumulative counters): a tile of pass i+1 waits until all tiles of pass i of its transform
+// are stored (release/acquire on a global counter); a tile that writes a ring slot waits until the slot's previous
+// occupant has been consumed.  Every wait is on tickets handed out EARLIER, the grid is sized to be co-resident, so the
+// scheme cannot deadlock.  Ring data is read with ld.global.cg (L2 only): a stale L1 line of a recycled slot is impossible.
+// Transforms too large for L2 (> ~16 MB) run the same code with rings of 1-3 slots; the traffic then goes to HBM.
+//
+// Replaces, for these sizes, the cfftf1_ps/rfftf1_ps pass sweeps + finalize/preprocess + zreorder of the reference
+// (src/pffft_priv_impl.h:809-1048, :1195-1462, :1158-1193), whose passes stream the whole vector through the cache
+// hierarchy once per radix-4 factor.
+#pragma once
+#include "butterfly.cuh"
+#include "generic_kernels.cuh"
+#include "cta_kernels.cuh"   // brev4, ldtab
+
+namespace pf {
+
+enum TsKind { TS_FIRST = 0, TS_LATER = 1, TS_PRE = 2, TS_POST = 3, TS_SMALL = 4 };
+enum { kTsSmallFlag = 100 };   // plan encoding: A >= kTsSmallFlag means a closing radix-(A - 100) pass without the factor 16
+enum { kTsMaxStages = 6, kTsMaxRings = 5, kTsThreads = 256, kTsChunk = 4096, kTsCounterBase = 32 };
+
+struct TsStage {
+  int kind;      // TsKind
+  int A;         // FFT stages: radix R = 16*A
+  int mode;      // TS_PRE: LoadMode, TS_POST: StoreMode
+  int tiles;     // work items per transform
+  int src, dst;  // 0 = user input, 1 = user output, 2 + r = ring r
+  int m;         // FFT stages: Nc / R
+  int s;         // FFT stages: product of the earlier radices
+  int tw_off;    // FFT stages: offset of W_R^{q k_a} (R entries, [k_a*A + q]) inside twR
+};
+
+template <typename T> struct TsParams {
+  const T* in;                      // dense batch, 2*Nc scalars per transform (complex: Nc pairs; real: N = 2*Nc samples)
+  T* out;
+  cpx<T>* ring[kTsMaxRings];        // ring_slots * Nc complex words each
+  const cpx<T>* tw;                 // exp(-2 pi i k / Nc), k < Nc
+  const cpx<T>* twr;                // exp(-2 pi i k / N),  k < N/2  (real transforms)
+  const cpx<T>* twR;                // per-radix tables
+  unsigned* counters;               // [0] ticket; [kTsCounterBase + stage*ring_slots + slot] tiles done (cumulative)
+  long long batch;
+  int N, Nc;
+  int nstages, lag, ring_slots, group_items;
+  unsigned total_items;
+  TsStage st[kTsMaxStages];
+};
+
+// read that may observe data written by another SM during this launch: L2 only
+template <typename T> PF_HD cpx<T> ld_l2(const cpx<T>* p) {
+#ifdef __CUDA_ARCH__
+  if constexpr (sizeof(T) == 4) { const float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
+  else { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
+#else
+  return *p;
+#endif
+}
+
+// Radices with a small second factor A would leave most of the CTA idle in phase 1 (16*A threads hold a tile), so a work
+// item is G = 16/A neighbouring 16-column tiles (A <= 8; one tile for the larger A): 240-256 busy threads for every radix.
+template <int A> struct TsShape {
+  static constexpr int R = 16 * A;
+  static constexpr int G = A >= 9 ? 1 : 16 / A;              // tiles per work item
+  static constexpr int COLS = 16 * G;                        // columns per work item
+};
+PF_HD constexpr int ts_cols_for(int A) { return A >= 9 ? 16 : 16 * (16 / A); }
+
+// exchange-tile index of (k_a, q, column j): first pass -> phase 2 runs its lanes along k_a (XOR keeps both phases
+// conflict free); later passes -> both phases run their lanes along j
+template <int A, bool FIRST> PF_HD int ts_tile_idx(int ka, int q, int j) {
+  return FIRST ? ((q + A * j) * 16 + (ka ^ j)) : ((ka * A + q) * 16 + j);
+}
+
+// ---- phase 1 (both kinds): thread t -> column j = t & 15 of tile grp = (t >> 4) / A, sub-sequence q = (t >> 4) % A
+template <int A, bool FIRST, int SIGN, typename T>
+PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile) {
+  using S = TsShape<A>;
+  const int j = t & 15, qq = t >> 4, q = qq % A, grp = qq / A;
+  const int bg = b0 + 16 * grp;
+  if (grp >= S::G || bg >= m) return;
+  cpx<T> v[16];
+  const cpx<T>* c = src + bg + j + (long long)m * q;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
+  reg_fft<16, SIGN>(v);
+  cpx<T>* tl = tile + grp * (16 * S::R);
+  tl[ts_tile_idx<A, FIRST>(0, q, j)] = v[0];
+#pragma unroll
+  for (int ka = 1; ka < 16; ++ka) tl[ts_tile_idx<A, FIRST>(ka, q, j)] = cmul_dir<SIGN>(v[ka], ldtab(twR + ka * A + q));
+}
+// ---- phase 2, first pass (s = 1, p = b): y[R*b + k] = W_Nc^{b k} (...),  W^{b k} = W^{b k_a} * W^{16 b k_b}
+template <int A, int SIGN, typename T>
+PF_HD void ts_phase2_first(int t, int b0, int m, const cpx<T>* tw, const cpx<T>* tile, cpx<T>* dst /* transform base */) {
+  using S = TsShape<A>;
+  const int ka = t & 15, j = t >> 4;
+#pragma unroll 1
+  for (int grp = 0; grp < S::G; ++grp) {
+    const int b = b0 + 16 * grp + j;
+    if (b0 + 16 * grp >= m) break;
+    const cpx<T>* tl = tile + grp * (16 * S::R);
+    cpx<T> u[A];
+#pragma unroll
+    for (int q = 0; q < A; ++q) u[q] = tl[ts_tile_idx<A, true>(ka, q, j)];
+    dft_small<A, SIGN>(u);
+    const cpx<T> w1 = ldtab(tw + b * ka);
+    cpx<T>* o = dst + (long long)S::R * b + ka;
+    o[0] = cmul_dir<SIGN>(u[0], w1);
+#pragma unroll
+    for (int kb = 1; kb < A; ++kb) o[16 * kb] = cmul_dir<SIGN>(u[kb], cmul(w1, ldtab(tw + 16 * b * kb)));
+  }
+}
+// ---- phase 2, later passes (16 | s): p and the twiddle exponent base are uniform over a tile
+template <int A, int SIGN, typename T>
+PF_HD void ts_phase2_later(int t, int b0, int m, int s, const cpx<T>* tw, const cpx<T>* tile, cpx<T>* dst) {
+  using S = TsShape<A>;
+  const int j = t & 15, ka = t >> 4;
+#pragma unroll 1
+  for (int grp = 0; grp < S::G; ++grp) {
+    const int bg = b0 + 16 * grp;
+    if (bg >= m) break;
+    const cpx<T>* tl = tile + grp * (16 * S::R);
+    cpx<T> u[A];
+#pragma unroll
+    for (int q = 0; q < A; ++q) u[q] = tl[ts_tile_idx<A, false>(ka, q, j)];
+    dft_small<A, SIGN>(u);
+    const int pq = bg / s, e0 = pq * s;                     // e0 = s*p
+    cpx<T>* o = dst + (bg - e0 + j) + (long long)s * ((long long)S::R * pq + ka);
+    const long long ks = 16LL * s;
+    if (e0 == 0) {
+#pragma unroll
+      for (int kb = 0; kb < A; ++kb) o[ks * kb] = u[kb];
+    } else {
+#pragma unroll
+      for (int kb = 0; kb < A; ++kb) o[ks * kb] = cmul_dir<SIGN>(u[kb], ldtab(tw + (long long)e0 * (ka + 16 * kb)));
+    }
+  }
+}
+
+// one FFT work item, phase by phase (the kernel puts a CTA barrier between them; tests/emu steps them lane by lane)
+template <int A, bool FIRST, int SIGN, typename T>
+PF_HD void ts_item_phase(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
+                         const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
+  const int b0 = TsShape<A>::COLS * item;
+  if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile);
+  else if (FIRST) ts_phase2_first<A, SIGN, T>(t, b0, st.m, tw, tile, dst);
+  else ts_phase2_later<A, SIGN, T>(t, b0, st.m, st.s, tw, tile, dst);
+}
+template <bool FIRST, int SIGN, typename T>
+PF_HD void ts_item_phase_any(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
+                             const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
+  switch (st.A) {
+#define PF_TS(a) case a: ts_item_phase<a, FIRST, SIGN, T>(phase, t, item, st, src, dst, tw, twR, tile); break;
+    PF_TS(1) PF_TS(2) PF_TS(3) PF_TS(4) PF_TS(5) PF_TS(6) PF_TS(8) PF_TS(9) PF_TS(10) PF_TS(12) PF_TS(15) PF_TS(16)
+#undef PF_TS
+    default: break;
+  }
+}
+
+// ---- closing pass of a small radix A (no factor 16; cores with fewer than 4 factors of two per pass, e.g. 384000 =
+// 240 x 160 x 10): one column per thread, no exchange.  Work item = 256 neighbouring columns.
+template <int A, int SIGN, typename T>
+PF_HD void ts_small_item(int t, int item, int m, int s, const cpx<T>* src, cpx<T>* dst, const cpx<T>* tw) {
+  const int b = 256 * item + t;
+  if (b >= m) return;
+  cpx<T> u[A];
+#pragma unroll
+  for (int n = 0; n < A; ++n) u[n] = ld_l2(src + b + (long long)m * n);
+  dft_small<A, SIGN>(u);
+  const int pq = b / s, e0 = pq * s;
+  cpx<T>* o = dst + (b - e0) + (long long)s * ((long long)A * pq);
+  o[0] = u[0];
+#pragma unroll
+  for (int k = 1; k < A; ++k) o[(long long)s * k] = e0 ? cmul_dir<SIGN>(u[k], ldtab(tw + (long long)e0 * k)) : u[k];
+}
+template <int SIGN, typename T>
+PF_HD void ts_small_item_any(int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst, const cpx<T>* tw) {
+  switch (st.A) {
+#define PF_TS(a) case a: ts_small_item<a, SIGN, T>(t, item, st.m, st.s, src, dst, tw); break;
+    PF_TS(2) PF_TS(3) PF_TS(4) PF_TS(5) PF_TS(6) PF_TS(8) PF_TS(9) PF_TS(10) PF_TS(12) PF_TS(15)
+#undef PF_TS
+    default: break;
+  }
+}
+
+// element-wise stages: chunk c of kTsChunk core elements of one transform
+template <typename T>
+PF_HD void ts_pre_item(int t, int nthreads, int chunk, int mode, const T* ibase, cpx<T>* core, int N, int Nc, const cpx<T>* twr) {
+  const int hi = (chunk + 1) * kTsChunk < Nc ? (chunk + 1) * kTsChunk : Nc;
+  for (int i = chunk * kTsChunk + t; i < hi; i += nthreads) {
+    cpx<T> v;
+    if (mode == L_C_Z) v = load_core<L_C_Z, T>(ibase, i, N, Nc, twr, -1, true);
+    else if (mode == L_R_ORD) v = load_core<L_R_ORD, T>(ibase, i, N, Nc, twr, -1, true);
+    else v = load_core<L_R_Z, T>(ibase, i, N, Nc, twr, -1, true);
+    core[i] = v;
+  }
+}
+template <typename T>
+PF_HD void ts_post_item(int t, int nthreads, int chunk, int mode, const cpx<T>* core, T* obase, int N, int Nc, const cpx<T>* twr) {
+  const int hi = (chunk + 1) * kTsChunk < Nc ? (chunk + 1) * kTsChunk : Nc;
+  for (int k = chunk * kTsChunk + t; k < hi; k += nthreads) {
+    if (mode == S_C_Z) store_core<S_C_Z, T, true>(obase, core, k, N, Nc, twr, N, true);
+    else if (mode == S_R_ORD) store_core<S_R_ORD, T, true>(obase, core, k, N, Nc, twr, N, true);
+    else store_core<S_R_Z, T, true>(obase, core, k, N, Nc, twr, N, true);
+  }
+}
+
+// ticket -> (stage, transform, tile); false when the slot is padding (pipeline fill / drain)
+template <typename T>
+PF_HD bool ts_decode(const TsParams<T>& P, unsigned ticket, int* stage, long long* tr, int* item) {
+  const unsigned g = ticket / (unsigned)P.group_items;
+  int r = (int)(ticket - g * (unsigned)P.group_items);
+  int i = 0;
+  while (i < P.nstages - 1 && r >= P.st[i].tiles) { r -= P.st[i].tiles; ++i; }
+  const long long t = (long long)g - (long long)i * P.lag;
+  *stage = i; *tr = t; *item = r;
+  return t >= 0 && t < P.batch;
+}
+template <typename T> PF_HD const cpx<T>* ts_src(const TsParams<T>& P, int which, long long tr) {
+  if (which == 0) return reinterpret_cast<const cpx<T>*>(P.in) + tr * P.Nc;
+  return P.ring[which - 2] + (long long)(tr % P.ring_slots) * P.Nc;
+}
+template <typename T> PF_HD cpx<T>* ts_dst(const TsParams<T>& P, int which, long long tr) {
+  if (which == 1) return reinterpret_cast<cpx<T>*>(P.out) + tr * P.Nc;
+  return P.ring[which - 2] + (long long)(tr % P.ring_slots) * P.Nc;
+}
+
+#ifdef __CUDACC__
+PF_D unsigned ts_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+PF_D void ts_wait_at_least(const unsigned* p, unsigned need) {
+  while (ts_ld_acquire(p) < need) __nanosleep(200);
+}
+
+template <typename T, int SIGN, int MINB>
+__global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
+  __shared__ unsigned s_ticket;
+  const int t = threadIdx.x;
+  if (t == 0) s_ticket = atomicAdd(P.counters, 1u);
+  __syncthreads();
+  unsigned cur = s_ticket;
+  while (cur < P.total_items) {
+    int stage, item; long long tr;
+    const bool live = ts_decode(P, cur, &stage, &tr, &item);
+    const TsStage& st = P.st[stage];
+    unsigned next = 0;
+    unsigned* done = nullptr;
+    if (t == 0) {
+      next = atomicAdd(P.counters, 1u);                       // next ticket: in flight while this item is processed
+      if (live) {
+        const int slot = (int)(tr % P.ring_slots);
+        const unsigned gen = (unsigned)(tr / P.ring_slots);
+        unsigned* base = P.counters + kTsCounterBase + slot;
+        done = base + stage * P.ring_slots;
+        if (stage > 0)                                        // input complete
+          ts_wait_at_least(base + (stage - 1) * P.ring_slots, (gen + 1u) * (unsigned)P.st[stage - 1].tiles);
+        if (stage + 1 < P.nstages && gen > 0)                 // ring slot free: its previous occupant was consumed
+          ts_wait_at_least(base + (stage + 1) * P.ring_slots, gen * (unsigned)P.st[stage + 1].tiles);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      const cpx<T>* src = ts_src(P, st.src, tr);
+      cpx<T>* dst = ts_dst(P, st.dst, tr);
+      if (st.kind == TS_FIRST) {
+        ts_item_phase_any<true, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile);
+        __syncthreads();
+        ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+      } else if (st.kind == TS_LATER) {
+        ts_item_phase_any<false, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile);
+        __syncthreads();
+        ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+      } else if (st.kind == TS_SMALL) {
+        ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
+      } else if (st.kind == TS_PRE) {
+        ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+      } else {
+        ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+      }
+    }
+    if (t == 0) s_ticket = next;
+    __syncthreads();                                          // every store of the item is issued; tile is free again
+    if (t == 0 && live) { __threadfence(); atomicAdd(done, 1u); }
+    cur = s_ticket;
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace pf

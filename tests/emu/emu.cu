@@ -82,3 +82,89 @@ extern "C" int emu_regfft(int N, int dir, const float* in, float* out) {
 extern "C" long long emu_fastconv_produced(long long inputLen, int Nfft, int filterLen, int flush, int even_out) {
   return pfplan::plan_blocks(inputLen, Nfft, filterLen, flush, even_out != 0).produced;
 }
+
+// ---- tiled Stockham pipeline (ts_kernels.cuh): the persistent kernel's ticket loop stepped on the CPU.  `window` tickets
+// are "in flight" at a time (as many as the GPU has resident CTAs); the next one to run is picked AT RANDOM among those whose
+// dependency counters are satisfied, so the emulation checks that (1) the counters alone are sufficient for correct data
+// under any interleaving the hardware may produce and (2) some in-flight ticket is always runnable (no deadlock).
+#include "../../pffft_b200/csrc/ts_plan.h"
+template <typename T, int SIGN>
+static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
+  std::vector<unsigned> counters(kTsCounterBase + (size_t)kTsMaxStages * P.ring_slots, 0u);
+  std::vector<cpx<T>> tile(16 * 256);
+  std::vector<unsigned> flight;
+  unsigned next = 0;
+  uint32_t rs = seed * 2654435761u + 12345u;
+  auto ready = [&](unsigned ticket) {
+    int stage, item; long long tr;
+    if (!ts_decode(P, ticket, &stage, &tr, &item)) return true;
+    const int slot = (int)(tr % P.ring_slots); const unsigned gen = (unsigned)(tr / P.ring_slots);
+    const unsigned* base = counters.data() + kTsCounterBase + slot;
+    if (stage > 0 && base[(stage - 1) * P.ring_slots] < (gen + 1u) * (unsigned)P.st[stage - 1].tiles) return false;
+    if (stage + 1 < P.nstages && gen > 0 && base[(stage + 1) * P.ring_slots] < gen * (unsigned)P.st[stage + 1].tiles) return false;
+    return true;
+  };
+  while (next < P.total_items || !flight.empty()) {
+    while ((int)flight.size() < window && next < P.total_items) flight.push_back(next++);
+    std::vector<int> cand;
+    for (int i = 0; i < (int)flight.size(); ++i) if (ready(flight[i])) cand.push_back(i);
+    if (cand.empty()) return -10;                                  // deadlock
+    rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+    const int pick = cand[rs % cand.size()];
+    const unsigned cur = flight[pick];
+    flight.erase(flight.begin() + pick);
+    int stage, item; long long tr;
+    if (!ts_decode(P, cur, &stage, &tr, &item)) continue;
+    const TsStage& st = P.st[stage];
+    const cpx<T>* src = ts_src(P, st.src, tr);
+    cpx<T>* dst = ts_dst(P, st.dst, tr);
+    if (st.kind == TS_FIRST || st.kind == TS_LATER) {
+      for (int phase = 0; phase < 2; ++phase)
+        for (int t = 0; t < kTsThreads; ++t) {
+          if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(phase, t, item, st, src, dst, P.tw, P.twR, tile.data());
+          else ts_item_phase_any<false, SIGN, T>(phase, t, item, st, src, dst, P.tw, P.twR, tile.data());
+        }
+    } else if (st.kind == TS_SMALL) {
+      for (int t = 0; t < kTsThreads; ++t) ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
+    } else if (st.kind == TS_PRE) {
+      for (int t = 0; t < kTsThreads; ++t) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+    } else {
+      for (int t = 0; t < kTsThreads; ++t) ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+    }
+    counters[kTsCounterBase + stage * P.ring_slots + (int)(tr % P.ring_slots)] += 1;
+  }
+  return 0;
+}
+template <typename T>
+static int emu_ts_t(int N, int transform, int dir, int ordered, const T* in, T* out, long long batch, int lag, int window, unsigned seed) {
+  const int Nc = transform == 0 ? N / 2 : N;
+  int Pn = 0, A[4], tw_off[4];
+  if (!ts_factorize(Nc, &Pn, A)) return -1;
+  std::vector<T> tw(2 * (size_t)Nc), twr(2 * (size_t)(N / 2));
+  pfplan::fill_roots<T>(tw.data(), Nc, Nc);
+  pfplan::fill_roots<T>(twr.data(), N / 2, N);
+  const std::vector<T> twR = ts_radix_tables<T>(Pn, A, tw_off);
+  TsParams<T> P;
+  memset(&P, 0, sizeof(P));
+  P.in = in; P.out = out; P.batch = batch; P.N = N; P.Nc = Nc;
+  P.tw = reinterpret_cast<const cpx<T>*>(tw.data()); P.twr = reinterpret_cast<const cpx<T>*>(twr.data());
+  P.twR = reinterpret_cast<const cpx<T>*>(twR.data());
+  P.lag = lag; P.ring_slots = lag > 0 ? 2 * lag + 1 : 1;
+  std::vector<std::vector<cpx<T>>> rings(kTsMaxRings, std::vector<cpx<T>>((size_t)P.ring_slots * Nc));
+  for (int i = 0; i < kTsMaxRings; ++i) P.ring[i] = rings[i].data();
+  int lm, sm;
+  const bool fwd = dir == 0;
+  if (transform == 1) { lm = (fwd || ordered) ? L_C_ORD : L_C_Z; sm = (fwd && !ordered) ? S_C_Z : S_C_ORD; }
+  else if (fwd) { lm = L_R_TIME; sm = ordered ? S_R_ORD : S_R_Z; }
+  else { lm = ordered ? L_R_ORD : L_R_Z; sm = S_R_TIME; }
+  ts_build_stages<T>(P, Nc, Pn, A, tw_off, lm, sm);
+  P.total_items = (unsigned)((batch + (long long)(P.nstages - 1) * lag) * P.group_items);
+  return fwd ? ts_emulate<T, -1>(P, window, seed) : ts_emulate<T, +1>(P, window, seed);
+}
+// radices come from PFFFT_B200_TS_RADICES when set (ts_factorize reads it), else the default factorisation
+extern "C" int emu_ts(int prec, int N, int transform, int dir, int ordered, const void* in, void* out, long long batch,
+                      int lag, int window, unsigned seed) {
+  if (prec == 0) return emu_ts_t<float>(N, transform, dir, ordered, (const float*)in, (float*)out, batch, lag, window, seed);
+  return emu_ts_t<double>(N, transform, dir, ordered, (const double*)in, (double*)out, batch, lag, window, seed);
+}
+extern "C" int emu_ts_factorize(int Nc, int* P, int* A) { return ts_factorize(Nc, P, A) ? 1 : 0; }

@@ -1,0 +1,106 @@
+"""Oracle parity AT BASELINE SCALE: the full resident batches of BASELINE configs C2, C3, C4 are transformed
+on the GPU and >= 4096 transforms sampled across the whole batch -- first, last and indices far beyond the persistent
+grids (every grid-stride / persistent loop wraps many times) -- are compared with the UNMODIFIED reference (oracle/_ref)
+on the same inputs.  C4 compares all 16 773 120 outputs with the reference's pffastconv_apply.
+Tolerance: relmax <= 1e-5 per transform (north_star; the reference validator's metric, bench_pffft.c:372)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_indices(batch, count, seed):
+    rng = np.random.default_rng(seed)
+    head = np.arange(64)
+    tail = np.arange(batch - 64, batch)
+    # a run of consecutive transforms in the middle (neighbouring warps / CTAs of one wave) + uniform samples
+    mid = np.arange(batch // 2 - 32, batch // 2 + 32)
+    rest = rng.integers(0, batch, size=count - head.size - tail.size - mid.size)
+    return np.unique(np.concatenate([head, mid, rest, tail]))
+
+
+def _parity_on_samples(pf, ref, R, N, tr, batch, seed, tol=1e-5):
+    import torch
+    per = N if tr == 0 else 2 * N
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)           # Philox counter-based generator
+    x = torch.rand((batch, per), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    idx = _sample_indices(batch, 4160, seed)
+    assert idx.size >= 4096
+    ti = torch.from_numpy(idx).cuda()
+    with pf.Setup(N, tr) as s:
+        kern = s.kernel
+        y = s.transform_batch(x, 0, True)
+        torch.cuda.synchronize()
+        xs = x[ti].cpu().numpy()
+        ys = y[ti].cpu().numpy()
+        # backward on the forward result, in place over y (the reference allows in == out, pffft.h:137-142)
+        s.transform_batch(y, 1, True, out=y)
+        torch.cuda.synchronize()
+        zs = y[ti].cpu().numpy()
+        rt = float(((y / N - x) ** 2).sum(dim=1).max().item())        # every transform of the batch: round trip
+    assert rt <= N * 1e-7, (kern, rt)                                 # tests/test_pffft.c:239
+    want_f = ref.transform_batch(N, tr, xs, 0, True)
+    worst_f = max(R.relmax(ys[i], want_f[i]) for i in range(idx.size))
+    assert worst_f <= tol, ("forward", kern, worst_f)
+    want_b = ref.transform_batch(N, tr, want_f, 1, True)
+    worst_b = max(R.relmax(zs[i], want_b[i]) for i in range(idx.size))
+    assert worst_b <= 2 * tol, ("backward", kern, worst_b)            # GPU backward ran on the GPU's own forward output
+    return kern, worst_f, worst_b
+
+
+def test_c2_full_batch_sampled_vs_reference(pf, ref, R):
+    """BASELINE configs[1]: N=1024 complex fp32 fwd+inv, batch 2^20 (8 GiB in, 8 GiB out), seed 1234"""
+    kern, wf, wb = _parity_on_samples(pf, ref, R, 1024, 1, 1 << 20, 1234)
+    assert "c1024" in kern
+
+
+def test_c3_full_batch_sampled_vs_reference(pf, ref, R):
+    """BASELINE configs[2]: N=4096 real fp32 forward (+ backward), batch 2^18, seed 1235"""
+    kern, wf, wb = _parity_on_samples(pf, ref, R, 4096, 0, 1 << 18, 1235)
+    assert kern == "cta_16x16x8"
+
+
+def test_c2_unordered_full_batch_sampled(pf, ref, R):
+    """pffft_transform (z-domain) at a batch that wraps the persistent grid many times: element-wise vs the reference's
+    internal layout, and backward from the z-domain"""
+    import torch
+    N, batch = 1024, 1 << 17
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    x = torch.rand((batch, 2 * N), generator=g, device="cuda") * 2 - 1
+    idx = _sample_indices(batch, 1024, 77)
+    ti = torch.from_numpy(idx).cuda()
+    with pf.Setup(N, 1) as s:
+        z = s.transform_batch(x, 0, False)
+        b = s.transform_batch(z, 1, False)
+        torch.cuda.synchronize()
+        xs, zs = x[ti].cpu().numpy(), z[ti].cpu().numpy()
+        assert float((b / N - x).abs().max().item()) <= 1e-5
+    want = ref.transform_batch(N, 1, xs, 0, False)
+    assert max(R.relmax(zs[i], want[i]) for i in range(idx.size)) <= 1e-5
+
+
+def test_c4_full_stream_vs_reference_apply(pf, ref):
+    """BASELINE configs[3]: 2^24-sample real stream, 4097 taps, blockLen 0 -> Nfft 8192, flush: ALL 16 773 120 outputs
+    against the reference's own pffastconv_apply (inputs exactly tests/test_pffastconv.c:538-569; limit (max-min)/1e5, :685)"""
+    import torch
+    n, taps = 1 << 24, 4097
+    x = (np.arange(n) % 4093).astype(np.float32)
+    h = np.array([-1.0, 1.0, 0.5], np.float32)[np.arange(taps) % 3]
+    want, produced, bl = ref.fastconv(h, x, 0, 0, 1)
+    assert produced == n - taps + 1 == 16773120 and bl == 8192
+    fc = pf.FastConv(h, 0, 0)
+    assert fc.block_len == 8192
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((n + 64,), float("nan"), device="cuda")
+    got_n = fc.apply(xd, yd, n, 1)
+    torch.cuda.synchronize()
+    assert got_n == produced
+    got = yd[:produced].cpu().numpy()
+    assert bool(torch.isnan(yd[produced:]).all())                      # nothing written past the produced samples
+    limit = (float(want.max()) - float(want.min())) / 1e5
+    assert float(np.max(np.abs(got.astype(np.float64) - want))) <= limit
+    # host-pointer path (pipelined pieces) is bit-identical to the one-launch device call
+    yh = np.full(n + 64, np.nan, np.float32)
+    assert fc.apply(x, yh, n, 1) == produced
+    assert np.array_equal(yh[:produced], got)
+    fc.close()
