@@ -419,13 +419,15 @@ inline bool is_cta_row_size(int n) { return cta_C_for(n) != 0; }
 
 // hooks for a precision whose only tuned kernels are the CTA ones (double)
 template <typename T> struct CtaOnlyHooks {
+  // THE decomposition of a core (tables and plan must agree on it): single-kernel form first unless switched off
+  static bool decompose(int Nc, int* R, int* N2, bool* fused) {
+    if (cta_C_for(Nc)) return false;
+    *fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_choose_fused<T>(Nc, R, N2);
+    return *fused || split_choose(Nc, is_cta_row_size, R, N2);
+  }
   static int rows_size(int N, int transform) {               // N2 of the split plan, 0 if the size is not split
-    const int Nc = transform == XF_REAL ? N / 2 : N;
-    int R = 0, N2 = 0;
-    if (cta_C_for(Nc)) return 0;
-    if (split_choose_fused<T>(Nc, &R, &N2)) return N2;
-    if (!split_choose(Nc, is_cta_row_size, &R, &N2)) return 0;
-    return N2;
+    int R = 0, N2 = 0; bool fused = false;
+    return decompose(transform == XF_REAL ? N / 2 : N, &R, &N2, &fused) ? N2 : 0;
   }
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
@@ -441,9 +443,8 @@ template <typename T> struct CtaOnlyHooks {
   }
   static bool plan(Setup<T>* s) {
     if (ts_wanted(s->Nc)) return ts_plan<T>(s);
-    int R = 0, N2 = 0;
-    const bool fused = !cta_C_for(s->Nc) && !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_choose_fused<T>(s->Nc, &R, &N2);
-    if (!cta_C_for(s->Nc) && (fused || split_choose(s->Nc, is_cta_row_size, &R, &N2))) {
+    int R = 0, N2 = 0; bool fused = false;
+    if (decompose(s->Nc, &R, &N2, &fused)) {
       if (getenv("PFFFT_B200_NO_SPLIT")) return false;
       s->split_R = R; s->split_N2 = N2; s->split_fused = fused;
       s->fast_variant = 300;

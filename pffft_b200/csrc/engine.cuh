@@ -76,6 +76,7 @@ struct Slot {                  // one lane of the host-pointer pipeline
   cudaStream_t stream = nullptr;
   void* d_in = nullptr;
   void* d_out = nullptr;
+  void* d_aux = nullptr;       // third operand of host-pointer zconvolve calls (per-batch b)
 };
 
 template <typename T> struct Setup {
@@ -111,7 +112,9 @@ template <typename T> struct Setup {
   // host-pointer pipeline (3 slots: H2D / kernels / D2H overlap across slots)
   std::mutex mu;
   Slot slot[3];
-  size_t slot_elems = 0;                  // capacity of each d_in / d_out, in T elements
+  size_t slot_elems = 0;                  // capacity of each d_in / d_out / d_aux, in T elements
+  void* d_bshared = nullptr;              // one spectrum: the shared operand b of host-pointer zconvolve calls
+  cudaEvent_t bshared_ready = nullptr;
   // scratch for the global-memory (large N) path
   cpx<T>* d_scratch[2] = {nullptr, nullptr};
   size_t scratch_cpx = 0;
@@ -196,8 +199,11 @@ S* engine_new_setup(int N, int transform) {
   bool ok = true;
   for (int i = 0; i < 3 && ok; ++i) {
     ok = cudaMalloc(&s->slot[i].d_in, s->slot_elems * sizeof(T)) == cudaSuccess &&
-         cudaMalloc(&s->slot[i].d_out, s->slot_elems * sizeof(T)) == cudaSuccess;
+         cudaMalloc(&s->slot[i].d_out, s->slot_elems * sizeof(T)) == cudaSuccess &&
+         cudaMalloc(&s->slot[i].d_aux, s->slot_elems * sizeof(T)) == cudaSuccess;
   }
+  ok = ok && cudaMalloc(&s->d_bshared, s->per() * sizeof(T)) == cudaSuccess &&
+       cudaEventCreateWithFlags(&s->bshared_ready, cudaEventDisableTiming) == cudaSuccess;
   if (ok && s->kind == KK_GLOBAL) {                                  // (tuned large-N plans allocate it on first fallback use)
     s->scratch_cpx = (size_t)s->Nc;
     ok = cudaMalloc((void**)&s->d_scratch[0], s->scratch_cpx * cbytes) == cudaSuccess &&
@@ -216,7 +222,10 @@ template <typename T, typename S> void engine_destroy_setup(S* s) {
     if (s->slot[i].stream) { cudaStreamSynchronize(s->slot[i].stream); cudaStreamDestroy(s->slot[i].stream); }
     if (s->slot[i].d_in) cudaFree(s->slot[i].d_in);
     if (s->slot[i].d_out) cudaFree(s->slot[i].d_out);
+    if (s->slot[i].d_aux) cudaFree(s->slot[i].d_aux);
   }
+  if (s->d_bshared) cudaFree(s->d_bshared);
+  if (s->bshared_ready) cudaEventDestroy(s->bshared_ready);
   for (int i = 0; i < 2; ++i) if (s->d_scratch[i]) cudaFree(s->d_scratch[i]);
   if (s->scratch_done) cudaEventDestroy(s->scratch_done);
   if (s->d_tables) cudaFree(s->d_tables);
@@ -331,19 +340,44 @@ template <typename T> int ensure_slots(Setup<T>* s, size_t elems) {
     PF_CUDA_OK(cudaStreamSynchronize(s->slot[i].stream));
     if (s->slot[i].d_in) cudaFree(s->slot[i].d_in);
     if (s->slot[i].d_out) cudaFree(s->slot[i].d_out);
-    s->slot[i].d_in = s->slot[i].d_out = nullptr;
+    if (s->slot[i].d_aux) cudaFree(s->slot[i].d_aux);
+    s->slot[i].d_in = s->slot[i].d_out = s->slot[i].d_aux = nullptr;
     PF_CUDA_OK(cudaMalloc(&s->slot[i].d_in, elems * sizeof(T)));
     PF_CUDA_OK(cudaMalloc(&s->slot[i].d_out, elems * sizeof(T)));
+    PF_CUDA_OK(cudaMalloc(&s->slot[i].d_aux, elems * sizeof(T)));
   }
   s->slot_elems = elems;
   return 0;
 }
 
+// makes the plan's device current for the scope of a call and restores the caller's on EVERY exit path
+struct DeviceScope {
+  int prev = -1; bool switched = false; int rc = 0;
+  explicit DeviceScope(int want) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != want) { rc = (int)cudaSetDevice(want); switched = (rc == 0); if (rc) set_error("cudaSetDevice(plan device)", (cudaError_t)rc); }
+  }
+  ~DeviceScope() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+// waits for everything queued on the slot streams (also on error paths: no copy into or out of a user buffer may still
+// be in flight when the call returns)
+template <typename T> struct SlotDrain {
+  Setup<T>* s; int rc = 0;
+  explicit SlotDrain(Setup<T>* s_) : s(s_) {}
+  int finish() {
+    for (int k = 0; k < 3; ++k) { const cudaError_t e = cudaStreamSynchronize(s->slot[k].stream); if (e != cudaSuccess && !rc) { rc = (int)e; set_error("host pipeline: stream synchronize", e); } }
+    s = nullptr;
+    return rc;
+  }
+  ~SlotDrain() { if (s) for (int k = 0; k < 3; ++k) cudaStreamSynchronize(s->slot[k].stream); }
+};
+
 template <typename T, typename Fn>
 int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device_op) {
   std::lock_guard<std::mutex> lock(s->mu);
-  int cur = 0; cudaGetDevice(&cur);
-  if (cur != s->device) PF_CUDA_OK(cudaSetDevice(s->device));
+  DeviceScope dev(s->device);
+  if (dev.rc) return dev.rc;
+  SlotDrain<T> drain(s);
   const size_t per = s->per();
   static const size_t chunk_bytes = []() {                                  // ~32 MiB per direction per chunk (PFFFT_B200_CHUNK_MB overrides)
     const char* e = getenv("PFFFT_B200_CHUNK_MB");
@@ -381,9 +415,7 @@ int host_pipeline(Setup<T>* s, const T* in, T* out, long long batch, Fn&& device
     return 0;
   };
   while (b0 < batch) { rc = submit((batch - b0 < chunk) ? (batch - b0) : chunk); if (rc) return rc; }
-  for (int k = 0; k < 3; ++k) PF_CUDA_OK(cudaStreamSynchronize(s->slot[k].stream));
-  if (cur != s->device) cudaSetDevice(cur);
-  return 0;
+  return drain.finish();
 }
 
 // the public transform: host or device pointers
@@ -393,13 +425,19 @@ int engine_transform(Setup<T>* s, const T* in, T* out, long long batch, int dire
   if (direction != DIR_FORWARD && direction != DIR_BACKWARD) { set_error_msg("pffft transform: bad direction"); return (int)cudaErrorInvalidValue; }
   const bool din = ptr_is_device(in), dout = ptr_is_device(out);
   if (din != dout) { set_error_msg("pffft transform: input and output must both be host or both be device pointers"); return (int)cudaErrorInvalidValue; }
-  if (din) return engine_transform_device<T, Hooks>(s, in, out, batch, direction, ordered, s->stream);
+  if (din) {                                                   // enqueue on the PLAN's device whatever the caller's current one is
+    DeviceScope dev(s->device);
+    if (dev.rc) return dev.rc;
+    return engine_transform_device<T, Hooks>(s, in, out, batch, direction, ordered, s->stream);
+  }
   // page-locked host buffers (pffft_aligned_malloc, cudaHostAlloc, cudaHostRegister) are mapped into the device's
   // address space: with PFFFT_B200_ZEROCOPY=1 the kernels read and write them directly over PCIe (no staging copies)
   if (zero_copy_enabled()) {
     void *din_p = nullptr, *dout_p = nullptr;
     if (host_mapped_pointer(in, &din_p) && host_mapped_pointer(out, &dout_p)) {
       std::lock_guard<std::mutex> lock(s->mu);
+      DeviceScope dev(s->device);
+      if (dev.rc) return dev.rc;
       cudaStream_t st = s->slot[0].stream;
       const int rc = engine_transform_device<T, Hooks>(s, (const T*)din_p, (T*)dout_p, batch, direction, ordered, st);
       if (rc) return rc;
@@ -463,7 +501,7 @@ template <typename T> int engine_zreorder(Setup<T>* s, const T* in, T* out, long
   if (in == out) { set_error_msg("pffft_zreorder: input and output must not alias (ref pffft_priv_impl.h:1162)"); return (int)cudaErrorInvalidValue; }
   const bool din = ptr_is_device(in), dout = ptr_is_device(out);
   if (din != dout) { set_error_msg("pffft_zreorder: mixed host/device pointers"); return (int)cudaErrorInvalidValue; }
-  if (din) return engine_zreorder_device<T>(s, in, out, batch, direction, s->stream);
+  if (din) { DeviceScope dev(s->device); if (dev.rc) return dev.rc; return engine_zreorder_device<T>(s, in, out, batch, direction, s->stream); }
   return host_pipeline<T>(s, in, out, batch, [&](const T* di, T* dst_, long long nb, cudaStream_t st) {
     return engine_zreorder_device<T>(s, di, dst_, nb, direction, st);
   });
@@ -494,31 +532,37 @@ template <typename T> int engine_zconvolve(Setup<T>* s, const T* a, const T* b, 
   if (batch <= 0) return 0;
   const bool da = ptr_is_device(a), db = ptr_is_device(b), dab = ptr_is_device(ab);
   if (da != db || da != dab) { set_error_msg("pffft_zconvolve: mixed host/device pointers"); return (int)cudaErrorInvalidValue; }
-  if (da) return engine_zconvolve_device<T>(s, a, b, ab, scaling, batch, b_shared, accumulate, s->stream);
-  // host: simple synchronous staging (this entry point is bandwidth-trivial next to the PCIe copies)
+  if (da) { DeviceScope dev(s->device); if (dev.rc) return dev.rc; return engine_zconvolve_device<T>(s, a, b, ab, scaling, batch, b_shared, accumulate, s->stream); }
+  // host pointers: the same three-slot pipeline as the transforms (a -> d_in, per-batch b -> d_aux, ab <-> d_out), ~32 MiB
+  // chunks, no allocation for single-spectrum calls (buffers are sized for one transform when the plan is built;
+  // ref README.md:269-271 "the fft functions do not perform any memory allocation")
   std::lock_guard<std::mutex> lock(s->mu);
-  int cur = 0; cudaGetDevice(&cur);
-  if (cur != s->device) PF_CUDA_OK(cudaSetDevice(s->device));
+  DeviceScope dev(s->device);
+  if (dev.rc) return dev.rc;
+  SlotDrain<T> drain(s);
   const size_t per = s->per();
-  const size_t nb_b = b_shared ? 1 : (size_t)batch;
-  T *d_a = nullptr, *d_b = nullptr, *d_ab = nullptr;
-  cudaStream_t st = s->slot[0].stream;
-  int rc = 0;
-  do {
-    if ((rc = (int)cudaMalloc((void**)&d_a, (size_t)batch * per * sizeof(T)))) break;
-    if ((rc = (int)cudaMalloc((void**)&d_b, nb_b * per * sizeof(T)))) break;
-    if ((rc = (int)cudaMalloc((void**)&d_ab, (size_t)batch * per * sizeof(T)))) break;
-    if ((rc = (int)cudaMemcpyAsync(d_a, a, (size_t)batch * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
-    if ((rc = (int)cudaMemcpyAsync(d_b, b, nb_b * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
-    if (accumulate && (rc = (int)cudaMemcpyAsync(d_ab, ab, (size_t)batch * per * sizeof(T), cudaMemcpyHostToDevice, st))) break;
-    if ((rc = engine_zconvolve_device<T>(s, d_a, d_b, d_ab, scaling, batch, b_shared, accumulate, st))) break;
-    if ((rc = (int)cudaMemcpyAsync(ab, d_ab, (size_t)batch * per * sizeof(T), cudaMemcpyDeviceToHost, st))) break;
-    rc = (int)cudaStreamSynchronize(st);
-  } while (0);
-  if (rc) set_error("pffft_zconvolve (host staging)", (cudaError_t)rc);
-  if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b); if (d_ab) cudaFree(d_ab);
-  if (cur != s->device) cudaSetDevice(cur);
-  return rc;
+  long long chunk = (long long)(((size_t)32 << 20) / (per * sizeof(T)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  { const int rc = ensure_slots(s, (size_t)chunk * per); if (rc) return rc; }
+  if (b_shared) {
+    PF_CUDA_OK(cudaMemcpyAsync(s->d_bshared, b, per * sizeof(T), cudaMemcpyHostToDevice, s->slot[0].stream));
+    PF_CUDA_OK(cudaEventRecord(s->bshared_ready, s->slot[0].stream));
+    for (int k = 1; k < 3; ++k) PF_CUDA_OK(cudaStreamWaitEvent(s->slot[k].stream, s->bshared_ready, 0));
+  }
+  int i = 0;
+  for (long long b0 = 0; b0 < batch; b0 += chunk, i = (i + 1) % 3) {
+    const long long nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const size_t off = (size_t)b0 * per, bytes = (size_t)nb * per * sizeof(T);
+    Slot& sl = s->slot[i];
+    PF_CUDA_OK(cudaMemcpyAsync(sl.d_in, a + off, bytes, cudaMemcpyHostToDevice, sl.stream));
+    if (!b_shared) PF_CUDA_OK(cudaMemcpyAsync(sl.d_aux, b + off, bytes, cudaMemcpyHostToDevice, sl.stream));
+    if (accumulate) PF_CUDA_OK(cudaMemcpyAsync(sl.d_out, ab + off, bytes, cudaMemcpyHostToDevice, sl.stream));
+    const T* db_ = b_shared ? (const T*)s->d_bshared : (const T*)sl.d_aux;
+    { const int rc = engine_zconvolve_device<T>(s, (const T*)sl.d_in, db_, (T*)sl.d_out, scaling, nb, b_shared, accumulate, sl.stream); if (rc) return rc; }
+    PF_CUDA_OK(cudaMemcpyAsync(ab + off, sl.d_out, bytes, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  return drain.finish();
 }
 
 }  // namespace pf
