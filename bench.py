@@ -28,8 +28,9 @@ sys.path.insert(0, ROOT)
 N = 1024
 BYTES_PER_FFT = 2 * N * 2 * 4          # 8 KiB read + 8 KiB written (algorithmic bytes / transform)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the forward kernel, per transform:
-# (2.147577 + 2.097573) GB over a 262144-transform launch (profiles/r01_ncu_full_c1024.txt).  bench.py scales it to
-# the units of its own launch; it is evidence that traffic ~= algorithmic bytes, not a live measurement.
+# (2.147577 + 2.097573) GB over a 262144-transform launch (profiles/r01_ncu_full_c1024.txt; the kernel is unchanged since).
+# STATIC: bench.py scales the committed capture to the units of its own launch and labels it so ("traffic_kind");
+# it is evidence that traffic ~= algorithmic bytes, not a measurement of this run (ncu cannot run inside a timed bench).
 NCU_DRAM_BYTES_PER_FFT = (2.147577e9 + 2.097573e9) / 262144
 FLOPS_PER_FFT = 5 * N * 10             # 5 N log2 N (bench_pffft.c:1021)
 
@@ -99,6 +100,37 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
+def host_llc_bytes():
+    """total last-level cache of the host (sum over the distinct L3 instances sysfs lists), 0 when unknown"""
+    seen, total = set(), 0
+    base = "/sys/devices/system/cpu"
+    try:
+        for cpu in os.listdir(base):
+            d = os.path.join(base, cpu, "cache", "index3")
+            if not (cpu.startswith("cpu") and cpu[3:].isdigit() and os.path.isdir(d)):
+                continue
+            ident = open(os.path.join(d, "shared_cpu_list")).read().strip()
+            if ident in seen:
+                continue
+            seen.add(ident)
+            sz = open(os.path.join(d, "size")).read().strip()
+            mult = {"K": 1 << 10, "M": 1 << 20, "G": 1 << 30}.get(sz[-1].upper(), 1)
+            total += int(sz[:-1] if sz[-1].isalpha() else sz) * mult
+    except Exception:
+        return 0
+    return total
+
+
+def cpu_sample_transforms():
+    """transforms per CPU pass: the working set (8 KiB in + 8 KiB out each) is >= 4x the host's total LLC so the
+    reference streams from DRAM like the GPU streams from HBM (2^16 = 1 GiB at least, 2^19 = 8 GiB at most)"""
+    llc = host_llc_bytes()
+    n = 1 << 16
+    while n * 2 * BYTES_PER_FFT // 2 < 4 * llc and n < (1 << 19):
+        n <<= 1
+    return n, llc
+
+
 def cpu_reference_rate(seconds_target, fwd_inv=True):
     """FFTs/s of the reference's own CPU implementation (oracle/_ref, unmodified pffft built with
     -O3 -march=haswell) on all host cores, through oracle/libcpubench.so: threads share one PFFFT_Setup
@@ -112,7 +144,7 @@ def cpu_reference_rate(seconds_target, fwd_inv=True):
     lib.cpu_bench_transform.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     path = R.REF_SO.encode()
-    sample = 1 << 16                                   # 2^16 transforms = 512 MiB in + 512 MiB out: DRAM-streamed
+    sample, llc = cpu_sample_transforms()              # >= 2^16 transforms (512 MiB in + 512 MiB out) and >= 4x LLC
     per_pass = 2 if fwd_inv else 1
     t1 = lib.cpu_bench_transform(path, N, 1, sample, cores, 1, 1 if fwd_inv else 0, 1, 1234)
     if t1 <= 0:
@@ -125,9 +157,11 @@ def cpu_reference_rate(seconds_target, fwd_inv=True):
     t_one = lib.cpu_bench_transform(path, N, 1, 1 << 13, 1, 4, 1 if fwd_inv else 0, 1, 1234)
     rate1 = (1 << 13) * per_pass * 4 / t_one if t_one > 0 else None
     return {"value": rate, "unit": "FFT/s", "cores": cores, "kind": "reference",
-            "sample": "%d x N=1024 cplx fp32 %s, ordered, %d passes, %d threads sharing one PFFFT_Setup, uniform(-1,1)"
-                      % (sample, "fwd+inv" if fwd_inv else "fwd", iters, cores),
-            "single_thread_value": rate1, "seconds": t}
+            "sample": "%d x N=1024 cplx fp32 %s (inverse in place on the just-written vector, as a per-vector caller would), "
+                      "ordered, %d passes, %d threads sharing one PFFFT_Setup, uniform(-1,1); working set %.2f GiB = %.1fx host LLC (%.0f MiB)"
+                      % (sample, "fwd+inv" if fwd_inv else "fwd", iters, cores, sample * BYTES_PER_FFT / 2**30,
+                         (sample * BYTES_PER_FFT / llc) if llc else float("nan"), llc / 2**20),
+            "single_thread_value": rate1, "seconds": t, "sample_transforms": sample, "host_llc_bytes": llc}
 
 
 def run_reference_arm(args):
@@ -150,13 +184,13 @@ def run_reference_arm(args):
             return 0
         per_step.append(res["value"])
     value = float(np.median(per_step))
-    sample = 1 << 16
+    sample = res["sample_transforms"]
     line = {
         "impl": "reference", "metric": "batched FFTs/sec at N=1024 cplx fp32 (fwd+inv)", "value": value, "unit": "FFT/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (2 * sample) / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: N=1024 complex fp32 fwd+inv, ordered; bounded sample of 2^16 transforms per step on the host CPU"},
+        "config": {"workload": "C2: N=1024 complex fp32 fwd+inv, ordered; bounded sample of %d transforms per step on the host CPU (>= 4x LLC)" % sample},
         "cpu_baseline": {"value": value, "unit": "FFT/s", "cores": res["cores"], "kind": "reference", "sample": res["sample"]},
         "e2e": {"value": value, "unit": "FFT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gbs_algorithmic": value * BYTES_PER_FFT / 1e9, "gflops": value * FLOPS_PER_FFT / 1e9,
@@ -205,10 +239,31 @@ def main():
     batch = args.batch
     setup = pf.Setup(N, pf.PFFFT_COMPLEX)
     # multi-GPU: rank 0's tables are THE tables (bit-identical plans everywhere): one NCCL broadcast over NVLink
+    table_broadcast = "none (1 GPU)"
     if world > 1:
-        tptr, tbytes = setup.tables()
-        tables = torch.as_tensor(_CudaMem(tptr, tbytes), device="cuda")
-        dist.broadcast(tables, src=0)
+        # the library's own collective (multi.cu): rank 0 makes an NCCL id, torch.distributed only carries its 128 bytes,
+        # ncclCommInitRank + ncclBroadcast(root 0) of the tables run inside libpffft_b200.so
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        ok = torch.ones(1, device="cuda", dtype=torch.int32)
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            ok[0] = 1 if pf.lib.pffftb_nccl_unique_id(raw) == 0 else 0
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idd = idbuf.cuda()
+        dist.broadcast(idd, src=0)
+        dist.broadcast(ok, src=0)
+        done = torch.zeros(1, device="cuda", dtype=torch.int32)
+        if int(ok.item()) == 1 and os.environ.get("PFFFT_B200_BENCH_TORCH_BCAST") is None:
+            raw = (C.c_char * 128).from_buffer_copy(bytes(idd.cpu().numpy().tobytes()))
+            done[0] = 1 if pf.lib.pffftb_setup_broadcast_tables(setup.handle, raw, rank, world) == 0 else 0
+        dist.all_reduce(done, op=dist.ReduceOp.MIN)
+        if int(done.item()) == 1:
+            table_broadcast = "libpffft_b200 (ncclCommInitRank + ncclBroadcast root 0)"
+        else:                                  # NCCL not loadable from the library on this box: same broadcast through torch
+            tptr, tbytes = setup.tables()
+            tables = torch.as_tensor(_CudaMem(tptr, tbytes), device="cuda")
+            dist.broadcast(tables, src=0)
+            table_broadcast = "torch.distributed (library NCCL unavailable: %s)" % pf.last_error()
         torch.cuda.synchronize()
 
     # synthetic batch, generated on the device: uniform(-1,1), seed 1234 + rank
@@ -302,12 +357,13 @@ def main():
             "config": {"workload": "C2: N=1024 complex fp32 fwd+inv (pffft_transform_ordered semantics), batch=%d per GPU" % batch,
                        "global_batch": world * batch, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (%.1f GiB per pass, fwd x->y, inv y->z)" % (batch * 8192 / 2**30),
-                       "kernel": setup.kernel},
+                       "kernel": setup.kernel, "table_broadcast": table_broadcast},
             "gflops": value * FLOPS_PER_FFT / 1e9,
             "gbs_algorithmic": value * BYTES_PER_FFT / 1e9,
             "roofline": {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
                          "traffic": NCU_DRAM_BYTES_PER_FFT * batch if "ldg" in setup.kernel else None,
-                         "traffic_source": "profiles/r01_ncu_full_c1024.txt (ncu --set full, per-transform DRAM bytes x this launch's transforms)",
+                         "traffic_kind": "static",
+                         "traffic_source": "profiles/r01_ncu_full_c1024.txt (ncu --set full of this unchanged kernel: per-transform DRAM bytes x this launch's transforms; not measured in this run)",
                          "kernel": setup.kernel + " (forward launch, %d transforms)" % batch,
                          "algorithmic_bytes_per_launch": batch * BYTES_PER_FFT, "ms_per_launch": fwd_ms,
                          "peak_source": peak_src,

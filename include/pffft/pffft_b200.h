@@ -69,13 +69,62 @@ PFFFT_EXPORT int pffftb_set_stream(PFFFT_Setup *setup, void *cuda_stream);
 PFFFT_EXPORT int pffftdb_set_stream(PFFFTD_Setup *setup, void *cuda_stream);
 PFFFT_EXPORT int pffastconvb_set_stream(PFFASTCONV_Setup *setup, void *cuda_stream);
 
-/* ---- multi-GPU: one process per GPU, batch sharded, tables broadcast once ---- */
+/* ---- streaming and partitioned convolution (callers of pffastconv_apply / pffft_zconvolve_accumulate) ---- */
+/* Stateful form of pffastconv_apply's contract ("returns the number of produced samples; feed the rest again", ref
+   include/pffft/pffastconv.h:160-171): the setup keeps the unconsumed tail of the stream ON THE DEVICE between calls.
+   push: appends cplxInputLen (complex) samples, writes the outputs of every block that became complete and returns their
+   count (<= outputCapacity, else an error); flush: outputs for everything fed so far, including the partial last block
+   (applyFlush = 1); the last filterLen-1 samples stay pending so the stream may continue.  Any chunking followed by one
+   flush produces bit-identical samples to ONE pffastconv_apply(flush=1) over the whole stream.  Host or device pointers;
+   returns -1 on error. */
+PFFFT_EXPORT int pffastconvb_push(PFFASTCONV_Setup *setup, const float *input, int cplxInputLen, float *output, int outputCapacity);
+PFFFT_EXPORT int pffastconvb_flush(PFFASTCONV_Setup *setup, float *output, int outputCapacity);
+PFFFT_EXPORT int pffastconvb_pending(const PFFASTCONV_Setup *setup);   /* samples waiting for more input */
+PFFFT_EXPORT void pffastconvb_reset(PFFASTCONV_Setup *setup);          /* forget the pending samples (new stream) */
+
+/* Uniformly partitioned overlap-save convolution for LONG real filters with low latency: taps in partitions of partLen (a
+   power of two >= 16), transforms of 2*partLen points, pffft_zconvolve_accumulate as the inner loop (ref pffft.h:182-195)
+   fused over the partitions.  Output convention of pffastconv: y[n] = sum_j x[n+j]*taps[filterLen-1-j], n in [0, len-filterLen].
+   apply returns the number of outputs written (0 when len < filterLen), < 0 on error; host or device pointers. */
+typedef struct PFFASTCONVB_Partitioned PFFASTCONVB_Partitioned;
+PFFFT_EXPORT PFFASTCONVB_Partitioned *pffastconvb_partitioned_new(const float *taps, int filterLen, int partLen);
+PFFFT_EXPORT void pffastconvb_partitioned_destroy(PFFASTCONVB_Partitioned *c);
+PFFFT_EXPORT long long pffastconvb_partitioned_apply(PFFASTCONVB_Partitioned *c, const float *input, long long len, float *output);
+PFFFT_EXPORT int pffastconvb_partitioned_partitions(const PFFASTCONVB_Partitioned *c);
+PFFFT_EXPORT int pffastconvb_partitioned_set_stream(PFFASTCONVB_Partitioned *c, void *cuda_stream);
+
+/* ---- multi-GPU: the batch is sharded over the GPUs of one node, the plan tables are broadcast ONCE over
+   NCCL / NVLink, and nothing else crosses GPUs (every transform is independent, ref pffft.h:102-106) ---- */
 /* Device address and size of the plan's twiddle/rotation tables (the analogue of the reference's
-   PFFFT_Setup::data, pffft_priv_impl.h:1085-1103).  Rank 0 builds them; the other ranks overwrite
-   theirs with one ncclBroadcast(root 0) over NVLink so every GPU uses bit-identical tables.
-   No other inter-GPU traffic exists on this path. */
+   PFFFT_Setup::data, pffft_priv_impl.h:1085-1103). */
 PFFFT_EXPORT int pffftb_setup_tables(PFFFT_Setup *setup, void **device_ptr, size_t *nbytes);
 PFFFT_EXPORT int pffftdb_setup_tables(PFFFTD_Setup *setup, void **device_ptr, size_t *nbytes);
+
+/* (a) ONE PROCESS, ALL GPUS.  pffftb_multi_new builds one plan per GPU (ngpus <= 0: every visible device), creates the
+   communicators with ncclCommInitAll and overwrites the tables of GPUs 1.. with GPU 0's by one ncclBroadcast (root 0), each
+   GPU on its own stream, so all GPUs use bit-identical tables.  NCCL is loaded at run time (libnccl.so.2); when it is
+   absent the same broadcast is done with cudaMemcpyPeer and pffftb_multi_broadcast_backend() says so. */
+typedef struct PFFFTB_Multi PFFFTB_Multi;
+PFFFT_EXPORT PFFFTB_Multi *pffftb_multi_new(int N, pffft_transform_t transform, int ngpus);
+PFFFT_EXPORT void pffftb_multi_destroy(PFFFTB_Multi *m);
+PFFFT_EXPORT int pffftb_multi_ngpus(const PFFFTB_Multi *m);
+PFFFT_EXPORT PFFFT_Setup *pffftb_multi_setup(PFFFTB_Multi *m, int gpu);        /* the plan living on GPU `gpu` */
+PFFFT_EXPORT const char *pffftb_multi_broadcast_backend(const PFFFTB_Multi *m); /* "nccl" or "memcpy_peer" */
+/* HOST pointers: contiguous ranges [g*batch/G, (g+1)*batch/G) go to GPU g, each through that plan's three-stream pipeline
+   driven by its own host thread; returns when `output` is complete. */
+PFFFT_EXPORT int pffftb_multi_transform_batch(PFFFTB_Multi *m, const float *input, float *output, size_t batch,
+                                              pffft_direction_t direction, int ordered);
+/* DEVICE-resident shards: input[g]/output[g] are device pointers on GPU g holding batch[g] transforms; enqueued on every
+   GPU's plan stream, returns at once; pffftb_multi_synchronize waits for all of them. */
+PFFFT_EXPORT int pffftb_multi_transform_shards(PFFFTB_Multi *m, const float *const *input, float *const *output,
+                                               const size_t *batch, pffft_direction_t direction, int ordered);
+PFFFT_EXPORT int pffftb_multi_synchronize(PFFFTB_Multi *m);
+
+/* (b) ONE PROCESS PER GPU (torchrun, MPI): rank 0 calls pffftb_nccl_unique_id and ships the 128 bytes to the other ranks
+   by any means; every rank then calls pffftb_setup_broadcast_tables with the same id -- ncclCommInitRank + one
+   ncclBroadcast(root 0) of the tables inside the library. */
+PFFFT_EXPORT int pffftb_nccl_unique_id(void *id128);
+PFFFT_EXPORT int pffftb_setup_broadcast_tables(PFFFT_Setup *setup, const void *id128, int rank, int nranks);
 
 /* ---- diagnostics ---- */
 PFFFT_EXPORT const char *pffftb_last_error(void);            /* thread-local, "" when none */

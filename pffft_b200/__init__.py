@@ -45,7 +45,15 @@ EXPORTED_SYMBOLS = (
      "pffftb_zconvolve_batch", "pffftdb_zconvolve_batch", "pffftb_floats_per_transform",
      "pffftdb_doubles_per_transform", "pffftb_setup_device", "pffftb_setup_kernel", "pffftdb_setup_kernel",
      "pffftb_set_stream", "pffftdb_set_stream", "pffastconvb_set_stream", "pffftb_setup_tables",
-     "pffftdb_setup_tables", "pffftb_last_error", "pffftb_launch_count", "pffftb_device_synchronize"])
+     "pffftdb_setup_tables", "pffftb_last_error", "pffftb_launch_count", "pffftb_device_synchronize",
+     # streaming / partitioned convolution under the boundary
+     "pffastconvb_push", "pffastconvb_flush", "pffastconvb_pending", "pffastconvb_reset",
+     "pffastconvb_partitioned_new", "pffastconvb_partitioned_destroy", "pffastconvb_partitioned_apply",
+     "pffastconvb_partitioned_partitions", "pffastconvb_partitioned_set_stream",
+     # multi-GPU
+     "pffftb_multi_new", "pffftb_multi_destroy", "pffftb_multi_ngpus", "pffftb_multi_setup",
+     "pffftb_multi_broadcast_backend", "pffftb_multi_transform_batch", "pffftb_multi_transform_shards",
+     "pffftb_multi_synchronize", "pffftb_nccl_unique_id", "pffftb_setup_broadcast_tables"])
 
 _vp = C.c_void_p
 
@@ -93,6 +101,25 @@ _proto("pffastconv_malloc", _vp, [C.c_size_t])
 _proto("pffastconv_free", None, [_vp])
 _proto("pffastconv_simd_size", C.c_int, [])
 _proto("pffastconvb_set_stream", C.c_int, [_vp, _vp])
+_proto("pffastconvb_push", C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int])
+_proto("pffastconvb_flush", C.c_int, [_vp, _vp, C.c_int])
+_proto("pffastconvb_pending", C.c_int, [_vp])
+_proto("pffastconvb_reset", None, [_vp])
+_proto("pffastconvb_partitioned_new", _vp, [_vp, C.c_int, C.c_int])
+_proto("pffastconvb_partitioned_destroy", None, [_vp])
+_proto("pffastconvb_partitioned_apply", C.c_longlong, [_vp, _vp, C.c_longlong, _vp])
+_proto("pffastconvb_partitioned_partitions", C.c_int, [_vp])
+_proto("pffastconvb_partitioned_set_stream", C.c_int, [_vp, _vp])
+_proto("pffftb_multi_new", _vp, [C.c_int, C.c_int, C.c_int])
+_proto("pffftb_multi_destroy", None, [_vp])
+_proto("pffftb_multi_ngpus", C.c_int, [_vp])
+_proto("pffftb_multi_setup", _vp, [_vp, C.c_int])
+_proto("pffftb_multi_broadcast_backend", C.c_char_p, [_vp])
+_proto("pffftb_multi_transform_batch", C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int])
+_proto("pffftb_multi_transform_shards", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t), C.c_int, C.c_int])
+_proto("pffftb_multi_synchronize", C.c_int, [_vp])
+_proto("pffftb_nccl_unique_id", C.c_int, [_vp])
+_proto("pffftb_setup_broadcast_tables", C.c_int, [_vp, _vp, C.c_int, C.c_int])
 
 
 def ptr(a):
@@ -323,3 +350,90 @@ class FastConv:
     def apply(self, x, y, length, flush):
         """x, y: numpy arrays or torch CUDA tensors; length in (complex) samples; returns samples produced"""
         return lib.pffastconv_apply(self.handle, ptr(x), int(length), ptr(y), int(flush))
+
+    # stateful stream (include/pffft/pffft_b200.h: pffastconvb_push / _flush)
+    def push(self, x, length, y, capacity):
+        n = lib.pffastconvb_push(self.handle, ptr(x), int(length), ptr(y), int(capacity))
+        if n < 0:
+            raise RuntimeError("pffastconvb_push failed: " + last_error())
+        return n
+
+    def flush(self, y, capacity):
+        n = lib.pffastconvb_flush(self.handle, ptr(y), int(capacity))
+        if n < 0:
+            raise RuntimeError("pffastconvb_flush failed: " + last_error())
+        return n
+
+    @property
+    def pending(self):
+        return lib.pffastconvb_pending(self.handle)
+
+    def reset(self):
+        lib.pffastconvb_reset(self.handle)
+
+
+class PartitionedConv:
+    """owns a PFFASTCONVB_Partitioned (uniformly partitioned overlap-save, include/pffft/pffft_b200.h)"""
+
+    def __init__(self, taps, part_len):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.filter_len = taps.size
+        self.handle = lib.pffastconvb_partitioned_new(taps.ctypes.data, taps.size, int(part_len))
+        if not self.handle:
+            raise ValueError("pffastconvb_partitioned_new failed: " + last_error())
+        self.partitions = lib.pffastconvb_partitioned_partitions(self.handle)
+
+    def apply(self, x, y, length):
+        n = lib.pffastconvb_partitioned_apply(self.handle, ptr(x), int(length), ptr(y))
+        if n < 0:
+            raise RuntimeError("pffastconvb_partitioned_apply failed: " + last_error())
+        return int(n)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            try:
+                lib.pffastconvb_partitioned_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+
+class Multi:
+    """owns a PFFFTB_Multi: one plan per GPU of the node, tables broadcast once over NCCL (single process)"""
+
+    def __init__(self, N, transform, ngpus=0):
+        self.handle = lib.pffftb_multi_new(int(N), int(transform), int(ngpus))
+        if not self.handle:
+            raise ValueError("pffftb_multi_new failed: " + last_error())
+        self.ngpus = lib.pffftb_multi_ngpus(self.handle)
+        self.backend = lib.pffftb_multi_broadcast_backend(self.handle).decode()
+        self.per = int(N) if transform == PFFFT_REAL else 2 * int(N)
+
+    def setup(self, gpu):
+        return lib.pffftb_multi_setup(self.handle, int(gpu))
+
+    def transform_batch(self, x, out, batch, direction, ordered=1):
+        _check(lib.pffftb_multi_transform_batch(self.handle, ptr(x), ptr(out), int(batch), int(direction), int(ordered)),
+               "multi_transform_batch")
+
+    def transform_shards(self, xs, outs, batches, direction, ordered=1):
+        n = self.ngpus
+        X = (_vp * n)(*[ptr(x) for x in xs]); O = (_vp * n)(*[ptr(o) for o in outs]); Bn = (C.c_size_t * n)(*[int(b) for b in batches])
+        _check(lib.pffftb_multi_transform_shards(self.handle, X, O, Bn, int(direction), int(ordered)), "multi_transform_shards")
+
+    def synchronize(self):
+        _check(lib.pffftb_multi_synchronize(self.handle), "multi_synchronize")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            try:
+                lib.pffftb_multi_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+    def __del__(self):
+        self.close()

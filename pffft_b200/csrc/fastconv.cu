@@ -37,6 +37,11 @@ struct PFFASTCONV_Setup {
   // piece c+1, the kernel of piece c and the D2H copy of piece c-1 overlap (PCIe is full duplex)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t h2d_done[3] = {nullptr, nullptr, nullptr};
+  // stateful stream (pffastconvb_push / _flush): the unconsumed tail of the stream lives on the device between calls
+  float* d_carry = nullptr;      // capacity 2*Nfft floats (fewer than Nfft samples ever stay pending)
+  long long carry = 0;           // pending (complex) samples
+  float* d_stage = nullptr; size_t stage_elems = 0;     // [carry | new input] of one push
+  float* d_sout = nullptr;  size_t sout_elems = 0;      // device-side outputs of a host-pointer push
 };
 
 namespace {
@@ -200,6 +205,9 @@ PFFASTCONV_EXPORT void pffastconv_destroy_setup(PFFASTCONV_Setup* s) {
   if (s->d_spec) cudaFree(s->d_spec);
   if (s->d_x) cudaFree(s->d_x);
   if (s->d_y) cudaFree(s->d_y);
+  if (s->d_carry) cudaFree(s->d_carry);
+  if (s->d_stage) cudaFree(s->d_stage);
+  if (s->d_sout) cudaFree(s->d_sout);
   for (int k = 0; k < 3; ++k) { if (s->hs[k]) cudaStreamDestroy(s->hs[k]); if (s->h2d_done[k]) cudaEventDestroy(s->h2d_done[k]); }
   pffft_destroy_setup(s->st);
   delete s;
@@ -313,6 +321,51 @@ PFFASTCONV_EXPORT int pffastconv_apply(PFFASTCONV_Setup* s, const float* input, 
   if (cudaGetLastError() != cudaSuccess) return 0;
   return (int)(bp.produced / cplxFactor);                      // ref :201, :262
 }
+
+// ---- stateful stream: the caller of pffastconv_apply's "re-feed what was not consumed" contract
+// (include/pffft/pffastconv.h:160-171; src/pffastconv.c:201, :262) moved under the boundary.  Blocks of successive pushes
+// start at multiples of the block stride counted from the beginning of the stream -- exactly where one call over the whole
+// stream puts them -- so any chunking followed by one flush yields bit-identical samples.
+static int stream_step(PFFASTCONV_Setup* s, const float* input, long long n, float* output, long long out_capacity, int flush) {
+  const int w = (s->flags & PFFASTCONV_CPLX_INP_OUT) ? 2 : 1;              // floats per (complex) sample
+  const bool dout = output && pf::ptr_is_device(output);
+  if (n > 0 && pf::ptr_is_device(input) != dout) { pf::set_error_msg("pffastconvb_push: input and output must both be host or both be device pointers"); return -1; }
+  const long long total = s->carry + n;
+  if (total > 0x7fffffffLL) { pf::set_error_msg("pffastconvb_push: more than 2^31 pending samples"); return -1; }
+  cudaStream_t st = s->stream;
+  if (!s->d_carry && cudaMalloc((void**)&s->d_carry, (size_t)2 * s->Nfft * sizeof(float) + 64) != cudaSuccess) { pf::set_error("pffastconvb_push: carry buffer", cudaGetLastError()); return -1; }
+  if (grow(&s->d_stage, &s->stage_elems, (size_t)total * w + 8)) return -1;
+  if (s->carry && cudaMemcpyAsync(s->d_stage, s->d_carry, (size_t)s->carry * w * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+  if (n > 0 && cudaMemcpyAsync(s->d_stage + s->carry * w, input, (size_t)n * w * sizeof(float), cudaMemcpyDefault, st) != cudaSuccess) { pf::set_error("pffastconvb_push: staging copy", cudaGetLastError()); return -1; }
+  // how many samples this step will produce (same algebra as pffastconv_apply)
+  const int cplxFactor = (w == 2 && (s->flags & PFFASTCONV_CPLX_SINGLE_FFT)) ? 2 : 1;
+  const BlockPlan bp = plan_blocks((long long)cplxFactor * total, s->Nfft, s->filterLen, flush, cplxFactor == 2);
+  const long long produced = bp.produced / cplxFactor;
+  if (produced > out_capacity) { pf::set_error_msg("pffastconvb_push: output capacity too small for the samples this call produces"); return -1; }
+  if (produced > 0) {
+    float* dy = output;
+    if (!dout) { if (grow(&s->d_sout, &s->sout_elems, (size_t)produced * w + 8)) return -1; dy = s->d_sout; }
+    const int got = pffastconv_apply(s, s->d_stage, (int)total, dy, flush);
+    if (got != (int)produced) { if (!*pffftb_last_error()) pf::set_error_msg("pffastconvb_push: block algebra mismatch"); return -1; }
+    if (!dout && cudaMemcpyAsync(output, dy, (size_t)produced * w * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) { pf::set_error("pffastconvb_push: D2H", cudaGetLastError()); return -1; }
+  }
+  const long long rest = total - produced;                                 // < Nfft after a step without flush; F-1 after a flush
+  if (rest * w > 2LL * s->Nfft) { pf::set_error_msg("pffastconvb_push: internal carry overflow"); return -1; }
+  if (rest > 0 && cudaMemcpyAsync(s->d_carry, s->d_stage + produced * w, (size_t)rest * w * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+  s->carry = rest;
+  if (!dout && cudaStreamSynchronize(st) != cudaSuccess) { pf::set_error("pffastconvb_push: synchronize", cudaGetLastError()); return -1; }
+  return (int)produced;
+}
+PFFFT_EXPORT int pffastconvb_push(PFFASTCONV_Setup* s, const float* input, int cplxInputLen, float* output, int outputCapacity) {
+  if (!s || cplxInputLen < 0 || (cplxInputLen > 0 && !input)) { pf::set_error_msg("pffastconvb_push: bad argument"); return -1; }
+  return stream_step(s, input, cplxInputLen, output, outputCapacity, 0);
+}
+PFFFT_EXPORT int pffastconvb_flush(PFFASTCONV_Setup* s, float* output, int outputCapacity) {
+  if (!s) { pf::set_error_msg("pffastconvb_flush: bad argument"); return -1; }
+  return stream_step(s, nullptr, 0, output, outputCapacity, 1);
+}
+PFFFT_EXPORT int pffastconvb_pending(const PFFASTCONV_Setup* s) { return s ? (int)s->carry : 0; }
+PFFFT_EXPORT void pffastconvb_reset(PFFASTCONV_Setup* s) { if (s) s->carry = 0; }
 
 PFFASTCONV_EXPORT void* pffastconv_malloc(size_t nb) { return pffft_aligned_malloc(nb); }
 PFFASTCONV_EXPORT void pffastconv_free(void* p) { pffft_aligned_free(p); }

@@ -29,16 +29,27 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
+// resident CTAs per SM the register budget is sized for.  float: 3 (80 registers, some spilled loop scalars) or, with
+// PFFFT_B200_TS_MINB=2, 2 (128 registers); double: 2 (128 registers), no prefetch buffer
 template <typename T> struct TsKernels {
-  static constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
-  static auto fwd() { return k_ts_pipeline<T, -1, MINB>; }
-  static auto bwd() { return k_ts_pipeline<T, +1, MINB>; }
+  static constexpr bool kPrefetch = sizeof(T) == 4;
+  static constexpr size_t kSmem = (kPrefetch ? 2 : 1) * (size_t)16 * 256 * sizeof(cpx<T>);
+  static bool two() { static const bool v = getenv("PFFFT_B200_TS_MINB") && atoi(getenv("PFFFT_B200_TS_MINB")) == 2; return v; }
+  using Kern = void (*)(const TsParams<T>);
+  static Kern fwd() {
+    if constexpr (sizeof(T) == 4) return two() ? (Kern)k_ts_pipeline<T, -1, 2, true> : (Kern)k_ts_pipeline<T, -1, 3, true>;
+    else return (Kern)k_ts_pipeline<T, -1, 2, false>;
+  }
+  static Kern bwd() {
+    if constexpr (sizeof(T) == 4) return two() ? (Kern)k_ts_pipeline<T, +1, 2, true> : (Kern)k_ts_pipeline<T, +1, 3, true>;
+    else return (Kern)k_ts_pipeline<T, +1, 2, false>;
+  }
 };
 
 template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
   static PerDeviceInt attr_f, attr_b;
-  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), 16 * 256 * sizeof(cpx<T>)); if (rc) return rc; }
-  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), 16 * 256 * sizeof(cpx<T>)); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), TsKernels<T>::kSmem); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), TsKernels<T>::kSmem); if (rc) return rc; }
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
   if (n < 1) n = 1;
@@ -71,7 +82,7 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   int amax = 0; long long group = 0;
   for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
   (void)amax;
-  h->smem = (size_t)16 * 256 * csz;                             // one work item = up to 16 columns x 256 points (or G tiles of 16 x 16A)
+  h->smem = dbl ? TsKernels<double>::kSmem : TsKernels<float>::kSmem;                             // exchange tile + prefetch buffer, each one work item = 16 columns x 256 points (or G tiles of 16 x 16A)
   bool ok = (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
   ok = ok && (dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h));
   // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
@@ -124,6 +135,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   for (long long b0 = 0; b0 < batch; b0 += max_batch) {
     const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
     P.in = in + b0 * 2LL * h->Nc; P.out = out + b0 * 2LL * h->Nc; P.batch = nb;
+    P.in_aligned16 = (reinterpret_cast<uintptr_t>(P.in) & 15) == 0 ? 1 : 0;
     const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));

@@ -62,6 +62,7 @@ template <typename T> struct TsParams {
   int N, Nc;
   int nstages, lag, ring_slots, group_items;
   unsigned total_items;
+  int in_aligned16;                 // user input 16-byte aligned (cp.async prefetch of the first pass)
   TsStage st[kTsMaxStages];
 };
 
@@ -91,16 +92,24 @@ template <int A, bool FIRST> PF_HD int ts_tile_idx(int ka, int q, int j) {
 }
 
 // ---- phase 1 (both kinds): thread t -> column j = t & 15 of tile grp = (t >> 4) / A, sub-sequence q = (t >> 4) % A
+// `staged` != nullptr: the item's input was prefetched into shared memory as [tile grp][row n][16 columns]
 template <int A, bool FIRST, int SIGN, typename T>
-PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile) {
+PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile,
+                     const cpx<T>* staged = nullptr) {
   using S = TsShape<A>;
   const int j = t & 15, qq = t >> 4, q = qq % A, grp = qq / A;
   const int bg = b0 + 16 * grp;
   if (grp >= S::G || bg >= m) return;
   cpx<T> v[16];
-  const cpx<T>* c = src + bg + j + (long long)m * q;
+  if (staged) {
+    const cpx<T>* c = staged + (grp * S::R + q) * 16 + j;
 #pragma unroll
-  for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
+    for (int p = 0; p < 16; ++p) v[p] = c[(A * brev4(p)) * 16];
+  } else {
+    const cpx<T>* c = src + bg + j + (long long)m * q;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
+  }
   reg_fft<16, SIGN>(v);
   cpx<T>* tl = tile + grp * (16 * S::R);
   tl[ts_tile_idx<A, FIRST>(0, q, j)] = v[0];
@@ -158,17 +167,17 @@ PF_HD void ts_phase2_later(int t, int b0, int m, int s, const cpx<T>* tw, const 
 // one FFT work item, phase by phase (the kernel puts a CTA barrier between them; tests/emu steps them lane by lane)
 template <int A, bool FIRST, int SIGN, typename T>
 PF_HD void ts_item_phase(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
-                         const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
+                         const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile, const cpx<T>* staged = nullptr) {
   const int b0 = TsShape<A>::COLS * item;
-  if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile);
+  if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile, staged);
   else if (FIRST) ts_phase2_first<A, SIGN, T>(t, b0, st.m, tw, tile, dst);
   else ts_phase2_later<A, SIGN, T>(t, b0, st.m, st.s, tw, tile, dst);
 }
 template <bool FIRST, int SIGN, typename T>
 PF_HD void ts_item_phase_any(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
-                             const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
+                             const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile, const cpx<T>* staged = nullptr) {
   switch (st.A) {
-#define PF_TS(a) case a: ts_item_phase<a, FIRST, SIGN, T>(phase, t, item, st, src, dst, tw, twR, tile); break;
+#define PF_TS(a) case a: ts_item_phase<a, FIRST, SIGN, T>(phase, t, item, st, src, dst, tw, twR, tile, staged); break;
     PF_TS(1) PF_TS(2) PF_TS(3) PF_TS(4) PF_TS(5) PF_TS(6) PF_TS(8) PF_TS(9) PF_TS(10) PF_TS(12) PF_TS(15) PF_TS(16)
 #undef PF_TS
     default: break;
@@ -249,63 +258,145 @@ PF_D unsigned ts_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+PF_D unsigned ts_ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 PF_D void ts_wait_at_least(const unsigned* p, unsigned need) {
-  while (ts_ld_acquire(p) < need) __nanosleep(200);
+  while (ts_ld_acquire(p) < need) __nanosleep(100);
+}
+PF_D void ts_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only (.cg): ring data never enters L1
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+PF_D void ts_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// dependency counters of a live work item: `in_need` tiles of the producing stage, `free_need` tiles of the consuming
+// stage's previous occupant of the ring slot (nullptr pointers: no such dependency)
+struct TsDeps { const unsigned* in_ctr; unsigned in_need; const unsigned* free_ctr; unsigned free_need; unsigned* done; };
+template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, int stage, long long tr) {
+  const int slot = (int)(tr % P.ring_slots);
+  const unsigned gen = (unsigned)(tr / P.ring_slots);
+  unsigned* base = P.counters + kTsCounterBase + slot;
+  TsDeps d;
+  d.done = base + stage * P.ring_slots;
+  d.in_ctr = stage > 0 ? base + (stage - 1) * P.ring_slots : nullptr;
+  d.in_need = stage > 0 ? (gen + 1u) * (unsigned)P.st[stage - 1].tiles : 0u;
+  const bool fr = stage + 1 < P.nstages && gen > 0;
+  d.free_ctr = fr ? base + (stage + 1) * P.ring_slots : nullptr;
+  d.free_need = fr ? gen * (unsigned)P.st[stage + 1].tiles : 0u;
+  return d;
 }
 
-template <typename T, int SIGN, int MINB>
+// input of FFT work item (stage st, item) -> shared memory [tile grp][row n < R][16 columns], 16-byte cp.async chunks
+template <typename T>
+PF_D void ts_prefetch_item(int t, const TsStage& st, int item, const cpx<T>* src, cpx<T>* staging) {
+  constexpr int EPC = 16 / (int)sizeof(cpx<T>);                    // elements per 16-byte chunk: 2 (float), 1 (double)
+  constexpr int CPR = 16 / EPC;                                    // chunks per 16-column row
+  const int A = st.A, R = 16 * A, cols = ts_cols_for(A), G = cols / 16, m = st.m;
+  const int b0 = cols * item;
+  const int rows = G * R;                                          // <= 256
+  for (int c = t; c < rows * CPR; c += kTsThreads) {
+    const int row = c / CPR, h = c - row * CPR;
+    const int grp = row / R, n = row - grp * R;
+    const int bg = b0 + 16 * grp;
+    if (bg >= m) continue;
+    ts_cp_async16(staging + row * 16 + h * EPC, src + bg + (long long)m * n + h * EPC);
+  }
+}
+
+// The CTA loop is software-pipelined two tickets deep so that NO global round trip sits between two work items:
+//   * thread 0 holds ticket i+1 while item i runs and fetches ticket i+2 (atomic in flight during phase 1);
+//   * the dependency counters of item i+1 are read (relaxed) at the top of item i; when they are already satisfied --
+//     the normal case, the pipeline lag is sized for it -- the whole CTA PREFETCHES item i+1's input into a second
+//     shared-memory buffer with cp.async right after phase 1 of item i, so those loads overlap phase 2, the stores and
+//     the barriers of item i, and item i+1 starts without touching global memory;
+//   * only when the early look failed does item i+1 poll its counters at its own top (blocking waits are only ever on
+//     the OLDEST ticket a CTA holds, after everything older was signalled: the no-deadlock argument is unchanged).
+// PREFETCH = false (double: a second 64 KB buffer would leave one CTA per SM): same loop, inputs always read directly
+template <typename T, int SIGN, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
-  __shared__ unsigned s_ticket;
+  cpx<T>* staging = tile + 16 * 256;
+  __shared__ unsigned s_cur, s_next;
+  __shared__ int s_cur_pf, s_next_ok;
   const int t = threadIdx.x;
-  if (t == 0) s_ticket = atomicAdd(P.counters, 1u);
+  unsigned t_next2 = 0;
+  if (t == 0) { s_cur = atomicAdd(P.counters, 1u); s_next = atomicAdd(P.counters, 1u); s_cur_pf = 0; }
   __syncthreads();
-  unsigned cur = s_ticket;
+  unsigned cur = s_cur;
   while (cur < P.total_items) {
-    int stage, item; long long tr;
-    const bool live = ts_decode(P, cur, &stage, &tr, &item);
-    const TsStage& st = P.st[stage];
-    unsigned next = 0;
-    unsigned* done = nullptr;
+    // (decoded ticket fields are recomputed where they are needed instead of being kept live across the FFT bodies)
+    int look_ok = 0;
     if (t == 0) {
-      next = atomicAdd(P.counters, 1u);                       // next ticket: in flight while this item is processed
-      if (live) {
-        const int slot = (int)(tr % P.ring_slots);
-        const unsigned gen = (unsigned)(tr / P.ring_slots);
-        unsigned* base = P.counters + kTsCounterBase + slot;
-        done = base + stage * P.ring_slots;
-        if (stage > 0)                                        // input complete
-          ts_wait_at_least(base + (stage - 1) * P.ring_slots, (gen + 1u) * (unsigned)P.st[stage - 1].tiles);
-        if (stage + 1 < P.nstages && gen > 0)                 // ring slot free: its previous occupant was consumed
-          ts_wait_at_least(base + (stage + 1) * P.ring_slots, gen * (unsigned)P.st[stage + 1].tiles);
+      t_next2 = atomicAdd(P.counters, 1u);                     // ticket i+2: in flight while this item is processed
+      int stage, item; long long tr;
+      if (ts_decode(P, cur, &stage, &tr, &item) && !s_cur_pf) { // (a prefetched item had its counters checked already)
+        const TsDeps d = ts_deps(P, stage, tr);
+        if (d.in_ctr) ts_wait_at_least(d.in_ctr, d.in_need);
+        if (d.free_ctr) ts_wait_at_least(d.free_ctr, d.free_need);
       }
+      // early, non-blocking look at the next item's counters
+      const unsigned nxt = s_next;
+      int nstage, nitem; long long ntr;
+      if (nxt < P.total_items && ts_decode(P, nxt, &nstage, &ntr, &nitem)) {
+        const TsStage& nst = P.st[nstage];
+        if (PREFETCH && (nst.kind == TS_FIRST || nst.kind == TS_LATER) && (nst.src != 0 || P.in_aligned16)) {
+          const TsDeps nd = ts_deps(P, nstage, ntr);
+          const unsigned li = nd.in_ctr ? ts_ld_relaxed(nd.in_ctr) : 0u;
+          const unsigned lf = nd.free_ctr ? ts_ld_relaxed(nd.free_ctr) : 0u;
+          look_ok = (!nd.in_ctr || li >= nd.in_need) && (!nd.free_ctr || lf >= nd.free_need);
+        }
+      }
+    }
+    const int cur_pf = s_cur_pf;
+    if (cur_pf) ts_cp_async_wait_all();
+    __syncthreads();
+    {
+      int stage, item; long long tr;
+      if (ts_decode(P, cur, &stage, &tr, &item)) {
+        const TsStage& st = P.st[stage];
+        if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, t, item, st, ts_src(P, st.src, tr), (cpx<T>*)nullptr, P.tw, P.twR, tile, cur_pf ? staging : nullptr);
+        else if (st.kind == TS_LATER) ts_item_phase_any<false, SIGN, T>(0, t, item, st, ts_src(P, st.src, tr), (cpx<T>*)nullptr, P.tw, P.twR, tile, cur_pf ? staging : nullptr);
+      }
+    }
+    if (t == 0) {
+      if (look_ok) __threadfence();                             // acquire side of the relaxed reads above
+      s_next_ok = look_ok;
     }
     __syncthreads();
-    if (live) {
-      const cpx<T>* src = ts_src(P, st.src, tr);
-      cpx<T>* dst = ts_dst(P, st.dst, tr);
-      if (st.kind == TS_FIRST) {
-        ts_item_phase_any<true, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile);
-        __syncthreads();
-        ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-      } else if (st.kind == TS_LATER) {
-        ts_item_phase_any<false, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile);
-        __syncthreads();
-        ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-      } else if (st.kind == TS_SMALL) {
-        ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
-      } else if (st.kind == TS_PRE) {
-        ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
-      } else {
-        ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+    const int next_ok = s_next_ok;
+    if (next_ok) {                                              // staging was consumed in phase 1 (barrier above)
+      int nstage, nitem; long long ntr;
+      ts_decode(P, s_next, &nstage, &ntr, &nitem);
+      ts_prefetch_item<T>(t, P.st[nstage], nitem, ts_src(P, P.st[nstage].src, ntr), staging);
+    }
+    unsigned* done = nullptr;
+    {
+      int stage, item; long long tr;
+      if (ts_decode(P, cur, &stage, &tr, &item)) {
+        const TsStage& st = P.st[stage];
+        const cpx<T>* src = ts_src(P, st.src, tr);
+        cpx<T>* dst = ts_dst(P, st.dst, tr);
+        if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+        else if (st.kind == TS_LATER) ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+        else if (st.kind == TS_SMALL) ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
+        else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+        else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+        if (t == 0) done = ts_deps(P, stage, tr).done;
       }
     }
-    if (t == 0) s_ticket = next;
     __syncthreads();                                          // every store of the item is issued; tile is free again
-    if (t == 0 && live) { __threadfence(); atomicAdd(done, 1u); }
-    cur = s_ticket;
+    if (t == 0) {
+      if (done) { __threadfence(); atomicAdd(done, 1u); }
+      s_cur = s_next; s_cur_pf = next_ok; s_next = t_next2;
+    }
+    __syncthreads();
+    cur = s_cur;
   }
+  ts_cp_async_wait_all();
 }
 #endif  // __CUDACC__
 

@@ -102,11 +102,12 @@ def test_no_cpu_fallback_without_a_gpu(pf):
     assert "CUDA" in pf.last_error() or "device" in pf.last_error()
 
 
-def test_c_example_compiles_as_c99_against_the_headers(tmp_path):
-    """examples/batch_c2c.c: the batched extension is usable from plain C (prototypes only; running needs a GPU)"""
+@pytest.mark.parametrize("name", ["batch_c2c", "multi_gpu_c2c"])
+def test_c_example_compiles_as_c99_against_the_headers(tmp_path, name):
+    """examples/*.c: the batched and multi-GPU extensions are usable from plain C (prototypes only; running needs a GPU)"""
     import subprocess
-    src = os.path.join(ROOT, "examples", "batch_c2c.c")
-    obj = str(tmp_path / "batch_c2c.o")
+    src = os.path.join(ROOT, "examples", name + ".c")
+    obj = str(tmp_path / (name + ".o"))
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include", "pffft"), "-c", src, "-o", obj],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
