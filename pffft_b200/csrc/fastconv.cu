@@ -83,26 +83,29 @@ using pfplan::BlockPlan;
 using pfplan::plan_blocks;
 
 // fused path: one launch for every block of the stream (Nfft = 512*C, C in {2,4,8,16})
-template <int C>
+// ES = 1: one real stream; ES = 2: interleaved complex stream, both planes in one launch (no split / merge copies)
+template <int C, int ES = 1>
 int launch_fused(PFFASTCONV_Setup* s, const float* x, long long inputLen, float* y, const BlockPlan& bp, cudaStream_t st) {
   constexpr int MINB = (C == 16) ? 3 : 1024 / (16 * C);
-  auto kern = pf::k_fastconv_fused<C, MINB>;
+  auto kern = pf::k_fastconv_fused<C, MINB, ES>;
   const size_t smem = 2 * (size_t)pf::K2<C>::NC * sizeof(pf::cf);
-  if (s->fused_ctas_per_sm == 0) {
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      pf::set_error("pffastconv: cudaFuncSetAttribute", cudaGetLastError()); return -1;
-    }
+  static pf::PerDeviceInt occ;                                   // per device: attribute set, then resident CTAs per SM
+  int arc = 0;
+  s->fused_ctas_per_sm = occ.get(s->device, [&]() -> int {
+    if (smem > 48 * 1024) arc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (arc) return -1;
     int per = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, 16 * C, smem);
-    s->fused_ctas_per_sm = per < 1 ? 1 : per;
-  }
+    return per < 1 ? 1 : per;
+  });
+  if (arc) { pf::set_error("pffastconv: cudaFuncSetAttribute", (cudaError_t)arc); return -1; }
   pf::FastconvParams p;
   p.x = x; p.y = y; p.input_len = inputLen; p.n_full = bp.n_full; p.stride = bp.stride;
   p.tail_out = bp.tail_off >= 0 ? bp.tail_out : 0;
   p.scale = s->scale; p.twr = s->tabs.twr; p.Hc = reinterpret_cast<const pf::cf*>(s->d_Hc);
   p.tw1 = s->tabs.tw1; p.tw2 = s->tabs.tw2;
   long long nblk = bp.n_full + (p.tail_out > 0 ? 1 : 0);
-  long long ctas = nblk;
+  long long ctas = nblk * ES;
   const long long cap = (long long)s->tabs.sm_count * s->fused_ctas_per_sm;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) return 0;
@@ -298,9 +301,19 @@ PFFASTCONV_EXPORT int pffastconv_apply(PFFASTCONV_Setup* s, const float* input, 
 
   if (!two_planes) {
     rc = conv_stream(s, dx, inputLen, dy, bp, st);
+  } else if (s->d_Hc && s->tabs.C && getenv("PFFFT_B200_CONV_SPLIT_PLANES") == nullptr) {
+    // two-FFT complex mode on the fused kernel: every (block, plane) pair is a work item of ONE launch; the planes are
+    // read and written in place in the interleaved streams
+    switch (s->tabs.C) {
+      case 2: rc = launch_fused<2, 2>(s, dx, inputLen, dy, bp, st); break;
+      case 4: rc = launch_fused<4, 2>(s, dx, inputLen, dy, bp, st); break;
+      case 8: rc = launch_fused<8, 2>(s, dx, inputLen, dy, bp, st); break;
+      default: rc = launch_fused<16, 2>(s, dx, inputLen, dy, bp, st); break;
+    }
   } else {
     const long long n = cplxInputLen;
-    const int thr = 256; long long g = (n + thr - 1) / thr; if (g > 148 * 16) g = 148 * 16;
+    const long long gcap = (long long)s->tabs.sm_count * 16;
+    const int thr = 256; long long g = (n + thr - 1) / thr; if (g > gcap) g = gcap;
     float* xr = x_planes; float* xi = x_planes + n;
     float* yr = y_planes; float* yi = y_planes + bp.produced;
     if (((uintptr_t)dx & 7) == 0) k_split<<<(int)g, thr, 0, st>>>(dx, xr, xi, n); else k_split_u<<<(int)g, thr, 0, st>>>(dx, xr, xi, n);
@@ -308,7 +321,7 @@ PFFASTCONV_EXPORT int pffastconv_apply(PFFASTCONV_Setup* s, const float* input, 
     rc = conv_stream(s, xr, inputLen, yr, bp, st);
     if (!rc) rc = conv_stream(s, xi, inputLen, yi, bp, st);
     if (!rc) {
-      const long long m = bp.produced; long long g2 = (m + thr - 1) / thr; if (g2 > 148 * 16) g2 = 148 * 16;
+      const long long m = bp.produced; long long g2 = (m + thr - 1) / thr; if (g2 > gcap) g2 = gcap;
       if (((uintptr_t)dy & 7) == 0) k_merge<<<(int)g2, thr, 0, st>>>(yr, yi, dy, m); else k_merge_u<<<(int)g2, thr, 0, st>>>(yr, yi, dy, m);
       pf::count_launch();
     }

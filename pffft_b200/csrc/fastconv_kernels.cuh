@@ -72,8 +72,29 @@ struct FastconvParams {
   const cpx<float>* tw2;
 };
 
+// forward pass 1 for one PLANE of an interleaved complex stream (ES = 2: sample n of the plane is base[2 n]): the two-FFT
+// complex mode of the reference (real and imaginary part convolved separately, src/pffastconv.c:212-247) without the
+// de-interleaving copies -- the plane is picked apart by the loads and woven back by the stores
+template <int C, typename T>
+PF_HD void fastconv_pass1_plane(int m, const T* base, long long avail, const cpx<T>* tw1, cpx<T>* tile) {
+  using K = K2<C>;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const long long e = 2LL * (m + K::BC * brev4(p));               // first sample of pair i
+    v[p] = mk<T>(e < avail ? base[2 * e] : T(0), e + 1 < avail ? base[2 * e + 2] : T(0));
+  }
+  reg_fft<16, -1>(v);
+  const int jb = m / C, jc = m % C;
+  tile[K::idx(0, jb, jc)] = v[0];
+#pragma unroll
+  for (int ka = 1; ka < 16; ++ka) tile[K::idx(ka, jb, jc)] = cmul_dir<-1>(v[ka], ldtab(tw1 + ka * K::BC + m));
+}
+
 #ifdef __CUDACC__
-template <int C, int MINB>
+// ES = 1: real stream.  ES = 2: interleaved complex stream, work item = (block, plane); x/y point at the complex samples,
+// input_len / stride / tail_out count complex samples.
+template <int C, int MINB, int ES = 1>
 __global__ void __launch_bounds__(16 * C, MINB) k_fastconv_fused(const FastconvParams p) {
   using K = K2<C>;
   constexpr int Nfft = 2 * K::NC;
@@ -86,17 +107,22 @@ __global__ void __launch_bounds__(16 * C, MINB) k_fastconv_fused(const FastconvP
   const cpx<float>* tw2 = p.tw2;
   const cpx<float>* twr = p.twr;
   const cpx<float>* Hc = p.Hc;
-  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+  for (long long w = blockIdx.x; w < nblk * ES; w += gridDim.x) {
     asm volatile("" : "+l"(tw1), "+l"(tw2), "+l"(twr), "+l"(Hc));   // keep table reads in the loop (see cta_kernels.cuh)
+    const long long b = (ES == 1) ? w : (w >> 1);
+    const int plane = (ES == 1) ? 0 : (int)(w & 1);                 // neighbouring CTAs take the two planes of one block
     const long long off = b * p.stride;
-    const float* ibase = p.x + off;
-    float* obase = p.y + off;
+    const float* ibase = p.x + ES * off + plane;
+    float* obase = p.y + ES * off + plane;
     const long long avail = p.input_len - off;
     const int out_count = (b < p.n_full) ? p.stride : p.tail_out;
     // ---- forward real FFT of the window
+    if (ES == 2) fastconv_pass1_plane<C, float>(t, ibase, avail, tw1, tile);
+    else {
     const bool vin = vec_aligned<float>(ibase);
     if (vin && avail >= (long long)Nfft) k2_pass1<C, L_R_TIME, -1, true, float>(t, ibase, Nfft, twr, avail, true, tw1, tile);
     else k2_pass1<C, L_R_TIME, -1, false, float>(t, ibase, Nfft, twr, avail, vin, tw1, tile);
+    }
     __syncthreads();
     k2_pass2<C, -1, float>(t, tw2, tile);
     __syncthreads();
@@ -121,7 +147,13 @@ __global__ void __launch_bounds__(16 * C, MINB) k_fastconv_fused(const FastconvP
 #pragma unroll
     for (int r = 0; r < 16 / C; ++r)
 #pragma unroll
-      for (int kc = 0; kc < C; ++kc) store_elem<S_R_TIME, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], Nfft, out_count, vok);
+      for (int kc = 0; kc < C; ++kc) {
+        if (ES == 2) {
+          const int e = 2 * k2_out_index<C>(t, r, kc);
+          if (e < out_count) obase[2 * e] = u[r * C + kc].x;
+          if (e + 1 < out_count) obase[2 * e + 2] = u[r * C + kc].y;
+        } else store_elem<S_R_TIME, float>(obase, k2_out_index<C>(t, r, kc), u[r * C + kc], Nfft, out_count, vok);
+      }
     // some threads may still be reading `tile` in pass 3 while others start the next block's pass 1
     __syncthreads();
   }

@@ -29,29 +29,33 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
-// resident CTAs per SM the register budget is sized for.  float: 3 (80 registers, some spilled loop scalars) or, with
-// PFFFT_B200_TS_MINB=2, 2 (128 registers); double: 2 (128 registers), no prefetch buffer
+// kernel shapes: (resident CTAs per SM the register budget is sized for, ticket slots, staged inputs).
+//   float : 2 CTAs x (8 consumer warps + producer), 2 staged items in flight per CTA, <= 113 registers   [default]
+//           PFFFT_B200_TS_SHAPE=1: 3 CTAs, 1 staged item (72 registers);  =2: 1 CTA, 4 staged items
+//   double: 1 CTA, 2 staged items (192 KB of shared memory, no spills);  PFFFT_B200_TS_SHAPE=1: 2 CTAs, inputs read directly
 template <typename T> struct TsKernels {
-  static constexpr bool kPrefetch = sizeof(T) == 4;
-  static constexpr size_t kSmem = (kPrefetch ? 2 : 1) * (size_t)16 * 256 * sizeof(cpx<T>);
-  static bool two() { static const bool v = getenv("PFFFT_B200_TS_MINB") && atoi(getenv("PFFFT_B200_TS_MINB")) == 2; return v; }
   using Kern = void (*)(const TsParams<T>);
-  static Kern fwd() {
-    if constexpr (sizeof(T) == 4) return two() ? (Kern)k_ts_pipeline<T, -1, 2, true> : (Kern)k_ts_pipeline<T, -1, 3, true>;
-    else return (Kern)k_ts_pipeline<T, -1, 2, false>;
+  static int shape() { static const int v = getenv("PFFFT_B200_TS_SHAPE") ? atoi(getenv("PFFFT_B200_TS_SHAPE")) : 0; return v; }
+  static size_t smem() {
+    const size_t item = (size_t)16 * 256 * sizeof(cpx<T>);
+    if constexpr (sizeof(T) == 8) return item * (shape() == 1 ? 1 : 3);
+    else return item * (shape() == 1 ? 2 : shape() == 2 ? 5 : 3);
   }
-  static Kern bwd() {
-    if constexpr (sizeof(T) == 4) return two() ? (Kern)k_ts_pipeline<T, +1, 2, true> : (Kern)k_ts_pipeline<T, +1, 3, true>;
-    else return (Kern)k_ts_pipeline<T, +1, 2, false>;
+  template <int SIGN> static Kern kern() {
+    if constexpr (sizeof(T) == 8) return shape() == 1 ? (Kern)k_ts_pipeline<T, SIGN, 2, 2, false> : (Kern)k_ts_pipeline<T, SIGN, 1, 2, true>;
+    else return shape() == 1 ? (Kern)k_ts_pipeline<T, SIGN, 3, 1, true> : shape() == 2 ? (Kern)k_ts_pipeline<T, SIGN, 1, 4, true>
+                                                                                       : (Kern)k_ts_pipeline<T, SIGN, 2, 2, true>;
   }
+  static Kern fwd() { return kern<-1>(); }
+  static Kern bwd() { return kern<+1>(); }
 };
 
 template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
   static PerDeviceInt attr_f, attr_b;
-  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), TsKernels<T>::kSmem); if (rc) return rc; }
-  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), TsKernels<T>::kSmem); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), TsKernels<T>::smem()); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), TsKernels<T>::smem()); if (rc) return rc; }
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads + 32, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
   if (n < 1) n = 1;
   h->grid = n * h->sm_count;
   return 0;
@@ -82,7 +86,7 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   int amax = 0; long long group = 0;
   for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
   (void)amax;
-  h->smem = dbl ? TsKernels<double>::kSmem : TsKernels<float>::kSmem;                             // exchange tile + prefetch buffer, each one work item = 16 columns x 256 points (or G tiles of 16 x 16A)
+  h->smem = dbl ? TsKernels<double>::smem() : TsKernels<float>::smem();                             // exchange tile + prefetch buffer, each one work item = 16 columns x 256 points (or G tiles of 16 x 16A)
   bool ok = (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
   ok = ok && (dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h));
   // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
@@ -140,7 +144,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
     const long long g = total < h->grid ? total : h->grid;
-    kern<<<(int)g, kTsThreads, h->smem, st>>>(P);
+    kern<<<(int)g, kTsThreads + 32, h->smem, st>>>(P);
     count_launch();
     PF_CUDA_OK(cudaGetLastError());
   }

@@ -233,12 +233,14 @@ PF_HD void ts_post_item(int t, int nthreads, int chunk, int mode, const cpx<T>* 
 }
 
 // ticket -> (stage, transform, tile); false when the slot is padding (pipeline fill / drain)
+// ST: the stage table (the kernel works on a shared-memory copy: dynamic indexing into the by-value parameter struct would
+// make the compiler copy it to local memory)
 template <typename T>
-PF_HD bool ts_decode(const TsParams<T>& P, unsigned ticket, int* stage, long long* tr, int* item) {
+PF_HD bool ts_decode(const TsParams<T>& P, const TsStage* ST, unsigned ticket, int* stage, long long* tr, int* item) {
   const unsigned g = ticket / (unsigned)P.group_items;
   int r = (int)(ticket - g * (unsigned)P.group_items);
   int i = 0;
-  while (i < P.nstages - 1 && r >= P.st[i].tiles) { r -= P.st[i].tiles; ++i; }
+  while (i < P.nstages - 1 && r >= ST[i].tiles) { r -= ST[i].tiles; ++i; }
   const long long t = (long long)g - (long long)i * P.lag;
   *stage = i; *tr = t; *item = r;
   return t >= 0 && t < P.batch;
@@ -258,145 +260,140 @@ PF_D unsigned ts_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-PF_D unsigned ts_ld_relaxed(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 PF_D void ts_wait_at_least(const unsigned* p, unsigned need) {
   while (ts_ld_acquire(p) < need) __nanosleep(100);
 }
-PF_D void ts_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only (.cg): ring data never enters L1
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+PF_D void ts_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-PF_D void ts_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+PF_D void ts_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+PF_D void ts_bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); static_assert(kTsThreads == 256, "consumer barrier width"); }
 
 // dependency counters of a live work item: `in_need` tiles of the producing stage, `free_need` tiles of the consuming
 // stage's previous occupant of the ring slot (nullptr pointers: no such dependency)
 struct TsDeps { const unsigned* in_ctr; unsigned in_need; const unsigned* free_ctr; unsigned free_need; unsigned* done; };
-template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, int stage, long long tr) {
+template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* ST, int stage, long long tr) {
   const int slot = (int)(tr % P.ring_slots);
   const unsigned gen = (unsigned)(tr / P.ring_slots);
   unsigned* base = P.counters + kTsCounterBase + slot;
   TsDeps d;
   d.done = base + stage * P.ring_slots;
   d.in_ctr = stage > 0 ? base + (stage - 1) * P.ring_slots : nullptr;
-  d.in_need = stage > 0 ? (gen + 1u) * (unsigned)P.st[stage - 1].tiles : 0u;
+  d.in_need = stage > 0 ? (gen + 1u) * (unsigned)ST[stage - 1].tiles : 0u;
   const bool fr = stage + 1 < P.nstages && gen > 0;
   d.free_ctr = fr ? base + (stage + 1) * P.ring_slots : nullptr;
-  d.free_need = fr ? gen * (unsigned)P.st[stage + 1].tiles : 0u;
+  d.free_need = fr ? gen * (unsigned)ST[stage + 1].tiles : 0u;
   return d;
 }
 
-// input of FFT work item (stage st, item) -> shared memory [tile grp][row n < R][16 columns], 16-byte cp.async chunks
-template <typename T>
-PF_D void ts_prefetch_item(int t, const TsStage& st, int item, const cpx<T>* src, cpx<T>* staging) {
-  constexpr int EPC = 16 / (int)sizeof(cpx<T>);                    // elements per 16-byte chunk: 2 (float), 1 (double)
-  constexpr int CPR = 16 / EPC;                                    // chunks per 16-column row
-  const int A = st.A, R = 16 * A, cols = ts_cols_for(A), G = cols / 16, m = st.m;
-  const int b0 = cols * item;
-  const int rows = G * R;                                          // <= 256
-  for (int c = t; c < rows * CPR; c += kTsThreads) {
-    const int row = c / CPR, h = c - row * CPR;
-    const int grp = row / R, n = row - grp * R;
-    const int bg = b0 + 16 * grp;
-    if (bg >= m) continue;
-    ts_cp_async16(staging + row * 16 + h * EPC, src + bg + (long long)m * n + h * EPC);
-  }
-}
-
-// The CTA loop is software-pipelined two tickets deep so that NO global round trip sits between two work items:
-//   * thread 0 holds ticket i+1 while item i runs and fetches ticket i+2 (atomic in flight during phase 1);
-//   * the dependency counters of item i+1 are read (relaxed) at the top of item i; when they are already satisfied --
-//     the normal case, the pipeline lag is sized for it -- the whole CTA PREFETCHES item i+1's input into a second
-//     shared-memory buffer with cp.async right after phase 1 of item i, so those loads overlap phase 2, the stores and
-//     the barriers of item i, and item i+1 starts without touching global memory;
-//   * only when the early look failed does item i+1 poll its counters at its own top (blocking waits are only ever on
-//     the OLDEST ticket a CTA holds, after everything older was signalled: the no-deadlock argument is unchanged).
-// PREFETCH = false (double: a second 64 KB buffer would leave one CTA per SM): same loop, inputs always read directly
-template <typename T, int SIGN, int MINB, bool PREFETCH>
-__global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
+// WARP-SPECIALISED pipeline.  8 consumer warps run the work items; a 9th PRODUCER warp owns everything that has global
+// latency in it and runs NBUF items ahead of them:
+//   producer: wait until input buffer b is free (mbarrier `empty`), take the next ticket (atomic), wait for the item's
+//             dependency counters (acquire polling -- it may block: the consumers finish and signal their current item
+//             without it, and every wait is on tickets handed out earlier, so the no-deadlock argument is unchanged),
+//             then stage the item's input -- rows of 16 columns = 128-byte runs -- into shared memory with 1-D TMA bulk
+//             copies (cp.async.bulk, SASS UBLKCP; through L2, never L1) whose completion the mbarrier `full` counts;
+//   consumers: wait on `full`, phase 1 out of shared memory, release the buffer, phase 2, stores, completion signal.
+// The consumers never wait for a ticket, a counter or (once the pipeline is primed) a load: NBUF items' loads per CTA are
+// in flight while the previous ones are being transformed.
+// NBUF = ticket slots the producer may run ahead; STAGE = each slot has an input buffer (false: consumers read their inputs
+// directly -- double precision, where a second 64 KB buffer would cost the second resident CTA)
+template <typename T, int SIGN, int MINB, int NBUF, bool STAGE>
+__global__ void __launch_bounds__(kTsThreads + 32, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
-  cpx<T>* staging = tile + 16 * 256;
-  __shared__ unsigned s_cur, s_next;
-  __shared__ int s_cur_pf, s_next_ok;
+  cpx<T>* inbuf = tile + 16 * 256;                              // NBUF buffers of one work item each
+  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF];
+  __shared__ unsigned slot_ticket[NBUF];
+  __shared__ int slot_staged[NBUF];
+  __shared__ TsStage ST[kTsMaxStages];
+  constexpr unsigned kEnd = 0xFFFFFFFFu;
+  constexpr uint32_t kRowBytes = 16 * sizeof(cpx<T>);
   const int t = threadIdx.x;
-  unsigned t_next2 = 0;
-  if (t == 0) { s_cur = atomicAdd(P.counters, 1u); s_next = atomicAdd(P.counters, 1u); s_cur_pf = 0; }
+  if (t == 0) {
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], kTsThreads); }
+    fence_mbar_init();
+#pragma unroll
+    for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];       // constant indices: plain constant-bank reads
+  }
   __syncthreads();
-  unsigned cur = s_cur;
-  while (cur < P.total_items) {
-    // (decoded ticket fields are recomputed where they are needed instead of being kept live across the FFT bodies)
-    int look_ok = 0;
-    if (t == 0) {
-      t_next2 = atomicAdd(P.counters, 1u);                     // ticket i+2: in flight while this item is processed
-      int stage, item; long long tr;
-      if (ts_decode(P, cur, &stage, &tr, &item) && !s_cur_pf) { // (a prefetched item had its counters checked already)
-        const TsDeps d = ts_deps(P, stage, tr);
-        if (d.in_ctr) ts_wait_at_least(d.in_ctr, d.in_need);
-        if (d.free_ctr) ts_wait_at_least(d.free_ctr, d.free_need);
+  if (t >= kTsThreads) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = t - kTsThreads;
+    for (unsigned it = 0;; ++it) {
+      const int b = (int)(it % NBUF);
+      const unsigned use = it / NBUF;
+      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
+      unsigned ticket = 0;
+      if (lane == 0) ticket = atomicAdd(P.counters, 1u);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket >= P.total_items) {
+        if (lane == 0) { slot_ticket[b] = kEnd; ts_mbar_arrive(&full[b]); }
+        break;
       }
-      // early, non-blocking look at the next item's counters
-      const unsigned nxt = s_next;
-      int nstage, nitem; long long ntr;
-      if (nxt < P.total_items && ts_decode(P, nxt, &nstage, &ntr, &nitem)) {
-        const TsStage& nst = P.st[nstage];
-        if (PREFETCH && (nst.kind == TS_FIRST || nst.kind == TS_LATER) && (nst.src != 0 || P.in_aligned16)) {
-          const TsDeps nd = ts_deps(P, nstage, ntr);
-          const unsigned li = nd.in_ctr ? ts_ld_relaxed(nd.in_ctr) : 0u;
-          const unsigned lf = nd.free_ctr ? ts_ld_relaxed(nd.free_ctr) : 0u;
-          look_ok = (!nd.in_ctr || li >= nd.in_need) && (!nd.free_ctr || lf >= nd.free_need);
+      int stage, item; long long tr;
+      const bool live = ts_decode(P, ST, ticket, &stage, &tr, &item);
+      bool staged = false;
+      if (live) {
+        const TsStage& st = ST[stage];
+        if (lane == 0) {
+          const TsDeps d = ts_deps(P, ST, stage, tr);
+          if (d.in_ctr) ts_wait_at_least(d.in_ctr, d.in_need);
+          if (d.free_ctr) ts_wait_at_least(d.free_ctr, d.free_need);
+        }
+        __syncwarp();
+        staged = STAGE && (st.kind == TS_FIRST || st.kind == TS_LATER) && (st.src != 0 || P.in_aligned16);
+        if (staged) {
+          const int A = st.A, R = 16 * A, cols = ts_cols_for(A), m = st.m;
+          const int b0 = cols * item;
+          int gv = (m - b0 + 15) / 16;                            // valid 16-column tiles of this item
+          if (gv > cols / 16) gv = cols / 16;
+          const int rows = gv * R;
+          if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 1; mbar_expect_tx(&full[b], (uint32_t)rows * kRowBytes); }
+          __syncwarp();
+          ts_fence_proxy_async_all();                             // the acquire above orders these async-proxy reads too
+          const cpx<T>* src = ts_src(P, st.src, tr) + b0;
+          cpx<T>* dstb = inbuf + (size_t)b * (16 * 256);
+          for (int row = lane; row < rows; row += 32) {
+            const int grp = row / R, n = row - grp * R;
+            bulk_g2s(dstb + row * 16, src + 16 * grp + (long long)m * n, kRowBytes, &full[b]);
+          }
         }
       }
+      if (!staged && lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 0; ts_mbar_arrive(&full[b]); }
     }
-    const int cur_pf = s_cur_pf;
-    if (cur_pf) ts_cp_async_wait_all();
-    __syncthreads();
-    {
-      int stage, item; long long tr;
-      if (ts_decode(P, cur, &stage, &tr, &item)) {
-        const TsStage& st = P.st[stage];
-        if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, t, item, st, ts_src(P, st.src, tr), (cpx<T>*)nullptr, P.tw, P.twR, tile, cur_pf ? staging : nullptr);
-        else if (st.kind == TS_LATER) ts_item_phase_any<false, SIGN, T>(0, t, item, st, ts_src(P, st.src, tr), (cpx<T>*)nullptr, P.tw, P.twR, tile, cur_pf ? staging : nullptr);
-      }
-    }
-    if (t == 0) {
-      if (look_ok) __threadfence();                             // acquire side of the relaxed reads above
-      s_next_ok = look_ok;
-    }
-    __syncthreads();
-    const int next_ok = s_next_ok;
-    if (next_ok) {                                              // staging was consumed in phase 1 (barrier above)
-      int nstage, nitem; long long ntr;
-      ts_decode(P, s_next, &nstage, &ntr, &nitem);
-      ts_prefetch_item<T>(t, P.st[nstage], nitem, ts_src(P, P.st[nstage].src, ntr), staging);
-    }
-    unsigned* done = nullptr;
-    {
-      int stage, item; long long tr;
-      if (ts_decode(P, cur, &stage, &tr, &item)) {
-        const TsStage& st = P.st[stage];
-        const cpx<T>* src = ts_src(P, st.src, tr);
-        cpx<T>* dst = ts_dst(P, st.dst, tr);
-        if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-        else if (st.kind == TS_LATER) ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-        else if (st.kind == TS_SMALL) ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
-        else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
-        else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
-        if (t == 0) done = ts_deps(P, stage, tr).done;
-      }
-    }
-    __syncthreads();                                          // every store of the item is issued; tile is free again
-    if (t == 0) {
-      if (done) { __threadfence(); atomicAdd(done, 1u); }
-      s_cur = s_next; s_cur_pf = next_ok; s_next = t_next2;
-    }
-    __syncthreads();
-    cur = s_cur;
+    return;
   }
-  ts_cp_async_wait_all();
+  // -------------------------------------------------------------------- consumer warps
+  for (unsigned it = 0;; ++it) {
+    const int b = (int)(it % NBUF);
+    mbar_wait(&full[b], (it / NBUF) & 1);
+    const unsigned ticket = slot_ticket[b];
+    const int staged = slot_staged[b];
+    if (ticket == kEnd) break;
+    int stage, item; long long tr;
+    const bool live = ts_decode(P, ST, ticket, &stage, &tr, &item);
+    if (!live) { ts_mbar_arrive(&empty[b]); continue; }
+    const TsStage& st = ST[stage];
+    const cpx<T>* src = ts_src(P, st.src, tr);
+    cpx<T>* dst = ts_dst(P, st.dst, tr);
+    if (st.kind == TS_FIRST || st.kind == TS_LATER) {
+      const cpx<T>* in_s = staged ? inbuf + (size_t)b * (16 * 256) : nullptr;
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile, in_s);
+      else ts_item_phase_any<false, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile, in_s);
+      ts_mbar_arrive(&empty[b]);                                  // this thread is done with the input buffer
+      ts_bar_consumers();
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+      else ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
+    } else {
+      ts_mbar_arrive(&empty[b]);
+      if (st.kind == TS_SMALL) ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
+      else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+      else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+    }
+    ts_bar_consumers();                                           // every store of the item is issued; tile is free again
+    if (t == 0) { __threadfence(); atomicAdd(ts_deps(P, ST, stage, tr).done, 1u); }
+  }
 }
 #endif  // __CUDACC__
 

@@ -97,7 +97,7 @@ static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
   uint32_t rs = seed * 2654435761u + 12345u;
   auto ready = [&](unsigned ticket) {
     int stage, item; long long tr;
-    if (!ts_decode(P, ticket, &stage, &tr, &item)) return true;
+    if (!ts_decode(P, P.st, ticket, &stage, &tr, &item)) return true;
     const int slot = (int)(tr % P.ring_slots); const unsigned gen = (unsigned)(tr / P.ring_slots);
     const unsigned* base = counters.data() + kTsCounterBase + slot;
     if (stage > 0 && base[(stage - 1) * P.ring_slots] < (gen + 1u) * (unsigned)P.st[stage - 1].tiles) return false;
@@ -114,7 +114,7 @@ static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
     const unsigned cur = flight[pick];
     flight.erase(flight.begin() + pick);
     int stage, item; long long tr;
-    if (!ts_decode(P, cur, &stage, &tr, &item)) continue;
+    if (!ts_decode(P, P.st, cur, &stage, &tr, &item)) continue;
     const TsStage& st = P.st[stage];
     const cpx<T>* src = ts_src(P, st.src, tr);
     cpx<T>* dst = ts_dst(P, st.dst, tr);

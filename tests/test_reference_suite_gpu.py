@@ -20,6 +20,9 @@ CASES = [
     ("test_fft_factors", [], 300),
     ("test_pffastconv", ["--no-bench", "--quick"], 1500),
     ("test_pffastconv", ["--no-bench", "--quick", "--sym"], 1500),
+    # the FULL sweep of tests/test_pffastconv.c:915-936: filter lengths 124 .. 256, real / complex 2x / complex single FFT,
+    # block sizes 64 .. 64 K, output lengths with and without flush
+    ("test_pffastconv", ["--no-bench"], 1500),
     ("example_c_real_flt_fwd", [], 60),
     ("example_c_cplx_dbl_fwd", [], 60),
 ]
