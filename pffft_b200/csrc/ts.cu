@@ -29,22 +29,27 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
-// kernel shapes: (resident CTAs per SM the register budget is sized for, ticket slots, staged inputs).
-//   float : 2 CTAs x (8 consumer warps + producer), 2 staged items in flight per CTA, <= 113 registers   [default]
-//           PFFFT_B200_TS_SHAPE=1: 3 CTAs, 1 staged item (72 registers);  =2: 1 CTA, 4 staged items
-//   double: 1 CTA, 2 staged items (192 KB of shared memory, no spills);  PFFFT_B200_TS_SHAPE=1: 2 CTAs, inputs read directly
+// kernel shapes (PFFFT_B200_TS_SHAPE): resident CTAs per SM the register budget is sized for, ticket slots the producer runs
+// ahead, inputs staged in shared memory by the producer warp (cp.async) or read directly by the consumers
+//   0: 2 CTAs, 2 slots, staged      1: 3 CTAs, 1 slot, staged      2: 2 CTAs, 2 slots, direct      3: 3 CTAs, 2 slots, direct
 template <typename T> struct TsKernels {
   using Kern = void (*)(const TsParams<T>);
-  static int shape() { static const int v = getenv("PFFFT_B200_TS_SHAPE") ? atoi(getenv("PFFFT_B200_TS_SHAPE")) : 0; return v; }
+  static int shape() {
+    static const int v = getenv("PFFFT_B200_TS_SHAPE") ? atoi(getenv("PFFFT_B200_TS_SHAPE")) : (sizeof(T) == 8 ? 2 : 0);
+    return v < 0 || v > 3 ? 0 : v;
+  }
   static size_t smem() {
     const size_t item = (size_t)16 * 256 * sizeof(cpx<T>);
-    if constexpr (sizeof(T) == 8) return item * (shape() == 1 ? 1 : 3);
-    else return item * (shape() == 1 ? 2 : shape() == 2 ? 5 : 3);
+    const int sh = shape();
+    return item * (sh == 0 ? 3 : sh == 1 ? 2 : 1);
   }
   template <int SIGN> static Kern kern() {
-    if constexpr (sizeof(T) == 8) return shape() == 1 ? (Kern)k_ts_pipeline<T, SIGN, 2, 2, false> : (Kern)k_ts_pipeline<T, SIGN, 1, 2, true>;
-    else return shape() == 1 ? (Kern)k_ts_pipeline<T, SIGN, 3, 1, true> : shape() == 2 ? (Kern)k_ts_pipeline<T, SIGN, 1, 4, true>
-                                                                                       : (Kern)k_ts_pipeline<T, SIGN, 2, 2, true>;
+    switch (shape()) {
+      case 1: return (Kern)k_ts_pipeline<T, SIGN, 3, 1, true>;
+      case 2: return (Kern)k_ts_pipeline<T, SIGN, 2, 2, false>;
+      case 3: return (Kern)k_ts_pipeline<T, SIGN, 3, 2, false>;
+      default: return (Kern)k_ts_pipeline<T, SIGN, 2, 2, true>;
+    }
   }
   static Kern fwd() { return kern<-1>(); }
   static Kern bwd() { return kern<+1>(); }

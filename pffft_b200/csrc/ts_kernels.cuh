@@ -266,7 +266,13 @@ PF_D void ts_wait_at_least(const unsigned* p, unsigned need) {
 PF_D void ts_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-PF_D void ts_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+PF_D void ts_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only (.cg): ring data never enters L1
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// arrive on `bar` when every cp.async this thread issued so far has landed (counts as one of the expected arrivals)
+PF_D void ts_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 PF_D void ts_bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); static_assert(kTsThreads == 256, "consumer barrier width"); }
 
 // dependency counters of a live work item: `in_need` tiles of the producing stage, `free_need` tiles of the consuming
@@ -291,8 +297,10 @@ template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* S
 //   producer: wait until input buffer b is free (mbarrier `empty`), take the next ticket (atomic), wait for the item's
 //             dependency counters (acquire polling -- it may block: the consumers finish and signal their current item
 //             without it, and every wait is on tickets handed out earlier, so the no-deadlock argument is unchanged),
-//             then stage the item's input -- rows of 16 columns = 128-byte runs -- into shared memory with 1-D TMA bulk
-//             copies (cp.async.bulk, SASS UBLKCP; through L2, never L1) whose completion the mbarrier `full` counts;
+//             then stage the item's input -- rows of 16 columns = 128-byte runs -- into shared memory with 16-byte
+//             cp.async.cg copies (SASS LDGSTS; through L2, never L1; 8 lanes per row) whose completion the mbarrier `full`
+//             counts (cp.async.mbarrier.arrive).  [One 1-D TMA bulk copy per row (cp.async.bulk, UBLKCP) was built and
+//             measured first: 128-byte bulk copies cost ~10-20 ns each in the SM's TMA unit, 0.07-0.18 of the HBM roofline.]
 //   consumers: wait on `full`, phase 1 out of shared memory, release the buffer, phase 2, stores, completion signal.
 // The consumers never wait for a ticket, a counter or (once the pipeline is primed) a load: NBUF items' loads per CTA are
 // in flight while the previous ones are being transformed.
@@ -308,10 +316,9 @@ __global__ void __launch_bounds__(kTsThreads + 32, MINB) k_ts_pipeline(const __g
   __shared__ int slot_staged[NBUF];
   __shared__ TsStage ST[kTsMaxStages];
   constexpr unsigned kEnd = 0xFFFFFFFFu;
-  constexpr uint32_t kRowBytes = 16 * sizeof(cpx<T>);
   const int t = threadIdx.x;
   if (t == 0) {
-    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], kTsThreads); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 32); mbar_init(&empty[b], kTsThreads); }
     fence_mbar_init();
 #pragma unroll
     for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];       // constant indices: plain constant-bank reads
@@ -328,7 +335,8 @@ __global__ void __launch_bounds__(kTsThreads + 32, MINB) k_ts_pipeline(const __g
       if (lane == 0) ticket = atomicAdd(P.counters, 1u);
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
       if (ticket >= P.total_items) {
-        if (lane == 0) { slot_ticket[b] = kEnd; ts_mbar_arrive(&full[b]); }
+        if (lane == 0) slot_ticket[b] = kEnd;
+        ts_mbar_arrive(&full[b]);
         break;
       }
       int stage, item; long long tr;
@@ -349,18 +357,20 @@ __global__ void __launch_bounds__(kTsThreads + 32, MINB) k_ts_pipeline(const __g
           int gv = (m - b0 + 15) / 16;                            // valid 16-column tiles of this item
           if (gv > cols / 16) gv = cols / 16;
           const int rows = gv * R;
-          if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 1; mbar_expect_tx(&full[b], (uint32_t)rows * kRowBytes); }
-          __syncwarp();
-          ts_fence_proxy_async_all();                             // the acquire above orders these async-proxy reads too
+          constexpr int EPC = 16 / (int)sizeof(cpx<T>);           // elements per 16-byte chunk: 2 (float), 1 (double)
+          constexpr int CPR = 16 / EPC;                           // chunks per 16-column row
+          if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 1; }
           const cpx<T>* src = ts_src(P, st.src, tr) + b0;
           cpx<T>* dstb = inbuf + (size_t)b * (16 * 256);
-          for (int row = lane; row < rows; row += 32) {
+          for (int c = lane; c < rows * CPR; c += 32) {
+            const int row = c / CPR, h = c - row * CPR;
             const int grp = row / R, n = row - grp * R;
-            bulk_g2s(dstb + row * 16, src + 16 * grp + (long long)m * n, kRowBytes, &full[b]);
+            ts_cp_async16(dstb + row * 16 + h * EPC, src + 16 * grp + (long long)m * n + h * EPC);
           }
+          ts_cp_async_arrive(&full[b]);                           // all 32 lanes: fires when this lane's copies have landed
         }
       }
-      if (!staged && lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 0; ts_mbar_arrive(&full[b]); }
+      if (!staged) { if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 0; } ts_mbar_arrive(&full[b]); }
     }
     return;
   }

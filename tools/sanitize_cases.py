@@ -33,4 +33,33 @@ for taps, bl, n in [(100, 1024, 5000), (4097, 0, 40000), (31, 0, 3000), (200, 16
         got = fc.apply(x, y, n // (2 if flags & 1 else 1), 1)
         torch.cuda.synchronize(); fc.close()
         print("fastconv taps=%d Nfft=%d flags=%d produced=%d" % (taps, fc.block_len, flags, got), flush=True)
+# large cores: the default single/two-launch plans and the tiled Stockham pipeline (2, 3 passes, closing small radix,
+# pre-/post-rotation stages, ring recycling with a batch larger than the ring)
+for N, tr, batch in [(16384, 1, 3), (32768, 1, 3), (65536, 1, 3), (131072, 0, 2), (36864, 1, 2), (131072, 1, 2), (1 << 20, 1, 1),
+                     (384000, 1, 1), (1 << 18, 0, 2)]:
+    run(N, tr, np.float32, batch)
+os.environ["PFFFT_B200_TS"] = "1"
+for N, tr, batch in [(16384, 1, 300), (8192, 0, 50), (65536, 1, 8)]:
+    run(N, tr, np.float32, batch)
+run(16384, 1, np.float64, 20)
+del os.environ["PFFFT_B200_TS"]
+# streaming push / flush and partitioned convolution (C-ABI entry points of round 2)
+n, taps = 30000, 301
+x = (np.arange(n) % 4093).astype(np.float32)
+h = np.array([(-1.0, 1.0, 0.5)[j % 3] for j in range(taps)], np.float32)
+for flags in (0, 1):
+    fc = pf.FastConv(h, 1024, flags)
+    w = 2 if flags & 1 else 1
+    xd = torch.from_numpy(x).cuda(); yd = torch.zeros(n + 64, device="cuda")
+    got = 0
+    for lo in range(0, n // w, 7001):
+        c = min(7001, n // w - lo)
+        got += fc.push(xd[lo * w:], c, yd[got * w:], fc.pending + c)
+    got += fc.flush(yd[got * w:], fc.pending)
+    torch.cuda.synchronize(); fc.close()
+    print("stream push/flush flags=%d produced=%d" % (flags, got), flush=True)
+pc = pf.PartitionedConv(h, 64)
+yd = torch.zeros(n, device="cuda")
+print("partitioned produced=%d" % pc.apply(torch.from_numpy(x).cuda(), yd, n), flush=True)
+torch.cuda.synchronize(); pc.close()
 print("done")
