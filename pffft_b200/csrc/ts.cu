@@ -16,7 +16,7 @@ namespace pf {
 struct TsPlanHost {
   int Nc = 0, N = 0, device = 0, sm_count = 0;
   bool dbl = false;
-  int P = 0, A[4] = {0, 0, 0, 0}, tw_off[4] = {0, 0, 0, 0};
+  int P = 0, A[4] = {0, 0, 0, 0}, tw_off[4] = {0, 0, 0, 0}, twR_entries = 0;
   void* d_twR = nullptr;
   void* d_ring[kTsMaxRings] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int nrings = 0;
@@ -29,9 +29,9 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
-// kernel shapes (PFFFT_B200_TS_SHAPE): resident CTAs per SM the register budget is sized for, ticket slots the producer runs
-// ahead, inputs staged in shared memory by the producer warp (cp.async) or read directly by the consumers
-//   0: 2 CTAs, 2 slots, staged      1: 3 CTAs, 1 slot, staged      2: 2 CTAs, 2 slots, direct      3: 3 CTAs, 2 slots, direct
+// kernel shapes (PFFFT_B200_TS_SHAPE): resident CTAs per SM the register budget is sized for; PREFETCH = the next work
+// item's input is staged in a second shared buffer by cp.async while the current one finishes
+//   0: 3 CTAs, direct reads     1: 3 CTAs, prefetch     2: 2 CTAs (128 registers), direct     3: 2 CTAs, prefetch
 template <typename T> struct TsKernels {
   using Kern = void (*)(const TsParams<T>);
   static int shape() {
@@ -40,15 +40,14 @@ template <typename T> struct TsKernels {
   }
   static size_t smem() {
     const size_t item = (size_t)16 * 256 * sizeof(cpx<T>);
-    const int sh = shape();
-    return item * (sh == 0 ? 3 : sh == 1 ? 2 : 1);
+    return item * ((shape() & 1) ? 2 : 1) + 1024 * sizeof(cpx<T>);
   }
   template <int SIGN> static Kern kern() {
     switch (shape()) {
-      case 1: return (Kern)k_ts_pipeline<T, SIGN, 3, 1, true>;
-      case 2: return (Kern)k_ts_pipeline<T, SIGN, 2, 2, false>;
-      case 3: return (Kern)k_ts_pipeline<T, SIGN, 3, 2, false>;
-      default: return (Kern)k_ts_pipeline<T, SIGN, 2, 2, true>;
+      case 1: return (Kern)k_ts_pipeline<T, SIGN, 3, true>;
+      case 2: return (Kern)k_ts_pipeline<T, SIGN, 2, false>;
+      case 3: return (Kern)k_ts_pipeline<T, SIGN, 2, true>;
+      default: return (Kern)k_ts_pipeline<T, SIGN, 3, false>;
     }
   }
   static Kern fwd() { return kern<-1>(); }
@@ -60,7 +59,7 @@ template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
   { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), TsKernels<T>::smem()); if (rc) return rc; }
   { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), TsKernels<T>::smem()); if (rc) return rc; }
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads + 32, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
   if (n < 1) n = 1;
   h->grid = n * h->sm_count;
   return 0;
@@ -68,6 +67,7 @@ template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
 
 template <typename T> static bool ts_fill_radix_tables(TsPlanHost* h) {
   const std::vector<T> host = ts_radix_tables<T>(h->P, h->A, h->tw_off);
+  h->twR_entries = (int)(host.size() / 2);
   if (cudaMalloc(&h->d_twR, host.size() * sizeof(T)) != cudaSuccess) return false;
   return cudaMemcpy(h->d_twR, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
 }
@@ -131,6 +131,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   for (int i = 0; i < kTsMaxRings; ++i) P.ring[i] = reinterpret_cast<cpx<T>*>(h->d_ring[i]);
   P.counters = h->d_counters;
   P.N = h->N; P.Nc = h->Nc; P.lag = h->lag; P.ring_slots = h->ring_slots;
+  P.twR_entries = h->twR_entries;
   ts_build_stages<T>(P, h->Nc, h->P, h->A, h->tw_off, lm, sm);
   const int ns = P.nstages;
   const long long group = P.group_items;
@@ -149,7 +150,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
     const long long g = total < h->grid ? total : h->grid;
-    kern<<<(int)g, kTsThreads + 32, h->smem, st>>>(P);
+    kern<<<(int)g, kTsThreads, h->smem, st>>>(P);
     count_launch();
     PF_CUDA_OK(cudaGetLastError());
   }

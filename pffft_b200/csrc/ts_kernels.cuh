@@ -63,6 +63,7 @@ template <typename T> struct TsParams {
   int nstages, lag, ring_slots, group_items;
   unsigned total_items;
   int in_aligned16;                 // user input 16-byte aligned (cp.async prefetch of the first pass)
+  int twR_entries;                  // total entries of twR (copied to shared memory by the kernel)
   TsStage st[kTsMaxStages];
 };
 
@@ -114,7 +115,7 @@ PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int 
   cpx<T>* tl = tile + grp * (16 * S::R);
   tl[ts_tile_idx<A, FIRST>(0, q, j)] = v[0];
 #pragma unroll
-  for (int ka = 1; ka < 16; ++ka) tl[ts_tile_idx<A, FIRST>(ka, q, j)] = cmul_dir<SIGN>(v[ka], ldtab(twR + ka * A + q));
+  for (int ka = 1; ka < 16; ++ka) tl[ts_tile_idx<A, FIRST>(ka, q, j)] = cmul_dir<SIGN>(v[ka], twR[ka * A + q]);   // (shared-memory copy in the kernel)
 }
 // ---- phase 2, first pass (s = 1, p = b): y[R*b + k] = W_Nc^{b k} (...),  W^{b k} = W^{b k_a} * W^{16 b k_b}
 template <int A, int SIGN, typename T>
@@ -292,118 +293,136 @@ template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* S
   return d;
 }
 
-// WARP-SPECIALISED pipeline.  8 consumer warps run the work items; a 9th PRODUCER warp owns everything that has global
-// latency in it and runs NBUF items ahead of them:
-//   producer: wait until input buffer b is free (mbarrier `empty`), take the next ticket (atomic), wait for the item's
-//             dependency counters (acquire polling -- it may block: the consumers finish and signal their current item
-//             without it, and every wait is on tickets handed out earlier, so the no-deadlock argument is unchanged),
-//             then stage the item's input -- rows of 16 columns = 128-byte runs -- into shared memory with 16-byte
-//             cp.async.cg copies (SASS LDGSTS; through L2, never L1; 8 lanes per row) whose completion the mbarrier `full`
-//             counts (cp.async.mbarrier.arrive).  [One 1-D TMA bulk copy per row (cp.async.bulk, UBLKCP) was built and
-//             measured first: 128-byte bulk copies cost ~10-20 ns each in the SM's TMA unit, 0.07-0.18 of the HBM roofline.]
-//   consumers: wait on `full`, phase 1 out of shared memory, release the buffer, phase 2, stores, completion signal.
-// The consumers never wait for a ticket, a counter or (once the pipeline is primed) a load: NBUF items' loads per CTA are
-// in flight while the previous ones are being transformed.
-// NBUF = ticket slots the producer may run ahead; STAGE = each slot has an input buffer (false: consumers read their inputs
-// directly -- double precision, where a second 64 KB buffer would cost the second resident CTA)
-template <typename T, int SIGN, int MINB, int NBUF, bool STAGE>
-__global__ void __launch_bounds__(kTsThreads + 32, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
+PF_D unsigned ts_ld_relaxed(const unsigned* p) {                    // L2 read without the L1 invalidation of an acquire
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+PF_D void ts_red_release(unsigned* p) {                             // completion signal: earlier writes of the CTA first
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+PF_D void ts_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// input of FFT work item (stage st, item) -> shared memory [tile grp][row n < R][16 columns], 16-byte cp.async.cg chunks
+template <typename T>
+PF_D void ts_prefetch_item(int t, const TsStage& st, int item, const cpx<T>* src, cpx<T>* staging) {
+  constexpr int EPC = 16 / (int)sizeof(cpx<T>);                    // elements per 16-byte chunk: 2 (float), 1 (double)
+  constexpr int CPR = 16 / EPC;                                    // chunks per 16-column row
+  const int A = st.A, R = 16 * A, cols = ts_cols_for(A), m = st.m;
+  const int b0 = cols * item;
+  int gv = (m - b0 + 15) / 16;
+  if (gv > cols / 16) gv = cols / 16;
+  const int rows = gv * R;                                         // <= 256
+  for (int c = t; c < rows * CPR; c += kTsThreads) {
+    const int row = c / CPR, h = c - row * CPR;
+    const int grp = row / R, n = row - grp * R;
+    ts_cp_async16(staging + row * 16 + h * EPC, src + b0 + 16 * grp + (long long)m * n + h * EPC);
+  }
+}
+
+// THE PERSISTENT LOOP.  What the first hardware profile showed (profiles/r02_ts.md): the arithmetic was fine, the CTAs
+// were waiting -- 24 % of all stall samples sat at the barrier behind thread 0's dependency check (two serialised
+// ld.acquire = two L2 round trips, each followed by CCTL.IVALL, an invalidation of the SM's whole L1 that also threw out
+// the twiddle tables of the neighbouring CTAs), more behind the __threadfence of the completion signal.  So:
+//   * tickets are taken TWO ahead; the counters of item i+1 are read (ld.relaxed, both at once) at the top of item i and
+//     looked at when item i is done -- by then they have long arrived, and with the pipeline lag they are satisfied:
+//     item i+1 starts without waiting for anything.  Only if the early look failed does its top poll (still relaxed);
+//   * nothing invalidates L1: ring data is only ever read with ld.cg / cp.async.cg (L2), tables are immutable, the
+//     per-radix tables live in shared memory; the completion signal is one red.release issued by a thread of another
+//     warp than the one that handles tickets, so neither waits for the other;
+//   * PREFETCH: when the early look at item i+1 succeeds by the middle of item i, all threads stage its input in a second
+//     shared buffer with cp.async (overlapping phase 2 and the stores of item i).
+template <typename T, int SIGN, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
-  cpx<T>* inbuf = tile + 16 * 256;                              // NBUF buffers of one work item each
-  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF];
-  __shared__ unsigned slot_ticket[NBUF];
-  __shared__ int slot_staged[NBUF];
+  cpx<T>* twRs = tile + 16 * 256;                               // per-radix tables of every pass (<= 4 x 256 entries)
+  cpx<T>* staging = twRs + 1024;                                // PREFETCH only
+  __shared__ unsigned s_cur, s_next;
+  __shared__ int s_cur_ready, s_cur_pf, s_next_ready, s_next_pf;
   __shared__ TsStage ST[kTsMaxStages];
-  constexpr unsigned kEnd = 0xFFFFFFFFu;
   const int t = threadIdx.x;
+  for (int i = t; i < P.twR_entries; i += kTsThreads) twRs[i] = P.twR[i];
   if (t == 0) {
-    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 32); mbar_init(&empty[b], kTsThreads); }
-    fence_mbar_init();
 #pragma unroll
     for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];       // constant indices: plain constant-bank reads
+    s_cur = atomicAdd(P.counters, 1u); s_next = atomicAdd(P.counters, 1u); s_cur_ready = 0; s_cur_pf = 0;
   }
   __syncthreads();
-  if (t >= kTsThreads) {
-    // ------------------------------------------------------------------ producer warp
-    const int lane = t - kTsThreads;
-    for (unsigned it = 0;; ++it) {
-      const int b = (int)(it % NBUF);
-      const unsigned use = it / NBUF;
-      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
-      unsigned ticket = 0;
-      if (lane == 0) ticket = atomicAdd(P.counters, 1u);
-      ticket = __shfl_sync(0xffffffffu, ticket, 0);
-      if (ticket >= P.total_items) {
-        if (lane == 0) slot_ticket[b] = kEnd;
-        ts_mbar_arrive(&full[b]);
-        break;
-      }
+  unsigned cur = s_cur;
+  while (cur < P.total_items) {
+    // ---- thread 0: ticket i+2, readiness of item i (poll only if the early look failed), early look at item i+1
+    // (only three values stay live across the FFT bodies: the ticket and the two counter reads in flight)
+    unsigned t_next2 = 0, li = 0, lf = 0;
+    if (t == 0) {
+      t_next2 = atomicAdd(P.counters, 1u);
       int stage, item; long long tr;
-      const bool live = ts_decode(P, ST, ticket, &stage, &tr, &item);
-      bool staged = false;
-      if (live) {
-        const TsStage& st = ST[stage];
-        if (lane == 0) {
-          const TsDeps d = ts_deps(P, ST, stage, tr);
-          if (d.in_ctr) ts_wait_at_least(d.in_ctr, d.in_need);
-          if (d.free_ctr) ts_wait_at_least(d.free_ctr, d.free_need);
-        }
-        __syncwarp();
-        staged = STAGE && (st.kind == TS_FIRST || st.kind == TS_LATER) && (st.src != 0 || P.in_aligned16);
-        if (staged) {
-          const int A = st.A, R = 16 * A, cols = ts_cols_for(A), m = st.m;
-          const int b0 = cols * item;
-          int gv = (m - b0 + 15) / 16;                            // valid 16-column tiles of this item
-          if (gv > cols / 16) gv = cols / 16;
-          const int rows = gv * R;
-          constexpr int EPC = 16 / (int)sizeof(cpx<T>);           // elements per 16-byte chunk: 2 (float), 1 (double)
-          constexpr int CPR = 16 / EPC;                           // chunks per 16-column row
-          if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 1; }
-          const cpx<T>* src = ts_src(P, st.src, tr) + b0;
-          cpx<T>* dstb = inbuf + (size_t)b * (16 * 256);
-          for (int c = lane; c < rows * CPR; c += 32) {
-            const int row = c / CPR, h = c - row * CPR;
-            const int grp = row / R, n = row - grp * R;
-            ts_cp_async16(dstb + row * 16 + h * EPC, src + 16 * grp + (long long)m * n + h * EPC);
-          }
-          ts_cp_async_arrive(&full[b]);                           // all 32 lanes: fires when this lane's copies have landed
+      if (!s_cur_ready && ts_decode(P, ST, cur, &stage, &tr, &item)) {
+        const TsDeps d = ts_deps(P, ST, stage, tr);
+        for (;;) {
+          const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
+          if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
+          __nanosleep(100);
         }
       }
-      if (!staged) { if (lane == 0) { slot_ticket[b] = ticket; slot_staged[b] = 0; } ts_mbar_arrive(&full[b]); }
+      const unsigned nxt = s_next;
+      int nstage, nitem; long long ntr;
+      if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
+        const TsDeps nd = ts_deps(P, ST, nstage, ntr);
+        if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);             // in flight during the whole item
+        if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
+      }
     }
-    return;
-  }
-  // -------------------------------------------------------------------- consumer warps
-  for (unsigned it = 0;; ++it) {
-    const int b = (int)(it % NBUF);
-    mbar_wait(&full[b], (it / NBUF) & 1);
-    const unsigned ticket = slot_ticket[b];
-    const int staged = slot_staged[b];
-    if (ticket == kEnd) break;
+    const int cur_pf = PREFETCH ? s_cur_pf : 0;
+    if (PREFETCH && cur_pf) ts_cp_async_wait_all();
+    __syncthreads();
     int stage, item; long long tr;
-    const bool live = ts_decode(P, ST, ticket, &stage, &tr, &item);
-    if (!live) { ts_mbar_arrive(&empty[b]); continue; }
+    const bool live = ts_decode(P, ST, cur, &stage, &tr, &item);
     const TsStage& st = ST[stage];
-    const cpx<T>* src = ts_src(P, st.src, tr);
-    cpx<T>* dst = ts_dst(P, st.dst, tr);
-    if (st.kind == TS_FIRST || st.kind == TS_LATER) {
-      const cpx<T>* in_s = staged ? inbuf + (size_t)b * (16 * 256) : nullptr;
-      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile, in_s);
-      else ts_item_phase_any<false, SIGN, T>(0, t, item, st, src, dst, P.tw, P.twR, tile, in_s);
-      ts_mbar_arrive(&empty[b]);                                  // this thread is done with the input buffer
-      ts_bar_consumers();
-      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-      else ts_item_phase_any<false, SIGN, T>(1, t, item, st, src, dst, P.tw, P.twR, tile);
-    } else {
-      ts_mbar_arrive(&empty[b]);
-      if (st.kind == TS_SMALL) ts_small_item_any<SIGN, T>(t, item, st, src, dst, P.tw);
+    const bool fft = live && (st.kind == TS_FIRST || st.kind == TS_LATER);
+    // the thread index is made opaque per iteration: otherwise the compiler hoists the per-thread index arithmetic of ALL
+    // 24 radix bodies (t % A, t / A, tile offsets ...) out of the persistent loop and spills ~150 values to local memory
+    int tt = t;
+    asm volatile("" : "+r"(tt));
+    if (fft) {
+      const cpx<T>* src = ts_src(P, st.src, tr);
+      const cpx<T>* in_s = cur_pf ? staging : nullptr;
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile, in_s);
+      else ts_item_phase_any<false, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile, in_s);
+    }
+    if (t == 0) {                                                 // is item i+1 known to be ready?
+      int n_ok = 0, pf = 0;
+      const unsigned nxt = s_next;
+      int nstage, nitem; long long ntr;
+      if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
+        const TsDeps nd = ts_deps(P, ST, nstage, ntr);
+        n_ok = (!nd.in_ctr || li >= nd.in_need) && (!nd.free_ctr || lf >= nd.free_need);
+        const TsStage& nst = ST[nstage];
+        pf = PREFETCH && n_ok && (nst.kind == TS_FIRST || nst.kind == TS_LATER) && (nst.src != 0 || P.in_aligned16);
+      }
+      s_next_ready = n_ok; s_next_pf = pf;
+    }
+    __syncthreads();
+    if (PREFETCH && s_next_pf) {                                  // staging was consumed in phase 1 (barrier above)
+      int nstage, nitem; long long ntr;
+      ts_decode(P, ST, s_next, &nstage, &ntr, &nitem);
+      ts_prefetch_item<T>(t, ST[nstage], nitem, ts_src(P, ST[nstage].src, ntr), staging);
+    }
+    if (live) {
+      const cpx<T>* src = ts_src(P, st.src, tr);
+      cpx<T>* dst = ts_dst(P, st.dst, tr);
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, tt, item, st, src, dst, P.tw, twRs, tile);
+      else if (st.kind == TS_LATER) ts_item_phase_any<false, SIGN, T>(1, tt, item, st, src, dst, P.tw, twRs, tile);
+      else if (st.kind == TS_SMALL) ts_small_item_any<SIGN, T>(tt, item, st, src, dst, P.tw);
       else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
       else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     }
-    ts_bar_consumers();                                           // every store of the item is issued; tile is free again
-    if (t == 0) { __threadfence(); atomicAdd(ts_deps(P, ST, stage, tr).done, 1u); }
+    if (t == 0) { s_cur = s_next; s_cur_ready = s_next_ready; s_cur_pf = s_next_pf; s_next = t_next2; }
+    __syncthreads();                                              // every store of the item is issued; tile is free again
+    if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage, tr).done);   // another warp than thread 0's
+    cur = s_cur;
   }
+  if (PREFETCH) ts_cp_async_wait_all();
 }
 #endif  // __CUDACC__
 
