@@ -4,6 +4,7 @@
 #include "api_impl.cuh"
 #include "fast_kernels.cuh"
 #include "cta_hooks.cuh"
+#include "radix.h"
 
 namespace pf {
 
@@ -143,10 +144,16 @@ static bool float_split_for(int N, int transform, int* R, int* N2) {
   return split_choose(Nc, is_float_row_size, R, N2);
 }
 
+// ---- compile-time-radix CTA kernels (radix_kernels.cuh): cores that are neither 32*R2 nor 256*C.  PFFFT_B200_RADIX=0 off.
+static bool radix_wanted(int Nc) {
+  static const int mode = getenv("PFFFT_B200_RADIX") ? atoi(getenv("PFFFT_B200_RADIX")) : 0;   // opt-in until measured
+  return mode != 0 && radix_core_supported(Nc, nullptr);
+}
+
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
-    if (ts_wanted(transform == XF_REAL ? N / 2 : N)) return 0;
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return 0;
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
     { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
@@ -154,7 +161,7 @@ template <> struct FastHooks<float> {
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
-    if (ts_wanted(transform == XF_REAL ? N / 2 : N)) return;
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return;
     if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
       for (int k2 = 0; k2 < 32; ++k2)
         for (int n1 = 0; n1 < 32; ++n1) {
@@ -194,6 +201,12 @@ template <> struct FastHooks<float> {
   }
   static bool plan(Setup<float>* s) {
     if (ts_wanted(s->Nc)) return ts_plan<float>(s);
+    if (radix_wanted(s->Nc)) {
+      const char* nm = "";
+      radix_core_supported(s->Nc, &nm);
+      s->fast_variant = 600; s->kernel_name = nm;
+      return true;
+    }
     if (is_warp1024(s->N, s->transform)) {
       int v = V_LDG_4x4;
       if (const char* e = getenv("PFFFT_B200_C1024")) { v = atoi(e); if (v < 0 || v >= V_COUNT) v = V_LDG_4x4; }
@@ -242,6 +255,13 @@ template <> struct FastHooks<float> {
   static int run(Setup<float>* s, const float* in, float* out, long long batch, int direction, int ordered, cudaStream_t st,
                  const XformOpts& o) {
     if (s->fast_variant == 500) return ts_dispatch<float>(s, in, out, batch, direction, ordered, st, o);
+    if (s->fast_variant == 600) {                           // compile-time-radix CTA kernels: dense aligned batches
+      const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+      if (!plain || !vec_aligned<float>(in) || !vec_aligned<float>(out)) return -1;
+      int lm = 0, sm = 0;
+      ts_modes(s->transform, direction, ordered, &lm, &sm);
+      return radix_launch_float(s->Nc, lm, sm, direction == DIR_FORWARD ? -1 : +1, in, out, batch, s->tw, s->twr, s->device, s->sm_count, st);
+    }
     if (s->fast_variant < 100) {                            // warp-per-transform N=1024 complex: contiguous batches only
       const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
       if (!plain) return -1;

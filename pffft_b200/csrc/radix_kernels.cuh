@@ -1,0 +1,153 @@
+// radix_kernels.cuh -- ONE transform (or a group of small ones) per CTA for complex cores that are neither 32*R2 (warp
+// kernels) nor 256*C (16x16xC kernels): 16, 48, 80, 144, 240, 400, 432, 1296, 2000, 2592, 4000, 6000, 12000 ... -- the sizes the
+// reference's validator walks (benchmarks/bench_pffft.c:445) that were left to the runtime-radix shared-memory kernel.
+//
+// Nc = R1 * R2 [* R3], every radix a register DFT of the library (butterfly.cuh), all COMPILE-TIME.  Autosort (Stockham)
+// stages with ONE butterfly per thread and stage:
+//   stage 1: thread b < Nc/R1 reads x[b + j*Nc/R1] STRAIGHT FROM GLOBAL memory (coalesced over b; the load function also
+//            performs the backward-real pre-rotation and the z-domain gather), radix-R1 DFT, * W_Nc^{b k}, to shared memory;
+//   stage 2: shared -> registers -> radix-R2 -> * W_Nc^{R1 p k} -> shared (in place, one barrier between reads and writes);
+//   stage 3: shared -> registers -> radix-R3 -> STRAIGHT TO GLOBAL memory (coalesced over b).  Forward-real outputs, which
+//            need the mirror bin, take one more trip through shared memory.
+// One HBM read and one HBM write per transform, two (three) barriers, no runtime radix dispatch, no index division that is
+// not by a constant.  The stage-1 result is stored with one pad word per R1 words when R1 is even, which makes the
+// stride-R1 writes of neighbouring threads conflict free (odd stride in 8-byte words).
+//
+// Replaces, for these sizes, passf2/3/4/5_ps + cplx_finalize (complex) and radf*/radb* + real_finalize/preprocess (real)
+// of the reference (src/pffft_priv_impl.h:122-807, :1195-1462).
+#pragma once
+#include "butterfly.cuh"
+#include "generic_kernels.cuh"
+#include "cta_kernels.cuh"   // store_elem, ldtab
+
+namespace pf {
+
+template <int R1, int R2, int R3> struct RadixShape {
+  static constexpr int NC = R1 * R2 * R3;
+  static constexpr int M1 = NC / R1, M2 = NC / R2, M3 = NC / R3;
+  static constexpr int STAGES = R3 > 1 ? 3 : (R2 > 1 ? 2 : 1);
+  static constexpr int TT = (STAGES == 3) ? (M3 > M2 ? (M3 > M1 ? M3 : M1) : (M2 > M1 ? M2 : M1))
+                          : (STAGES == 2) ? (M2 > M1 ? M2 : M1) : M1;          // threads per transform
+  static constexpr int PAD = (R1 % 2 == 0) ? 1 : 0;
+  static constexpr int NCP = NC + PAD * (NC / R1) + 8;                          // words of one transform's buffer
+  PF_HD static int idx1(int n) { return PAD ? n + n / R1 : n; }                // layout of the stage-1 result
+};
+
+// W_Nc^{e} for SIGN (table holds the forward roots)
+template <int SIGN, typename T> PF_HD cpx<T> radix_tw(cpx<T> v, const cpx<T>* tw, int e) { return cmul_dir<SIGN>(v, ldtab(tw + e)); }
+
+// ---- the three stages of ONE transform for thread li (0 <= li < TT); `buf` = this transform's shared buffer
+template <typename T, int R1, int R2, int R3, int LM, int SIGN>
+PF_HD void radix_stage1(int li, const T* ibase, int N, const cpx<T>* tw, const cpx<T>* twr, cpx<T>* buf, cpx<T> (&last)[R1]) {
+  using S = RadixShape<R1, R2, R3>;
+  if (li >= S::M1) return;
+  cpx<T> a[R1];
+#pragma unroll
+  for (int j = 0; j < R1; ++j) a[j] = load_core<LM, T>(ibase, li + j * S::M1, N, S::NC, twr, -1, true);
+  dft_small<R1, SIGN>(a);
+  if (S::STAGES == 1) {
+#pragma unroll
+    for (int k = 0; k < R1; ++k) last[k] = a[k];
+    return;
+  }
+  buf[S::idx1(R1 * li)] = a[0];
+#pragma unroll
+  for (int k = 1; k < R1; ++k) buf[S::idx1(R1 * li + k)] = radix_tw<SIGN>(a[k], tw, li * k);
+}
+template <typename T, int R1, int R2, int R3>
+PF_HD void radix_stage2_read(int li, const cpx<T>* buf, cpx<T> (&a)[R2]) {
+  using S = RadixShape<R1, R2, R3>;
+  if (li >= S::M2) return;
+#pragma unroll
+  for (int j = 0; j < R2; ++j) a[j] = buf[S::idx1(li + j * S::M2)];
+}
+// stage 2 of a 3-stage plan: in place (caller put a barrier between read and write)
+template <typename T, int R1, int R2, int R3, int SIGN>
+PF_HD void radix_stage2_write(int li, cpx<T> (&a)[R2], const cpx<T>* tw, cpx<T>* buf) {
+  using S = RadixShape<R1, R2, R3>;
+  if (li >= S::M2) return;
+  dft_small<R2, SIGN>(a);
+  const int p = li / R1, q = li - p * R1;
+  cpx<T>* o = buf + q + R1 * R2 * p;
+  o[0] = a[0];
+#pragma unroll
+  for (int k = 1; k < R2; ++k) o[R1 * k] = p ? radix_tw<SIGN>(a[k], tw, R1 * p * k) : a[k];
+}
+template <typename T, int R1, int R2, int R3>
+PF_HD void radix_stage3_read(int li, const cpx<T>* buf, cpx<T> (&a)[R3]) {
+  using S = RadixShape<R1, R2, R3>;
+  if (li >= S::M3) return;
+#pragma unroll
+  for (int j = 0; j < R3; ++j) a[j] = buf[li + j * S::M3];
+}
+
+// emit the LAST stage's outputs v[k] = X[b + M*k] (M = Nc / R_last, thread b < M): straight to global memory for the modes
+// whose element needs no partner, else into `nat` (natural order, shared) for the pairing pass
+template <typename T, int RL, int M, int SM>
+PF_HD void radix_emit(int b, const cpx<T> (&v)[RL], T* obase, int N, cpx<T>* nat) {
+  constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  if (b >= M) return;
+#pragma unroll
+  for (int k = 0; k < RL; ++k) {
+    if (partner) nat[b + M * k] = v[k];
+    else store_elem<SM, T>(obase, b + M * k, v[k], N, N, true);
+  }
+}
+
+#ifdef __CUDACC__
+// TPC transforms per CTA iteration, TT threads each (blockDim.x = TPC * TT)
+template <typename T, int R1, int R2, int R3, int LM, int SM, int SIGN, int TPC, int MINB>
+__global__ void __launch_bounds__(TPC * RadixShape<R1, R2, R3>::TT, MINB)
+k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, const cpx<T>* tw, const cpx<T>* twr) {
+  using S = RadixShape<R1, R2, R3>;
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  constexpr bool kReal = (LM == L_R_TIME || LM == L_R_ORD || LM == L_R_Z);
+  constexpr int N = kReal ? 2 * S::NC : S::NC;
+  constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  const int tid = threadIdx.x;
+  const int tl = tid / S::TT;
+  int li = tid - tl * S::TT;
+  cpx<T>* buf = reinterpret_cast<cpx<T>*>(pf_smem_raw) + (size_t)tl * S::NCP;
+  for (long long t0 = (long long)blockIdx.x * TPC; t0 < batch; t0 += (long long)gridDim.x * TPC) {
+    asm volatile("" : "+r"(li), "+l"(tw), "+l"(twr));              // keep index math and table reads inside the loop (no spills)
+    const bool live = t0 + tl < batch;
+    const T* ibase = in + (t0 + tl) * (2LL * S::NC);
+    T* obase = out + (t0 + tl) * (2LL * S::NC);
+    if (S::STAGES == 1) {
+      cpx<T> v[R1];
+      if (live) {
+        radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, v);
+        radix_emit<T, R1, S::M1, SM>(li, v, obase, N, buf);
+      }
+    } else if (S::STAGES == 2) {
+      { cpx<T> dummy[R1]; if (live) radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, dummy); }
+      __syncthreads();
+      cpx<T> a[R2];
+      if (live) radix_stage2_read<T, R1, R2, R3>(li, buf, a);
+      if (partner) __syncthreads();                               // `buf` becomes the natural-order buffer
+      if (live && li < S::M2) { dft_small<R2, SIGN>(a); radix_emit<T, R2, S::M2, SM>(li, a, obase, N, buf); }
+    } else {
+      { cpx<T> dummy[R1]; if (live) radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, dummy); }
+      __syncthreads();
+      {
+        cpx<T> a[R2];
+        if (live) radix_stage2_read<T, R1, R2, R3>(li, buf, a);
+        __syncthreads();
+        if (live) radix_stage2_write<T, R1, R2, R3, SIGN>(li, a, tw, buf);
+      }
+      __syncthreads();
+      cpx<T> c[R3];
+      if (live) radix_stage3_read<T, R1, R2, R3>(li, buf, c);
+      if (partner) __syncthreads();
+      if (live && li < S::M3) { dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, obase, N, buf); }
+    }
+    if (partner) {
+      __syncthreads();
+      if (live) for (int k = li; k < S::NC; k += S::TT) store_core<SM, T>(obase, buf, k, N, S::NC, twr, N, true);
+    }
+    __syncthreads();                                              // buffer is rewritten by the next group's stage 1
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace pf

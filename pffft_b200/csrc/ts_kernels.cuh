@@ -324,9 +324,13 @@ PF_D void ts_prefetch_item(int t, const TsStage& st, int item, const cpx<T>* src
 // were waiting -- 24 % of all stall samples sat at the barrier behind thread 0's dependency check (two serialised
 // ld.acquire = two L2 round trips, each followed by CCTL.IVALL, an invalidation of the SM's whole L1 that also threw out
 // the twiddle tables of the neighbouring CTAs), more behind the __threadfence of the completion signal.  So:
-//   * tickets are taken TWO ahead; the counters of item i+1 are read (ld.relaxed, both at once) at the top of item i and
-//     looked at when item i is done -- by then they have long arrived, and with the pipeline lag they are satisfied:
-//     item i+1 starts without waiting for anything.  Only if the early look failed does its top poll (still relaxed);
+//   * work items are dealt out STATICALLY, item k to CTA k mod gridDim.x (the first version took atomic tickets and kept
+//     one or two in hand to hide the atomic's latency -- but every ticket a CTA holds and has not started widens the window
+//     of unfinished items by a whole grid, the pipeline lag no longer covered it, and 45 % of the items had to poll);
+//     the deadlock argument is the same induction (a CTA only ever waits for items with a smaller index);
+//   * the counters of item i+1 are read (ld.relaxed, both at once) at the top of item i and looked at when item i's first
+//     phase is done -- by then they have long arrived, and with the pipeline lag they are satisfied: item i+1 starts
+//     without waiting for anything.  Only if the early look failed does its top poll (still relaxed);
 //   * nothing invalidates L1: ring data is only ever read with ld.cg / cp.async.cg (L2), tables are immutable, the
 //     per-radix tables live in shared memory; the completion signal is one red.release issued by a thread of another
 //     warp than the one that handles tickets, so neither waits for the other;
@@ -338,7 +342,6 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
   cpx<T>* twRs = tile + 16 * 256;                               // per-radix tables of every pass (<= 4 x 256 entries)
   cpx<T>* staging = twRs + 1024;                                // PREFETCH only
-  __shared__ unsigned s_cur, s_next;
   __shared__ int s_cur_ready, s_cur_pf, s_next_ready, s_next_pf;
   __shared__ TsStage ST[kTsMaxStages];
   const int t = threadIdx.x;
@@ -346,16 +349,14 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
   if (t == 0) {
 #pragma unroll
     for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];       // constant indices: plain constant-bank reads
-    s_cur = atomicAdd(P.counters, 1u); s_next = atomicAdd(P.counters, 1u); s_cur_ready = 0; s_cur_pf = 0;
+    s_cur_ready = 0; s_cur_pf = 0;
   }
   __syncthreads();
-  unsigned cur = s_cur;
-  while (cur < P.total_items) {
-    // ---- thread 0: ticket i+2, readiness of item i (poll only if the early look failed), early look at item i+1
-    // (only three values stay live across the FFT bodies: the ticket and the two counter reads in flight)
-    unsigned t_next2 = 0, li = 0, lf = 0;
+  for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
+    const unsigned nxt = cur + gridDim.x;                         // (total_items + gridDim.x < 2^32: checked by the host)
+    // ---- thread 0: readiness of item i (poll only if the early look failed), early look at item i+1
+    unsigned li = 0, lf = 0;
     if (t == 0) {
-      t_next2 = atomicAdd(P.counters, 1u);
       int stage, item; long long tr;
       if (!s_cur_ready && ts_decode(P, ST, cur, &stage, &tr, &item)) {
         const TsDeps d = ts_deps(P, ST, stage, tr);
@@ -365,11 +366,10 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
           __nanosleep(100);
         }
       }
-      const unsigned nxt = s_next;
       int nstage, nitem; long long ntr;
       if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
         const TsDeps nd = ts_deps(P, ST, nstage, ntr);
-        if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);             // in flight during the whole item
+        if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);             // in flight during phase 1
         if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
       }
     }
@@ -392,7 +392,6 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     }
     if (t == 0) {                                                 // is item i+1 known to be ready?
       int n_ok = 0, pf = 0;
-      const unsigned nxt = s_next;
       int nstage, nitem; long long ntr;
       if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
         const TsDeps nd = ts_deps(P, ST, nstage, ntr);
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     __syncthreads();
     if (PREFETCH && s_next_pf) {                                  // staging was consumed in phase 1 (barrier above)
       int nstage, nitem; long long ntr;
-      ts_decode(P, ST, s_next, &nstage, &ntr, &nitem);
+      ts_decode(P, ST, nxt, &nstage, &ntr, &nitem);
       ts_prefetch_item<T>(t, ST[nstage], nitem, ts_src(P, ST[nstage].src, ntr), staging);
     }
     if (live) {
@@ -417,10 +416,9 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
       else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     }
-    if (t == 0) { s_cur = s_next; s_cur_ready = s_next_ready; s_cur_pf = s_next_pf; s_next = t_next2; }
+    if (t == 0) { s_cur_ready = s_next_ready; s_cur_pf = s_next_pf; }
     __syncthreads();                                              // every store of the item is issued; tile is free again
     if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage, tr).done);   // another warp than thread 0's
-    cur = s_cur;
   }
   if (PREFETCH) ts_cp_async_wait_all();
 }

@@ -168,3 +168,67 @@ extern "C" int emu_ts(int prec, int N, int transform, int dir, int ordered, cons
   return emu_ts_t<double>(N, transform, dir, ordered, (const double*)in, (double*)out, batch, lag, window, seed);
 }
 extern "C" int emu_ts_factorize(int Nc, int* P, int* A) { return ts_factorize(Nc, P, A) ? 1 : 0; }
+
+// ---- compile-time-radix CTA kernels (radix_kernels.cuh): the stages of one transform stepped thread by thread
+#include "../../pffft_b200/csrc/radix_kernels.cuh"
+template <typename T, int R1, int R2, int R3, int LM, int SM, int SIGN>
+static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cpx<T>* twr) {
+  using S = RadixShape<R1, R2, R3>;
+  constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  std::vector<cpx<T>> buf(S::NCP);
+  std::vector<T> o(2 * (size_t)S::NC);
+  if (S::STAGES == 1) {
+    for (int li = 0; li < S::TT; ++li) { cpx<T> v[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), v); radix_emit<T, R1, S::M1, SM>(li, v, o.data(), N, buf.data()); }
+  } else if (S::STAGES == 2) {
+    for (int li = 0; li < S::TT; ++li) { cpx<T> d[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), d); }
+    std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
+    for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
+    for (int li = 0; li < S::M2; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; dft_small<R2, SIGN>(a); radix_emit<T, R2, S::M2, SM>(li, a, o.data(), N, buf.data()); }
+  } else {
+    for (int li = 0; li < S::TT; ++li) { cpx<T> d[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), d); }
+    std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
+    for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
+    for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; radix_stage2_write<T, R1, R2, R3, SIGN>(li, a, tw, buf.data()); }
+    std::vector<std::vector<cpx<T>>> r3(S::TT, std::vector<cpx<T>>(R3));
+    for (int li = 0; li < S::TT; ++li) { cpx<T> c[R3]; radix_stage3_read<T, R1, R2, R3>(li, buf.data(), c); for (int j = 0; j < R3; ++j) r3[li][j] = c[j]; }
+    for (int li = 0; li < S::M3; ++li) { cpx<T> c[R3]; for (int j = 0; j < R3; ++j) c[j] = r3[li][j]; dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, o.data(), N, buf.data()); }
+  }
+  if (partner) for (int k = 0; k < S::NC; ++k) store_core<SM, T>(o.data(), buf.data(), k, N, S::NC, twr, N, true);
+  memcpy(out, o.data(), sizeof(T) * 2 * (size_t)S::NC);
+}
+template <int R1, int R2, int R3>
+static int radix_emu_modes(int N, int lm, int sm, int sign, const float* in, float* out, const cf* tw, const cf* twr) {
+#define PF_RX(L, S_, SG) if (lm == L && sm == S_ && sign == SG) { radix_emulate<float, R1, R2, R3, L, S_, SG>(in, out, N, tw, twr); return 0; }
+  PF_RX(L_C_ORD, S_C_ORD, -1) PF_RX(L_C_ORD, S_C_ORD, +1) PF_RX(L_C_ORD, S_C_Z, -1) PF_RX(L_C_Z, S_C_ORD, +1)
+  PF_RX(L_R_TIME, S_R_ORD, -1) PF_RX(L_R_TIME, S_R_Z, -1) PF_RX(L_R_ORD, S_R_TIME, +1) PF_RX(L_R_Z, S_R_TIME, +1)
+#undef PF_RX
+  return -2;
+}
+extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float* in, float* out) {
+  const int Nc = transform == 0 ? N / 2 : N;
+  std::vector<float> tw(2 * (size_t)Nc), twr(2 * (size_t)(N / 2));
+  pfplan::fill_roots<float>(tw.data(), Nc, Nc);
+  pfplan::fill_roots<float>(twr.data(), N / 2, N);
+  const cf* t1 = reinterpret_cast<const cf*>(tw.data()); const cf* t2 = reinterpret_cast<const cf*>(twr.data());
+  int lm, sm; const bool fwd = dir == 0;
+  if (transform == 1) { lm = (fwd || ordered) ? L_C_ORD : L_C_Z; sm = (fwd && !ordered) ? S_C_Z : S_C_ORD; }
+  else if (fwd) { lm = L_R_TIME; sm = ordered ? S_R_ORD : S_R_Z; }
+  else { lm = ordered ? L_R_ORD : L_R_Z; sm = S_R_TIME; }
+  const int sign = fwd ? -1 : +1;
+  switch (Nc) {
+    case 16: return radix_emu_modes<4, 4, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 48: return radix_emu_modes<16, 3, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 80: return radix_emu_modes<16, 5, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 144: return radix_emu_modes<12, 12, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 240: return radix_emu_modes<16, 15, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 400: return radix_emu_modes<20, 20, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 432: return radix_emu_modes<12, 12, 3>(N, lm, sm, sign, in, out, t1, t2);
+    case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
+    case 2000: return radix_emu_modes<20, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 2592: return radix_emu_modes<18, 12, 12>(N, lm, sm, sign, in, out, t1, t2);
+    case 4000: return radix_emu_modes<20, 20, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 6000: return radix_emu_modes<20, 20, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 12000: return radix_emu_modes<25, 24, 20>(N, lm, sm, sign, in, out, t1, t2);
+  }
+  return -1;
+}

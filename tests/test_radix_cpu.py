@@ -1,0 +1,43 @@
+"""Compile-time-radix CTA kernels (pffft_b200/csrc/radix_kernels.cuh) stepped on the CPU through tests/emu: every core of
+the table, every API mode, against the unmodified reference.  No GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, uniform
+
+EMU = os.path.join(ROOT, "tests", "emu", "libemu.so")
+CORES = [16, 48, 80, 144, 240, 400, 432, 1296, 2000, 2592, 4000, 6000, 12000]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(EMU):
+        pytest.skip("tests/emu/libemu.so not built (python __graft_entry__.py)")
+    e = C.CDLL(EMU)
+    e.emu_radix.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    return e
+
+
+def _run(emu, N, tr, d, ordered, x):
+    x = np.ascontiguousarray(x, np.float32)
+    o = np.full_like(x, np.nan)
+    assert emu.emu_radix(N, tr, d, ordered, x.ctypes.data, o.ctypes.data) == 0
+    return o
+
+
+@pytest.mark.parametrize("tr", [1, 0])
+@pytest.mark.parametrize("core", CORES)
+def test_every_core_and_mode_vs_reference(emu, ref, R, core, tr):
+    N = core if tr == 1 else 2 * core
+    rng = np.random.default_rng(core + tr)
+    x = uniform(rng, 2 * core)
+    fo = _run(emu, N, tr, 0, 1, x)
+    fz = _run(emu, N, tr, 0, 0, x)
+    assert R.relmax(fo, ref.transform(N, tr, x, 0, True)) <= 1e-5
+    assert R.relmax(fz, ref.transform(N, tr, x, 0, False)) <= 1e-5
+    assert np.array_equal(ref.zreorder(N, tr, fz, 0), fo)            # ordered == zreorder(unordered), bit-exact
+    assert R.relmax(_run(emu, N, tr, 1, 1, fo), x * N) <= 1e-5
+    assert R.relmax(_run(emu, N, tr, 1, 0, fz), x * N) <= 1e-5

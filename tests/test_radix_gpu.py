@@ -1,0 +1,39 @@
+"""Compile-time-radix CTA kernels on hardware (pffft_b200/csrc/radix_kernels.cuh): every core of the table, complex and
+real, ordered and z-domain, forward and backward, batches that wrap the persistent grid, against the reference."""
+import numpy as np
+import pytest
+
+from conftest import uniform
+
+pytestmark = pytest.mark.gpu
+CORES = [16, 48, 80, 144, 240, 400, 432, 1296, 2000, 2592, 4000, 6000, 12000]
+
+
+@pytest.fixture()
+def radix_on(monkeypatch):
+    monkeypatch.setenv("PFFFT_B200_RADIX", "1")
+
+
+@pytest.mark.parametrize("tr", [1, 0])
+@pytest.mark.parametrize("core", CORES)
+def test_every_core_and_mode_vs_reference(pf, ref, R, radix_on, core, tr):
+    import torch
+    N = core if tr == 1 else 2 * core
+    rng = np.random.default_rng(core * 2 + tr)
+    batch = max(5, min(40000, (64 << 20) // (8 * core)))              # ~64 MB: many times the resident CTAs
+    x = uniform(rng, batch * 2 * core).reshape(batch, 2 * core)
+    with pf.Setup(N, tr) as s:
+        assert s.kernel.startswith("radix_"), s.kernel
+        xd = torch.from_numpy(x).cuda()
+        fo = s.transform_batch(xd, 0, True); fz = s.transform_batch(xd, 0, False)
+        bo = s.transform_batch(fo, 1, True); bz = s.transform_batch(fz, 1, False)
+        ro = s.zreorder_batch(fz, 0)
+        inpl = xd.clone(); s.transform_batch(inpl, 0, True, out=inpl)
+        torch.cuda.synchronize()
+        assert torch.equal(ro, fo) and torch.equal(inpl, fo)
+        assert float((bo / N - xd).abs().max()) <= 1e-5 and float((bz / N - xd).abs().max()) <= 1e-5
+        idx = [0, 1, batch // 2, batch - 2, batch - 1]
+        fo_, fz_ = fo[idx].cpu().numpy(), fz[idx].cpu().numpy()
+    wo = ref.transform_batch(N, tr, x[idx], 0, True); wz = ref.transform_batch(N, tr, x[idx], 0, False)
+    for j in range(len(idx)):
+        assert R.relmax(fo_[j], wo[j]) <= 1e-5 and R.relmax(fz_[j], wz[j]) <= 1e-5
