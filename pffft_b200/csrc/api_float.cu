@@ -146,14 +146,14 @@ static bool float_split_for(int N, int transform, int* R, int* N2) {
 
 // ---- compile-time-radix CTA kernels (radix_kernels.cuh): cores that are neither 32*R2 nor 256*C.  PFFFT_B200_RADIX=0 off.
 static bool radix_wanted(int Nc) {
-  static const int mode = getenv("PFFFT_B200_RADIX") ? atoi(getenv("PFFFT_B200_RADIX")) : 0;   // opt-in until measured
+  static const int mode = getenv("PFFFT_B200_RADIX") ? atoi(getenv("PFFFT_B200_RADIX")) : 1;   // default on (profiles/r02_radix.md)
   return mode != 0 && radix_core_supported(Nc, nullptr);
 }
 
 template <> struct FastHooks<float> {
   static bool is_warp1024(int N, int transform) { return transform == XF_COMPLEX && N == 1024; }
   static size_t extra_table_cpx(int N, int transform) {
-    if (ts_wanted(transform == XF_REAL ? N / 2 : N) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return 0;
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N, false) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return 0;
     if (is_warp1024(N, transform)) return 1024;
     if (wsmall_R2_for(N, transform) || wmixed_R2_for(N, transform)) return (size_t)(transform == XF_REAL ? N / 2 : N);
     { const int Nc = transform == XF_REAL ? N / 2 : N; int R = 0, N2 = 0;
@@ -161,7 +161,7 @@ template <> struct FastHooks<float> {
     return CtaOnlyHooks<float>::extra_table_cpx(N, transform);
   }
   static void fill_extra_table(int N, int transform, float* dst) {
-    if (ts_wanted(transform == XF_REAL ? N / 2 : N) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return;
+    if (ts_wanted(transform == XF_REAL ? N / 2 : N, false) || radix_wanted(transform == XF_REAL ? N / 2 : N)) return;
     if (is_warp1024(N, transform)) {                        // tw[k2*32 + n1] = exp(-2 pi i n1 k2 / 1024)
       for (int k2 = 0; k2 < 32; ++k2)
         for (int n1 = 0; n1 < 32; ++n1) {
@@ -200,7 +200,7 @@ template <> struct FastHooks<float> {
     CtaOnlyHooks<float>::fill_extra_table(N, transform, dst);
   }
   static bool plan(Setup<float>* s) {
-    if (ts_wanted(s->Nc)) return ts_plan<float>(s);
+    if (ts_wanted(s->Nc, false)) return ts_plan<float>(s);
     if (radix_wanted(s->Nc)) {
       const char* nm = "";
       radix_core_supported(s->Nc, &nm);
@@ -235,7 +235,7 @@ template <> struct FastHooks<float> {
         s->split_fused = !getenv("PFFFT_B200_NO_FUSED_SPLIT") && split_fused_ok<float>(R, N2);
         s->fast_variant = 300;
         int CL = 0, Q = 1, mode = 0, a1 = 0, a2 = 0;
-        if (t2dg_requested() && t2dg_shape_for(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_float(s->Nc)) != nullptr) {
+        if (t2dg_wanted(s->Nc, false) && t2dg_shape_for(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_float(s->Nc)) != nullptr) {
           s->split_fused = false;
           snprintf(s->name_buf, sizeof(s->name_buf), "tiled2dg_%dx%d", 16 * a1, 16 * a2);
         } else if (t2d_enabled(s->Nc) && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {

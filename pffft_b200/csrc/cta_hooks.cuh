@@ -163,14 +163,17 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 // ---- tiled Stockham pipeline (ts_kernels.cuh / ts.cu): complex cores that factor into 2-4 radices 16*A, one persistent
 // kernel, intermediates resident in L2.  PFFFT_B200_TS=0 never, =1 every factorisable core >= PFFFT_B200_TS_MIN (default
 // 8192); unset: the measured default range.
-inline bool ts_wanted(int Nc) {
-  int lo = 131072;                                                // default: everything the single-launch plans do not cover
+inline bool ts_wanted(int Nc, bool dbl) {
+  // measured defaults (profiles/r02_large_n.md): everything above 65536 (the global multi-launch path it replaces ran at
+  // 0.08 of the roofline), and the double core 16384 (0.37 against 0.34 for the two-launch split plan)
+  bool want = Nc >= 131072 || (dbl && Nc == 16384);
   if (const char* e = getenv("PFFFT_B200_TS")) {
     if (atoi(e) == 0) return false;
-    lo = 8192;
+    int lo = 8192;
     if (const char* m = getenv("PFFFT_B200_TS_MIN")) lo = atoi(m);
+    want = Nc >= lo;
   }
-  if (Nc < lo) return false;
+  if (!want) return false;
   int P = 0, A[4];
   return ts_factorize(Nc, &P, A);
 }
@@ -181,6 +184,7 @@ inline void ts_modes(int transform, int direction, int ordered, int* lm, int* sm
   else if (fwd) { *lm = L_R_TIME; *sm = ordered ? S_R_ORD : S_R_Z; }
   else { *lm = ordered ? L_R_ORD : L_R_Z; *sm = S_R_TIME; }
 }
+template <typename T> inline bool ts_wanted_for(int Nc) { return ts_wanted(Nc, sizeof(T) == 8); }
 template <typename T> inline bool ts_plan(Setup<T>* s) {
   s->ts = ts_create(s->N, s->Nc, sizeof(T) == 8, s->device, s->sm_count);
   if (!s->ts) return false;
@@ -217,7 +221,15 @@ bool t2dg_shape_for_double(int Nc, int* A1, int* A2);            // double: the 
 cpx<double>* t2dg_make_tables_double(int Nc);
 int t2dg_launch_double(int Nc, int sign, const cpx<double>* x, cpx<double>* S, cpx<double>* X, long long batch,
                        const cpx<double>* tables, int sm_count, cudaStream_t st);
-inline bool t2dg_requested() { const char* e = getenv("PFFFT_B200_TILED2D_GENERAL"); return e && atoi(e) != 0; }
+// PFFFT_B200_TILED2D_GENERAL=0 never, =1 every shape that exists; unset: where it measured faster than the split / tiled
+// plans on hardware (profiles/r02_large_n.md): float 20480 .. 65536 except the cores a single CTA or cluster holds; double 32768, 65536
+inline bool t2dg_wanted(int Nc, bool dbl) {
+  if (const char* e = getenv("PFFFT_B200_TILED2D_GENERAL")) return atoi(e) != 0;
+  if (getenv("PFFFT_B200_TILED2D")) return false;                 // an explicit choice among the other tiled plans wins
+  if (dbl) return Nc == 32768 || Nc == 65536;
+  switch (Nc) { case 20480: case 24576: case 36864: case 40960: case 49152: case 61440: case 65536: return true; }
+  return false;
+}
 // cluster-fused form of the same plan (8-CTA clusters, pass A -> pass C through DSMEM, one HBM round trip): verified by CPU
 // stepping, NOT YET RUN ON HARDWARE -> only with PFFFT_B200_TILED2D=2
 int t2d_cluster_max_active_float(int Nc);
@@ -431,18 +443,18 @@ template <typename T> struct CtaOnlyHooks {
   }
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    if (ts_wanted(Nc)) return 0;
+    if (ts_wanted_for<T>(Nc)) return 0;
     const int n2 = rows_size(N, transform);
     return n2 ? split_table_cpx(Nc, n2) : cta_table_cpx(Nc);
   }
   static void fill_extra_table(int N, int transform, T* dst) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    if (ts_wanted(Nc)) return;
+    if (ts_wanted_for<T>(Nc)) return;
     const int n2 = rows_size(N, transform);
     if (n2) split_fill_tables<T>(Nc, n2, dst); else cta_fill_tables<T>(Nc, dst);
   }
   static bool plan(Setup<T>* s) {
-    if (ts_wanted(s->Nc)) return ts_plan<T>(s);
+    if (ts_wanted_for<T>(s->Nc)) return ts_plan<T>(s);
     int R = 0, N2 = 0; bool fused = false;
     if (decompose(s->Nc, &R, &N2, &fused)) {
       if (getenv("PFFFT_B200_NO_SPLIT")) return false;
@@ -451,7 +463,7 @@ template <typename T> struct CtaOnlyHooks {
       snprintf(s->name_buf, sizeof(s->name_buf), fused ? "cta_split_%dx%d" : "split_%dx%d", R, N2);
       if constexpr (sizeof(T) == 8) {                            // opt-in tiled plan for doubles (not yet run on hardware)
         int a1 = 0, a2 = 0;
-        if (t2dg_requested() && t2dg_shape_for_double(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_double(s->Nc)) != nullptr) {
+        if (t2dg_wanted(s->Nc, true) && t2dg_shape_for_double(s->Nc, &a1, &a2) && (s->d_aux_tables = t2dg_make_tables_double(s->Nc)) != nullptr) {
           s->split_fused = false;
           snprintf(s->name_buf, sizeof(s->name_buf), "tiled2dg_%dx%d", 16 * a1, 16 * a2);
         }

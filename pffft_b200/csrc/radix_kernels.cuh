@@ -143,7 +143,8 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
     }
     if (partner) {
       __syncthreads();
-      if (live) for (int k = li; k < S::NC; k += S::TT) store_core<SM, T>(obase, buf, k, N, S::NC, twr, N, true);
+      // bins k and Nc-k share their sum, difference and twiddle: one pass over half the spectrum (k = 0 also emits Nc/2)
+      if (live) for (int k = li; k < S::NC / 2; k += S::TT) real_post_pair<SM, T>(obase, buf, k, N, S::NC, twr);
     }
     __syncthreads();                                              // buffer is rewritten by the next group's stage 1
   }

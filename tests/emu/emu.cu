@@ -193,7 +193,7 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
     for (int li = 0; li < S::TT; ++li) { cpx<T> c[R3]; radix_stage3_read<T, R1, R2, R3>(li, buf.data(), c); for (int j = 0; j < R3; ++j) r3[li][j] = c[j]; }
     for (int li = 0; li < S::M3; ++li) { cpx<T> c[R3]; for (int j = 0; j < R3; ++j) c[j] = r3[li][j]; dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, o.data(), N, buf.data()); }
   }
-  if (partner) for (int k = 0; k < S::NC; ++k) store_core<SM, T>(o.data(), buf.data(), k, N, S::NC, twr, N, true);
+  if (partner) for (int k = 0; k < S::NC / 2; ++k) real_post_pair<SM, T>(o.data(), buf.data(), k, N, S::NC, twr);
   memcpy(out, o.data(), sizeof(T) * 2 * (size_t)S::NC);
 }
 template <int R1, int R2, int R3>

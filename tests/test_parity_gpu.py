@@ -355,22 +355,32 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(800, 1) as s:
         assert s.kernel == "warp_32x25"
     with pf.Setup(4000, 1) as s:
-        assert s.kernel == "split_5x800"
+        assert s.kernel == "radix_20x20x10"
+    with pf.Setup(2400, 1) as s:
+        assert s.kernel == "split_3x800"
     with pf.Setup(36864, 1) as s:
-        assert s.kernel == "split_9x4096"
+        assert s.kernel == "tiled2dg_192x192"
     with pf.Setup(8192, 1) as s:
         assert s.kernel == "cta_split_2x4096"
     with pf.Setup(9216, 1) as s:
         assert s.kernel == "cta_split_9x1024"
     with pf.Setup(144, 1) as s:
+        assert s.kernel == "radix_12x12"
+    with pf.Setup(720, 1) as s:
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
-        assert s.kernel == "tiled2d_256x256"
-    with pf.Setup(36864, 1) as s:
-        assert s.kernel == "split_9x4096"
+        assert s.kernel == "tiled2dg_256x256"
+    with pf.Setup(32768, 1) as s:
+        assert s.kernel == "tiled2d_256x128"
+    with pf.Setup(65536, 1, np.float64) as s:
+        assert s.kernel == "tiled2dg_256x256"
+    with pf.Setup(16384, 1, np.float64) as s:
+        assert s.kernel == "ts_128x128"
     with pf.Setup(16384, 1) as s:
         assert s.kernel in ("cluster4_4x4096", "split_4x4096")      # 4-CTA clusters where the device schedules them
     with pf.Setup(1 << 20, 1) as s:
+        assert s.kernel == "ts_128x128x64"
+    with pf.Setup(250000, 1) as s:                               # 16 * 5^6: too few factors of two for the tiled pipeline
         assert s.kernel == "global_stockham"
     with pf.Setup(256, 1) as s:
         assert s.kernel == "warp_32x8"

@@ -51,12 +51,10 @@ def test_tiled2d_vs_reference(pf, ref, R, Nc, tr):
         s.close()
 
 
-@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_CLUSTER") != "1",
-                    reason="opt-in: the cluster-fused tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_CLUSTER=1)")
 @pytest.mark.parametrize("Nc", [16384, 32768, 65536])
 def test_tiled2d_cluster_fused_vs_reference(pf, ref, R, Nc):
-    """PFFFT_B200_TILED2D=2: pass A hands its rows to pass C through DSMEM (8-CTA clusters).  Written after the GPU budget
-    of round 1 was spent: verified by CPU stepping only (tests/test_host_logic.py), first thing to run next round."""
+    """PFFFT_B200_TILED2D=2: pass A hands its rows to pass C through DSMEM (8-CTA clusters).  First run on hardware at the start of round 2
+    (profiles/r02_large_n.md): correct, 0.39-0.48 of the roofline -- not faster than the two-launch form, so it stays opt-in."""
     import torch
     old = os.environ.get("PFFFT_B200_TILED2D")
     os.environ["PFFFT_B200_TILED2D"] = "2"
@@ -85,8 +83,6 @@ def test_tiled2d_cluster_fused_vs_reference(pf, ref, R, Nc):
         s.close()
 
 
-@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_GENERAL") != "1",
-                    reason="opt-in: the general-radix tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_GENERAL=1)")
 @pytest.mark.parametrize("Nc", [7680, 9216, 12288, 20480, 24576, 36864, 40960, 49152, 61440, 16384, 65536])
 def test_tiled2d_general_radix_vs_reference(pf, ref, R, Nc):
     """PFFFT_B200_TILED2D_GENERAL=1: Nc = 256*A1*A2 with radix-3/5 factors.  CPU-stepped only so far."""
@@ -114,8 +110,6 @@ def test_tiled2d_general_radix_vs_reference(pf, ref, R, Nc):
         s.close()
 
 
-@pytest.mark.skipif(os.environ.get("PFFFT_B200_TEST_T2D_GENERAL") != "1",
-                    reason="opt-in: the double-precision tiled plan has not run on hardware yet (PFFFT_B200_TEST_T2D_GENERAL=1)")
 @pytest.mark.parametrize("Nc", [16384, 32768, 65536])
 def test_tiled2d_double_vs_numpy(pf, Nc):
     import torch
