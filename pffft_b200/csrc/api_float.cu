@@ -240,7 +240,7 @@ template <> struct FastHooks<float> {
           snprintf(s->name_buf, sizeof(s->name_buf), "tiled2dg_%dx%d", 16 * a1, 16 * a2);
         } else if (t2d_enabled(s->Nc) && cta_C_for(N2) && t2d_shape_for(s->Nc, &a1, &a2)) {
           s->split_t2d = true; s->split_fused = false;
-          s->split_t2d_cluster = t2d_cluster_requested() && t2d_cluster_max_active_float(s->Nc) > 0;
+          s->split_t2d_cluster = t2d_cluster_requested(s->Nc) && t2d_cluster_max_active_float(s->Nc) > 0;
           snprintf(s->name_buf, sizeof(s->name_buf), s->split_t2d_cluster ? "tiled2d_cluster8_%dx%d" : "tiled2d_%dx%d", 16 * a1, 16 * a2);
         } else if (cluster_choose(R, N2, &CL, &Q, &mode)) {
           s->split_cluster = CL; s->split_Q = Q; s->split_mode = mode; s->split_fused = false;

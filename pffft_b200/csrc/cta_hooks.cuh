@@ -166,7 +166,8 @@ int split_combine(Setup<T>* s, const cpx<T>* rows, cpx<T>* dst, long long batch,
 inline bool ts_wanted(int Nc, bool dbl) {
   // measured defaults (profiles/r02_large_n.md): everything above 65536 (the global multi-launch path it replaces ran at
   // 0.08 of the roofline), and the double core 16384 (0.37 against 0.34 for the two-launch split plan)
-  bool want = Nc >= 131072 || (dbl && Nc == 16384);
+  const bool other_choice = getenv("PFFFT_B200_TILED2D_GENERAL") || getenv("PFFFT_B200_TILED2D");   // explicit plan switches win
+  bool want = Nc >= 131072 || (dbl && Nc == 16384 && !other_choice);
   if (const char* e = getenv("PFFFT_B200_TS")) {
     if (atoi(e) == 0) return false;
     int lo = 8192;
@@ -235,11 +236,13 @@ inline bool t2dg_wanted(int Nc, bool dbl) {
 int t2d_cluster_max_active_float(int Nc);
 int t2d_cluster_launch_float(int Nc, int sign, const cpx<float>* x, cpx<float>* X, long long batch,
                              const cpx<float>* tables, cudaStream_t st);
-inline bool t2d_cluster_requested() { const char* e = getenv("PFFFT_B200_TILED2D"); return e && atoi(e) == 2; }
+// measured on hardware in round 2 (profiles/r02_large_n.md): 16384: 0.48 (4-CTA cluster kernel 0.41, two-launch tiled 0.39) ->
+// the default there; 32768: 0.39, 65536: 0.43 -> not faster than the two-launch forms, opt-in (PFFFT_B200_TILED2D=2)
+inline bool t2d_cluster_requested(int Nc) { const char* e = getenv("PFFFT_B200_TILED2D"); return e ? atoi(e) == 2 : Nc == 16384; }
 inline bool t2d_enabled(int Nc) {
   const char* e = getenv("PFFFT_B200_TILED2D");
   if (e) return atoi(e) != 0;
-  return Nc == 32768 || Nc == 65536;
+  return Nc == 16384 || Nc == 32768 || Nc == 65536;
 }
 
 // ---- cluster variant (cluster_kernels.cuh, instantiated in cluster.cu): float complex cores (CL*Q) x 4096, rows parked

@@ -36,20 +36,46 @@ template <int R1, int R2, int R3> struct RadixShape {
 // W_Nc^{e} for SIGN (table holds the forward roots)
 template <int SIGN, typename T> PF_HD cpx<T> radix_tw(cpx<T> v, const cpx<T>* tw, int e) { return cmul_dir<SIGN>(v, ldtab(tw + e)); }
 
+// ---- backward real: the packed half-length spectrum Z' = 2 (E + i O) is built PAIR-WISE in shared memory first --
+// bins k and Nc-k share their sum, difference and twiddle -- instead of letting every stage-1 load rebuild
+// its element from two mirrored global reads.  `nat` receives Z' in natural order.
+template <typename T, int LM>
+PF_HD void radix_prerotate(int li, int TT, const T* ibase, int N, int Nc, const cpx<T>* twr, cpx<T>* nat) {
+  constexpr bool Z = (LM == L_R_Z);
+  for (int k = li; k < Nc / 2; k += TT) {
+    if (k == 0) {
+      const cpx<T> s0 = spec_get<Z, true>(ibase, 0, N);                 // (X[0], X[N/2])
+      nat[0] = mk<T>(s0.x + s0.y, s0.x - s0.y);
+      const cpx<T> am = spec_get<Z, true>(ibase, Nc / 2, N);            // self-paired middle bin: Z'[Nc/2] = 2 conj X[Nc/2]
+      nat[Nc / 2] = mk<T>(T(2) * am.x, T(-2) * am.y);
+      continue;
+    }
+    const cpx<T> a = spec_get<Z, true>(ibase, k, N);
+    const cpx<T> b = conj(spec_get<Z, true>(ibase, Nc - k, N));
+    const cpx<T> s = a + b, d = a - b;
+    const cpx<T> u = cmul_dir<+1>(d, ldtab(twr + k));                   // d * exp(+2 pi i k / N)
+    nat[k] = mk<T>(s.x - u.y, s.y + u.x);                               // s + i u
+    nat[Nc - k] = mk<T>(s.x + u.y, u.x - s.y);                          // conj(s) + i conj(u)
+  }
+}
+
 // ---- the three stages of ONE transform for thread li (0 <= li < TT); `buf` = this transform's shared buffer
-template <typename T, int R1, int R2, int R3, int LM, int SIGN>
-PF_HD void radix_stage1(int li, const T* ibase, int N, const cpx<T>* tw, const cpx<T>* twr, cpx<T>* buf, cpx<T> (&last)[R1]) {
+// stage 1, first half: the R1 inputs of butterfly li -- from global memory (any load mode) or from the natural-order
+// shared buffer a pre-rotation left behind
+template <typename T, int R1, int R2, int R3, int LM, bool FROM_SMEM>
+PF_HD void radix_stage1_load(int li, const T* ibase, int N, const cpx<T>* twr, const cpx<T>* nat, cpx<T> (&a)[R1]) {
   using S = RadixShape<R1, R2, R3>;
   if (li >= S::M1) return;
-  cpx<T> a[R1];
 #pragma unroll
-  for (int j = 0; j < R1; ++j) a[j] = load_core<LM, T>(ibase, li + j * S::M1, N, S::NC, twr, -1, true);
+  for (int j = 0; j < R1; ++j) a[j] = FROM_SMEM ? nat[li + j * S::M1] : load_core<LM, T>(ibase, li + j * S::M1, N, S::NC, twr, -1, true);
+}
+// second half: DFT, * W_Nc^{b k}, into the padded stage-1 layout (single-stage plans keep the result in `a`)
+template <typename T, int R1, int R2, int R3, int SIGN>
+PF_HD void radix_stage1_store(int li, cpx<T> (&a)[R1], const cpx<T>* tw, cpx<T>* buf) {
+  using S = RadixShape<R1, R2, R3>;
+  if (li >= S::M1) return;
   dft_small<R1, SIGN>(a);
-  if (S::STAGES == 1) {
-#pragma unroll
-    for (int k = 0; k < R1; ++k) last[k] = a[k];
-    return;
-  }
+  if (S::STAGES == 1) return;
   buf[S::idx1(R1 * li)] = a[0];
 #pragma unroll
   for (int k = 1; k < R1; ++k) buf[S::idx1(R1 * li + k)] = radix_tw<SIGN>(a[k], tw, li * k);
@@ -113,21 +139,26 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
     const bool live = t0 + tl < batch;
     const T* ibase = in + (t0 + tl) * (2LL * S::NC);
     T* obase = out + (t0 + tl) * (2LL * S::NC);
+    constexpr bool prerot = (LM == L_R_ORD || LM == L_R_Z);       // backward real: pair-wise pre-rotation through `buf`
+    cpx<T> v1[R1];
+    if (prerot) {
+      if (live) radix_prerotate<T, LM>(li, S::TT, ibase, N, S::NC, twr, buf);
+      __syncthreads();
+      if (live) radix_stage1_load<T, R1, R2, R3, LM, true>(li, ibase, N, twr, buf, v1);
+      if (S::STAGES > 1) __syncthreads();                         // stage 1 overwrites the buffer it has just read
+    } else if (live) {
+      radix_stage1_load<T, R1, R2, R3, LM, false>(li, ibase, N, twr, buf, v1);
+    }
+    if (live) radix_stage1_store<T, R1, R2, R3, SIGN>(li, v1, tw, buf);
     if (S::STAGES == 1) {
-      cpx<T> v[R1];
-      if (live) {
-        radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, v);
-        radix_emit<T, R1, S::M1, SM>(li, v, obase, N, buf);
-      }
+      if (live) radix_emit<T, R1, S::M1, SM>(li, v1, obase, N, buf);
     } else if (S::STAGES == 2) {
-      { cpx<T> dummy[R1]; if (live) radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, dummy); }
       __syncthreads();
       cpx<T> a[R2];
       if (live) radix_stage2_read<T, R1, R2, R3>(li, buf, a);
       if (partner) __syncthreads();                               // `buf` becomes the natural-order buffer
       if (live && li < S::M2) { dft_small<R2, SIGN>(a); radix_emit<T, R2, S::M2, SM>(li, a, obase, N, buf); }
     } else {
-      { cpx<T> dummy[R1]; if (live) radix_stage1<T, R1, R2, R3, LM, SIGN>(li, ibase, N, tw, twr, buf, dummy); }
       __syncthreads();
       {
         cpx<T> a[R2];

@@ -177,15 +177,26 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
   std::vector<cpx<T>> buf(S::NCP);
   std::vector<T> o(2 * (size_t)S::NC);
-  if (S::STAGES == 1) {
-    for (int li = 0; li < S::TT; ++li) { cpx<T> v[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), v); radix_emit<T, R1, S::M1, SM>(li, v, o.data(), N, buf.data()); }
-  } else if (S::STAGES == 2) {
-    for (int li = 0; li < S::TT; ++li) { cpx<T> d[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), d); }
+  constexpr bool prerot = (LM == L_R_ORD || LM == L_R_Z);
+  if (prerot) for (int li = 0; li < S::TT; ++li) radix_prerotate<T, LM>(li, S::TT, in, N, S::NC, twr, buf.data());
+  std::vector<std::vector<cpx<T>>> r1(S::TT, std::vector<cpx<T>>(R1));
+  for (int li = 0; li < S::TT; ++li) {
+    cpx<T> a[R1];
+    if (prerot) radix_stage1_load<T, R1, R2, R3, LM, true>(li, in, N, twr, buf.data(), a);
+    else radix_stage1_load<T, R1, R2, R3, LM, false>(li, in, N, twr, buf.data(), a);
+    for (int j = 0; j < R1; ++j) r1[li][j] = a[j];
+  }
+  for (int li = 0; li < S::TT; ++li) {
+    cpx<T> a[R1];
+    for (int j = 0; j < R1; ++j) a[j] = r1[li][j];
+    radix_stage1_store<T, R1, R2, R3, SIGN>(li, a, tw, buf.data());
+    if (S::STAGES == 1) radix_emit<T, R1, S::M1, SM>(li, a, o.data(), N, buf.data());
+  }
+  if (S::STAGES == 2) {
     std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
     for (int li = 0; li < S::M2; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; dft_small<R2, SIGN>(a); radix_emit<T, R2, S::M2, SM>(li, a, o.data(), N, buf.data()); }
-  } else {
-    for (int li = 0; li < S::TT; ++li) { cpx<T> d[R1]; radix_stage1<T, R1, R2, R3, LM, SIGN>(li, in, N, tw, twr, buf.data(), d); }
+  } else if (S::STAGES == 3) {
     std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; radix_stage2_write<T, R1, R2, R3, SIGN>(li, a, tw, buf.data()); }

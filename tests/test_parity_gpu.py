@@ -377,7 +377,7 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(16384, 1, np.float64) as s:
         assert s.kernel == "ts_128x128"
     with pf.Setup(16384, 1) as s:
-        assert s.kernel in ("cluster4_4x4096", "split_4x4096")      # 4-CTA clusters where the device schedules them
+        assert s.kernel in ("tiled2d_cluster8_128x128", "tiled2d_128x128")   # 8-CTA clusters where the device schedules them
     with pf.Setup(1 << 20, 1) as s:
         assert s.kernel == "ts_128x128x64"
     with pf.Setup(250000, 1) as s:                               # 16 * 5^6: too few factors of two for the tiled pipeline
