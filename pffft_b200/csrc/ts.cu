@@ -29,26 +29,15 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
-// kernel shapes (PFFFT_B200_TS_SHAPE): resident CTAs per SM the register budget is sized for; PREFETCH = the next work
-// item's input is staged in a second shared buffer by cp.async while the current one finishes
-//   0: 3 CTAs, direct reads     1: 3 CTAs, prefetch     2: 2 CTAs (128 registers), direct     3: 2 CTAs, prefetch
+// resident CTAs per SM the register budget is sized for: float 3 (80 registers, no spills), double 2 (128 registers);
+// PFFFT_B200_TS_MINB=2 selects the two-CTA float build (measured slower: 0.28 against 0.35 at 65536)
 template <typename T> struct TsKernels {
   using Kern = void (*)(const TsParams<T>);
-  static int shape() {
-    static const int v = getenv("PFFFT_B200_TS_SHAPE") ? atoi(getenv("PFFFT_B200_TS_SHAPE")) : (sizeof(T) == 8 ? 2 : 0);
-    return v < 0 || v > 3 ? 0 : v;
-  }
-  static size_t smem() {
-    const size_t item = (size_t)16 * 256 * sizeof(cpx<T>);
-    return item * ((shape() & 1) ? 2 : 1) + 1024 * sizeof(cpx<T>);
-  }
+  static bool two() { static const bool v = sizeof(T) == 8 || (getenv("PFFFT_B200_TS_MINB") && atoi(getenv("PFFFT_B200_TS_MINB")) == 2); return v; }
+  static size_t smem() { return ((size_t)16 * 256 + 1024) * sizeof(cpx<T>); }     // exchange tile + per-radix tables
   template <int SIGN> static Kern kern() {
-    switch (shape()) {
-      case 1: return (Kern)k_ts_pipeline<T, SIGN, 3, true>;
-      case 2: return (Kern)k_ts_pipeline<T, SIGN, 2, false>;
-      case 3: return (Kern)k_ts_pipeline<T, SIGN, 2, true>;
-      default: return (Kern)k_ts_pipeline<T, SIGN, 3, false>;
-    }
+    if constexpr (sizeof(T) == 8) return (Kern)k_ts_pipeline<T, SIGN, 2>;
+    else return two() ? (Kern)k_ts_pipeline<T, SIGN, 2> : (Kern)k_ts_pipeline<T, SIGN, 3>;
   }
   static Kern fwd() { return kern<-1>(); }
   static Kern bwd() { return kern<+1>(); }
@@ -145,7 +134,6 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   for (long long b0 = 0; b0 < batch; b0 += max_batch) {
     const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
     P.in = in + b0 * 2LL * h->Nc; P.out = out + b0 * 2LL * h->Nc; P.batch = nb;
-    P.in_aligned16 = (reinterpret_cast<uintptr_t>(P.in) & 15) == 0 ? 1 : 0;
     const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));

@@ -13,7 +13,7 @@
 //   The output is in natural order after the last pass: no transposes, no bit reversal, every HBM/L2 access a full line.
 //
 // ONE persistent kernel runs all passes (plus an element-wise pre-/post-rotation stage for real transforms and z-domain
-// layouts).  Work items are handed out by an atomic ticket in the order
+// layouts).  Work items are dealt out statically (item k to CTA k mod gridDim.x) in the order
 //        group g:  [pass 1 of transform g] [pass 2 of transform g - L] [pass 3 of transform g - 2L] ...
 // so pass i+1 of a transform is scheduled ~1.5 grid-fulls of tiles after pass i finished writing it: its input is still in
 // L2.  The intermediates are RINGS of 2L+1 transforms that are overwritten in place, so their dirty lines are re-written
@@ -21,7 +21,7 @@
 // round 1 moved 2x that and sat at 0.42-0.45 of the HBM roofline with both launches at ~0.85 of HBM speed).
 // Dependencies (per ring slot, cumulative counters): a tile of pass i+1 waits until all tiles of pass i of its transform
 // are stored (release/acquire on a global counter); a tile that writes a ring slot waits until the slot's previous
-// occupant has been consumed.  Every wait is on tickets handed out EARLIER, the grid is sized to be co-resident, so the
+// occupant has been consumed.  Every wait is on items with a SMALLER index, the grid is sized to be co-resident, so the
 // scheme cannot deadlock.  Ring data is read with ld.global.cg (L2 only): a stale L1 line of a recycled slot is impossible.
 // Transforms too large for L2 (> ~16 MB) run the same code with rings of 1-3 slots; the traffic then goes to HBM.
 //
@@ -62,7 +62,6 @@ template <typename T> struct TsParams {
   int N, Nc;
   int nstages, lag, ring_slots, group_items;
   unsigned total_items;
-  int in_aligned16;                 // user input 16-byte aligned (cp.async prefetch of the first pass)
   int twR_entries;                  // total entries of twR (copied to shared memory by the kernel)
   TsStage st[kTsMaxStages];
 };
@@ -93,24 +92,16 @@ template <int A, bool FIRST> PF_HD int ts_tile_idx(int ka, int q, int j) {
 }
 
 // ---- phase 1 (both kinds): thread t -> column j = t & 15 of tile grp = (t >> 4) / A, sub-sequence q = (t >> 4) % A
-// `staged` != nullptr: the item's input was prefetched into shared memory as [tile grp][row n][16 columns]
 template <int A, bool FIRST, int SIGN, typename T>
-PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile,
-                     const cpx<T>* staged = nullptr) {
+PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile) {
   using S = TsShape<A>;
   const int j = t & 15, qq = t >> 4, q = qq % A, grp = qq / A;
   const int bg = b0 + 16 * grp;
   if (grp >= S::G || bg >= m) return;
   cpx<T> v[16];
-  if (staged) {
-    const cpx<T>* c = staged + (grp * S::R + q) * 16 + j;
+  const cpx<T>* c = src + bg + j + (long long)m * q;
 #pragma unroll
-    for (int p = 0; p < 16; ++p) v[p] = c[(A * brev4(p)) * 16];
-  } else {
-    const cpx<T>* c = src + bg + j + (long long)m * q;
-#pragma unroll
-    for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
-  }
+  for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
   reg_fft<16, SIGN>(v);
   cpx<T>* tl = tile + grp * (16 * S::R);
   tl[ts_tile_idx<A, FIRST>(0, q, j)] = v[0];
@@ -168,17 +159,17 @@ PF_HD void ts_phase2_later(int t, int b0, int m, int s, const cpx<T>* tw, const 
 // one FFT work item, phase by phase (the kernel puts a CTA barrier between them; tests/emu steps them lane by lane)
 template <int A, bool FIRST, int SIGN, typename T>
 PF_HD void ts_item_phase(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
-                         const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile, const cpx<T>* staged = nullptr) {
+                         const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
   const int b0 = TsShape<A>::COLS * item;
-  if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile, staged);
+  if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile);
   else if (FIRST) ts_phase2_first<A, SIGN, T>(t, b0, st.m, tw, tile, dst);
   else ts_phase2_later<A, SIGN, T>(t, b0, st.m, st.s, tw, tile, dst);
 }
 template <bool FIRST, int SIGN, typename T>
 PF_HD void ts_item_phase_any(int phase, int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* dst,
-                             const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile, const cpx<T>* staged = nullptr) {
+                             const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
   switch (st.A) {
-#define PF_TS(a) case a: ts_item_phase<a, FIRST, SIGN, T>(phase, t, item, st, src, dst, tw, twR, tile, staged); break;
+#define PF_TS(a) case a: ts_item_phase<a, FIRST, SIGN, T>(phase, t, item, st, src, dst, tw, twR, tile); break;
     PF_TS(1) PF_TS(2) PF_TS(3) PF_TS(4) PF_TS(5) PF_TS(6) PF_TS(8) PF_TS(9) PF_TS(10) PF_TS(12) PF_TS(15) PF_TS(16)
 #undef PF_TS
     default: break;
@@ -256,25 +247,14 @@ template <typename T> PF_HD cpx<T>* ts_dst(const TsParams<T>& P, int which, long
 }
 
 #ifdef __CUDACC__
-PF_D unsigned ts_ld_acquire(const unsigned* p) {
+PF_D unsigned ts_ld_relaxed(const unsigned* p) {                    // L2 read without the L1 invalidation of an acquire
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-PF_D void ts_wait_at_least(const unsigned* p, unsigned need) {
-  while (ts_ld_acquire(p) < need) __nanosleep(100);
+PF_D void ts_red_release(unsigned* p) {                             // completion signal: earlier writes of the CTA first
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-PF_D void ts_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-PF_D void ts_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only (.cg): ring data never enters L1
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-// arrive on `bar` when every cp.async this thread issued so far has landed (counts as one of the expected arrivals)
-PF_D void ts_cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-PF_D void ts_bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); static_assert(kTsThreads == 256, "consumer barrier width"); }
 
 // dependency counters of a live work item: `in_need` tiles of the producing stage, `free_need` tiles of the consuming
 // stage's previous occupant of the ring slot (nullptr pointers: no such dependency)
@@ -293,63 +273,36 @@ template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* S
   return d;
 }
 
-PF_D unsigned ts_ld_relaxed(const unsigned* p) {                    // L2 read without the L1 invalidation of an acquire
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-PF_D void ts_red_release(unsigned* p) {                             // completion signal: earlier writes of the CTA first
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-PF_D void ts_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// input of FFT work item (stage st, item) -> shared memory [tile grp][row n < R][16 columns], 16-byte cp.async.cg chunks
-template <typename T>
-PF_D void ts_prefetch_item(int t, const TsStage& st, int item, const cpx<T>* src, cpx<T>* staging) {
-  constexpr int EPC = 16 / (int)sizeof(cpx<T>);                    // elements per 16-byte chunk: 2 (float), 1 (double)
-  constexpr int CPR = 16 / EPC;                                    // chunks per 16-column row
-  const int A = st.A, R = 16 * A, cols = ts_cols_for(A), m = st.m;
-  const int b0 = cols * item;
-  int gv = (m - b0 + 15) / 16;
-  if (gv > cols / 16) gv = cols / 16;
-  const int rows = gv * R;                                         // <= 256
-  for (int c = t; c < rows * CPR; c += kTsThreads) {
-    const int row = c / CPR, h = c - row * CPR;
-    const int grp = row / R, n = row - grp * R;
-    ts_cp_async16(staging + row * 16 + h * EPC, src + b0 + 16 * grp + (long long)m * n + h * EPC);
-  }
-}
-
-// THE PERSISTENT LOOP.  What the first hardware profile showed (profiles/r02_ts.md): the arithmetic was fine, the CTAs
-// were waiting -- 24 % of all stall samples sat at the barrier behind thread 0's dependency check (two serialised
-// ld.acquire = two L2 round trips, each followed by CCTL.IVALL, an invalidation of the SM's whole L1 that also threw out
-// the twiddle tables of the neighbouring CTAs), more behind the __threadfence of the completion signal.  So:
-//   * work items are dealt out STATICALLY, item k to CTA k mod gridDim.x (the first version took atomic tickets and kept
-//     one or two in hand to hide the atomic's latency -- but every ticket a CTA holds and has not started widens the window
-//     of unfinished items by a whole grid, the pipeline lag no longer covered it, and 45 % of the items had to poll);
-//     the deadlock argument is the same induction (a CTA only ever waits for items with a smaller index);
+// THE PERSISTENT LOOP.  What the hardware profiles of the first versions showed (profiles/r02_large_n.md) and what is
+// left of five variants:
+//   * work items are dealt out STATICALLY, item k to CTA k mod gridDim.x.  (Atomic tickets, one or two kept in hand to hide
+//     the atomic's latency, widen the window of unfinished items by a whole grid per ticket in hand; the pipeline lag no
+//     longer covered it and 45 % of the items polled.)  The deadlock argument is unchanged: a CTA only ever waits for
+//     items with a smaller index, and the grid is co-resident;
 //   * the counters of item i+1 are read (ld.relaxed, both at once) at the top of item i and looked at when item i's first
-//     phase is done -- by then they have long arrived, and with the pipeline lag they are satisfied: item i+1 starts
+//     phase is done -- by then they have long arrived and, with the pipeline lag, they are satisfied: item i+1 starts
 //     without waiting for anything.  Only if the early look failed does its top poll (still relaxed);
-//   * nothing invalidates L1: ring data is only ever read with ld.cg / cp.async.cg (L2), tables are immutable, the
-//     per-radix tables live in shared memory; the completion signal is one red.release issued by a thread of another
-//     warp than the one that handles tickets, so neither waits for the other;
-//   * PREFETCH: when the early look at item i+1 succeeds by the middle of item i, all threads stage its input in a second
-//     shared buffer with cp.async (overlapping phase 2 and the stores of item i).
-template <typename T, int SIGN, int MINB, bool PREFETCH>
+//   * nothing invalidates L1 (ld.acquire / __threadfence compile to CCTL.IVALL, which threw the twiddle tables of all
+//     resident CTAs out once per item): ring data is only ever read with ld.cg (L2), tables are immutable, the per-radix
+//     tables live in shared memory, the completion signal is one red.release issued by a thread of another warp than the
+//     one that handles the counters, so neither waits for the other;
+//   * the thread index is made opaque once per iteration, see below (0 spill bytes instead of 600-780).
+// Measured and dropped (slower): cp.async prefetch of the next item by all threads (0.25-0.30 of the roofline against
+// 0.35-0.40), a warp-specialised producer staging items with 1-D TMA bulk copies (0.14: 128-byte cp.async.bulk cost
+// 10-20 ns each) or with cp.async (0.19), a producer warp for the control path only (0.26-0.35).
+template <typename T, int SIGN, int MINB>
 __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
   cpx<T>* twRs = tile + 16 * 256;                               // per-radix tables of every pass (<= 4 x 256 entries)
-  cpx<T>* staging = twRs + 1024;                                // PREFETCH only
-  __shared__ int s_cur_ready, s_cur_pf, s_next_ready, s_next_pf;
-  __shared__ TsStage ST[kTsMaxStages];
-  const int t = threadIdx.x;
+  __shared__ int s_cur_ready, s_next_ready;
+  __shared__ TsStage ST[kTsMaxStages];                          // (dynamic indexing into the by-value parameter would
+  const int t = threadIdx.x;                                    //  make the compiler copy it to local memory)
   for (int i = t; i < P.twR_entries; i += kTsThreads) twRs[i] = P.twR[i];
   if (t == 0) {
 #pragma unroll
     for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];       // constant indices: plain constant-bank reads
-    s_cur_ready = 0; s_cur_pf = 0;
+    s_cur_ready = 0;
   }
   __syncthreads();
   for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
@@ -373,8 +326,6 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
         if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
       }
     }
-    const int cur_pf = PREFETCH ? s_cur_pf : 0;
-    if (PREFETCH && cur_pf) ts_cp_async_wait_all();
     __syncthreads();
     int stage, item; long long tr;
     const bool live = ts_decode(P, ST, cur, &stage, &tr, &item);
@@ -386,27 +337,19 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     asm volatile("" : "+r"(tt));
     if (fft) {
       const cpx<T>* src = ts_src(P, st.src, tr);
-      const cpx<T>* in_s = cur_pf ? staging : nullptr;
-      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile, in_s);
-      else ts_item_phase_any<false, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile, in_s);
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
+      else ts_item_phase_any<false, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
     }
     if (t == 0) {                                                 // is item i+1 known to be ready?
-      int n_ok = 0, pf = 0;
+      int n_ok = 0;
       int nstage, nitem; long long ntr;
       if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
         const TsDeps nd = ts_deps(P, ST, nstage, ntr);
         n_ok = (!nd.in_ctr || li >= nd.in_need) && (!nd.free_ctr || lf >= nd.free_need);
-        const TsStage& nst = ST[nstage];
-        pf = PREFETCH && n_ok && (nst.kind == TS_FIRST || nst.kind == TS_LATER) && (nst.src != 0 || P.in_aligned16);
       }
-      s_next_ready = n_ok; s_next_pf = pf;
+      s_next_ready = n_ok;
     }
     __syncthreads();
-    if (PREFETCH && s_next_pf) {                                  // staging was consumed in phase 1 (barrier above)
-      int nstage, nitem; long long ntr;
-      ts_decode(P, ST, nxt, &nstage, &ntr, &nitem);
-      ts_prefetch_item<T>(t, ST[nstage], nitem, ts_src(P, ST[nstage].src, ntr), staging);
-    }
     if (live) {
       const cpx<T>* src = ts_src(P, st.src, tr);
       cpx<T>* dst = ts_dst(P, st.dst, tr);
@@ -416,11 +359,10 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       else if (st.kind == TS_PRE) ts_pre_item<T>(t, kTsThreads, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
       else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     }
-    if (t == 0) { s_cur_ready = s_next_ready; s_cur_pf = s_next_pf; }
+    if (t == 0) s_cur_ready = s_next_ready;
     __syncthreads();                                              // every store of the item is issued; tile is free again
     if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage, tr).done);   // another warp than thread 0's
   }
-  if (PREFETCH) ts_cp_async_wait_all();
 }
 #endif  // __CUDACC__
 
