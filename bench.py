@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 N = 1024
 BYTES_PER_FFT = 2 * N * 2 * 4          # 8 KiB read + 8 KiB written (algorithmic bytes / transform)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the forward kernel, per transform:
-# (2.147577 + 2.097573) GB over a 262144-transform launch (profiles/r01_ncu_full_c1024.txt; the kernel is unchanged since).
+# (2.147577 + 2.097573) GB over a 262144-transform launch (profiles/r01_ncu_full_c1024.txt; re-captured in round 2 with the
+# same result, profiles/r02_ncu_c1024.txt: 2.147574 + 2.098634 GB).
 # STATIC: bench.py scales the committed capture to the units of its own launch and labels it so ("traffic_kind");
 # it is evidence that traffic ~= algorithmic bytes, not a measurement of this run (ncu cannot run inside a timed bench).
 NCU_DRAM_BYTES_PER_FFT = (2.147577e9 + 2.097573e9) / 262144
@@ -363,7 +364,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
                          "traffic": NCU_DRAM_BYTES_PER_FFT * batch if "ldg" in setup.kernel else None,
                          "traffic_kind": "static",
-                         "traffic_source": "profiles/r01_ncu_full_c1024.txt (ncu --set full of this unchanged kernel: per-transform DRAM bytes x this launch's transforms; not measured in this run)",
+                         "traffic_source": "profiles/r02_ncu_c1024.txt = profiles/r01_ncu_full_c1024.txt (ncu --set full of this unchanged kernel, 2.1476 + 2.0986 GB per 262144 transforms in both rounds: per-transform DRAM bytes x this launch's transforms; not measured in this run)",
                          "kernel": setup.kernel + " (forward launch, %d transforms)" % batch,
                          "algorithmic_bytes_per_launch": batch * BYTES_PER_FFT, "ms_per_launch": fwd_ms,
                          "peak_source": peak_src,
