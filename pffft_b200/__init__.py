@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpffft_b200.so")
+# PFFFT_B200_LIB: A/B builds of the same library for tuning runs (e.g. the scalar-arithmetic build); never a CPU path
+LIB_PATH = os.environ.get("PFFFT_B200_LIB") or os.path.join(_HERE, "libpffft_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

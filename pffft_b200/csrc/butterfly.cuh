@@ -62,12 +62,12 @@ template <int SIGN, typename T> PF_HD void dft2(cpx<T>* a) {
 }
 template <int SIGN, typename T> PF_HD void dft3(cpx<T>* a) {
   const T hs3 = T(SIGN) * T(0.86602540378443864676372317075294);
-  cpx<T> t1 = a[1] + a[2];
-  cpx<T> m = mk<T>(a[0].x - T(0.5) * t1.x, a[0].y - T(0.5) * t1.y);
-  cpx<T> d = scale(a[1] - a[2], hs3);          // SIGN*sin(2pi/3)*(a1-a2)
+  const cpx<T> t1 = a[1] + a[2];
+  const cpx<T> m = cfma(t1, T(-0.5), a[0]);      // a0 - (a1+a2)/2
+  const cpx<T> id = mul_pi(a[1] - a[2]);         // i*(a1-a2)
   a[0] = a[0] + t1;
-  a[1] = mk<T>(m.x - d.y, m.y + d.x);          // m + i*d
-  a[2] = mk<T>(m.x + d.y, m.y - d.x);          // m - i*d
+  a[1] = cfma(id, hs3, m);                       // m + i*SIGN*sin(2pi/3)*(a1-a2)
+  a[2] = cfma(id, -hs3, m);
 }
 template <int SIGN, typename T> PF_HD void dft4(cpx<T>* a) {
   cpx<T> t0 = a[0] + a[2], t1 = a[0] - a[2], t2 = a[1] + a[3];
@@ -77,16 +77,15 @@ template <int SIGN, typename T> PF_HD void dft4(cpx<T>* a) {
 template <int SIGN, typename T> PF_HD void dft5(cpx<T>* a) {
   const T tr11 = T(0.30901699437494742410229341718282), ti11 = T(SIGN) * T(0.95105651629515357211643933337938);
   const T tr12 = T(-0.80901699437494742410229341718282), ti12 = T(SIGN) * T(0.58778525229247312916870595463907);
-  cpx<T> t1 = a[1] + a[4], t2 = a[2] + a[3], t3 = a[1] - a[4], t4 = a[2] - a[3];
-  cpx<T> m1 = mk<T>(a[0].x + tr11 * t1.x + tr12 * t2.x, a[0].y + tr11 * t1.y + tr12 * t2.y);
-  cpx<T> m2 = mk<T>(a[0].x + tr12 * t1.x + tr11 * t2.x, a[0].y + tr12 * t1.y + tr11 * t2.y);
-  cpx<T> n1 = mk<T>(ti11 * t3.x + ti12 * t4.x, ti11 * t3.y + ti12 * t4.y);
-  cpx<T> n2 = mk<T>(ti12 * t3.x - ti11 * t4.x, ti12 * t3.y - ti11 * t4.y);
+  const cpx<T> t1 = a[1] + a[4], t2 = a[2] + a[3];
+  const cpx<T> i3 = mul_pi(a[1] - a[4]), i4 = mul_pi(a[2] - a[3]);      // i*(a1-a4), i*(a2-a3)
+  const cpx<T> m1 = cfma(t2, tr12, cfma(t1, tr11, a[0]));
+  const cpx<T> m2 = cfma(t2, tr11, cfma(t1, tr12, a[0]));
+  const cpx<T> n1 = cfma(i4, ti12, scale(i3, ti11));                     // i*(ti11 t3 + ti12 t4)
+  const cpx<T> n2 = cfma(i4, -ti11, scale(i3, ti12));                    // i*(ti12 t3 - ti11 t4)
   a[0] = a[0] + t1 + t2;
-  a[1] = mk<T>(m1.x - n1.y, m1.y + n1.x);      // m1 + i n1
-  a[4] = mk<T>(m1.x + n1.y, m1.y - n1.x);
-  a[2] = mk<T>(m2.x - n2.y, m2.y + n2.x);
-  a[3] = mk<T>(m2.x + n2.y, m2.y - n2.x);
+  a[1] = m1 + n1; a[4] = m1 - n1;
+  a[2] = m2 + n2; a[3] = m2 - n2;
 }
 template <int R, int SIGN, typename T> PF_HD void dftR(cpx<T>* a) {
   if (R == 2) dft2<SIGN>(a);
@@ -112,28 +111,23 @@ template <int J, int G, int SIGN, typename T> PF_HD void dit_bfly(cpx<T>& A, cpx
   } else if constexpr (4 * J == G) {
     const cpx<T> t = mul_si<SIGN>(b);
     A = a + t; B = a - t;
-  } else if constexpr (8 * J == G) {
+  } else if constexpr (8 * J == G) {             // w = (1 + SIGN i)/sqrt2:  w b = h (b + SIGN i b)
     const T h = T(0.70710678118654752440084436210485);
-    const T sx = (SIGN < 0) ? (b.x + b.y) : (b.x - b.y);
-    const T sy = (SIGN < 0) ? (b.y - b.x) : (b.y + b.x);
-    A.x = fma(h, sx, a.x); B.x = fma(-h, sx, a.x);
-    A.y = fma(h, sy, a.y); B.y = fma(-h, sy, a.y);
-  } else if constexpr (8 * J == 3 * G) {
+    const cpx<T> s = b + mul_si<SIGN>(b);
+    A = cfma(s, h, a); B = cfma(s, -h, a);
+  } else if constexpr (8 * J == 3 * G) {         // w = (-1 + SIGN i)/sqrt2: w b = -h (b - SIGN i b)
     const T h = T(0.70710678118654752440084436210485);
-    const T sx = (SIGN < 0) ? (b.x - b.y) : (b.x + b.y);
-    const T sy = (SIGN < 0) ? (b.y + b.x) : (b.y - b.x);
-    A.x = fma(-h, sx, a.x); B.x = fma(h, sx, a.x);
-    A.y = fma(-h, sy, a.y); B.y = fma(h, sy, a.y);
+    const cpx<T> s = b - mul_si<SIGN>(b);
+    A = cfma(s, -h, a); B = cfma(s, h, a);
   } else {
     constexpr ct::cs w = ct::cossin2pi(J, G);
     const T c = T(w.c), s = T(SIGN) * T(w.s);
-    // both outputs as their own 2-fma chains (8 fma per butterfly).  The 6-fma variant B = 2a - A
-    // re-injects A's rounding error into B, which costs ~4 dB of spur-free range on pure tones
-    // (tests/test_pffft.c wants >= 140 dB); the kernel is HBM-bound, the 2 extra fma are free.
-    A.x = fma(-b.y, s, fma(b.x, c, a.x));      // Re(a + w b)
-    A.y = fma(b.y, c, fma(b.x, s, a.y));       // Im(a + w b)
-    B.x = fma(b.y, s, fma(-b.x, c, a.x));      // Re(a - w b)
-    B.y = fma(-b.y, c, fma(-b.x, s, a.y));     // Im(a - w b)
+    // w b = c b + s (i b); both outputs as their own 2-fma chains (8 fma per butterfly, 4 FFMA2 packed).  The 6-fma
+    // variant B = 2a - A re-injects A's rounding error into B, which costs ~4 dB of spur-free range on pure tones
+    // (tests/test_pffft.c wants >= 140 dB).
+    const cpx<T> ib = mul_pi(b);
+    A = cfma(ib, s, cfma(b, c, a));
+    B = cfma(ib, -s, cfma(b, -c, a));
   }
 }
 
@@ -170,7 +164,7 @@ template <int J, int N, int SIGN, typename T> PF_HD cpx<T> mul_root(cpx<T> x) { 
   else {
     constexpr ct::cs w = ct::cossin2pi(J, N);
     const T c = T(w.c), s = T(SIGN) * T(w.s);
-    return mk<T>(fma(x.x, c, -(x.y * s)), fma(x.x, s, x.y * c));
+    return cfma(mul_pi(x), s, scale(x, c));      // c x + s (i x)
   }
 }
 template <int R, int SIGN, typename T> PF_HD void dft_small(cpx<T>* a);   // any supported size, defined below

@@ -121,8 +121,8 @@ PF_HD void real_post_pair(T* base, const cpx<T>* z, int k, int N, int Nc, const 
   const cpx<T> a = z[k], b = conj(z[Nc - k]);
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, ldtab(twr + k));
-  spec_put<Z, true, SWZ>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
-  spec_put<Z, true, SWZ>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+  spec_put<Z, true, SWZ>(base, k, N, scale(s + mul_mi(u), T(0.5)));
+  spec_put<Z, true, SWZ>(base, Nc - k, N, emul(s - mul_mi(u), mk<T>(T(0.5), T(-0.5))));
 }
 
 
@@ -166,8 +166,8 @@ PF_HD void real_post_regs(T* base, int k, int Nc, int N, cpx<T> a, cpx<T> zm, co
   const cpx<T> b = conj(zm);
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, ldtab(twr + k));
-  spec_put<Z, true, SWZ>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
-  spec_put<Z, true, SWZ>(base, Nc - k, N, mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x)));
+  spec_put<Z, true, SWZ>(base, k, N, scale(s + mul_mi(u), T(0.5)));
+  spec_put<Z, true, SWZ>(base, Nc - k, N, emul(s - mul_mi(u), mk<T>(T(0.5), T(-0.5))));
 }
 template <int C, int SM, typename T, bool SWZ = false>
 PF_HD void k2_store_pairs(int t, const cpx<T> (&u)[16], T* base, int N, const cpx<T>* twr) {

@@ -34,8 +34,8 @@ PF_HD void fastconv_pair(cpx<T>* z, int k, int Nc, const cpx<T>* twr, const cpx<
   const cpx<T> w = ldtab(twr + k);
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, w);
-  const cpx<T> xk = mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x));
-  const cpx<T> xm = mk<T>(T(0.5) * (s.x - u.y), T(-0.5) * (s.y + u.x));
+  const cpx<T> xk = scale2(s + mul_mi(u), T(0.5));
+  const cpx<T> xm = emul(s - mul_mi(u), mk<T>(T(0.5), T(-0.5)));
   const cpx<T> yk = scale2(cmul(xk, ldtab(Hc + k)), scale);
   const cpx<T> ym = scale2(cmul(xm, ldtab(Hc + Nc - k)), scale);
   const cpx<T> S = yk + conj(ym), D = yk - conj(ym);

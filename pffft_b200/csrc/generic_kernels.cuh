@@ -124,7 +124,7 @@ PF_HD void store_core(T* base, const cpx<T>* z, int k, int N, int Nc, const cpx<
   const cpx<T> b = conj(core_get<CG>(z + (Nc - k)));
   const cpx<T> s = a + b, d = a - b;
   const cpx<T> u = cmul(d, twr[k]);
-  spec_put<Z, true>(base, k, N, mk<T>(T(0.5) * (s.x + u.y), T(0.5) * (s.y - u.x)));
+  spec_put<Z, true>(base, k, N, scale(s + mul_mi(u), T(0.5)));
 }
 
 // ------------------------------------------------------------------ one Stockham butterfly

@@ -2,6 +2,7 @@
 // per-plan device resources (radix tables, L2-resident ring buffers, dependency counters) and the launcher.
 // Own translation unit so the C-ABI units stay small; float and double.
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -24,33 +25,57 @@ struct TsPlanHost {
   size_t counter_bytes = 0;
   int grid = 0, lag = 0, ring_slots = 1;
   size_t smem = 0;
+  bool pre = false;                    // input prefetch variant available (float)
+  int grid_v[2] = {0, 0};              // co-resident grid and shared memory of the variant without / with prefetch
+  size_t smem_v[2] = {0, 0};
   std::mutex mu;                       // rings and counters serve one launch at a time
   cudaEvent_t done = nullptr;
   char name[48] = {0};
 };
 
-// resident CTAs per SM the register budget is sized for: float 3 (80 registers, no spills), double 2 (128 registers);
-// PFFFT_B200_TS_MINB=2 selects the two-CTA float build (measured slower: 0.28 against 0.35 at 65536)
+// Kernel variants.  float: 3 resident CTAs per SM (80 registers) with the input prefetch (PRE, needs the second 32 KB
+// buffer); PFFFT_B200_TS_PRE=0 switches the prefetch off, PFFFT_B200_TS_MINB=2|4 selects the two-CTA (128 registers) or
+// four-CTA (64 registers, no prefetch: shared memory) builds -- tuning knobs, read once.  double: 2 CTAs, no prefetch.
 template <typename T> struct TsKernels {
   using Kern = void (*)(const TsParams<T>);
-  static bool two() { static const bool v = sizeof(T) == 8 || (getenv("PFFFT_B200_TS_MINB") && atoi(getenv("PFFFT_B200_TS_MINB")) == 2); return v; }
-  static size_t smem() { return ((size_t)16 * 256 + 1024) * sizeof(cpx<T>); }     // exchange tile + per-radix tables
-  template <int SIGN> static Kern kern() {
-    if constexpr (sizeof(T) == 8) return (Kern)k_ts_pipeline<T, SIGN, 2>;
-    else return two() ? (Kern)k_ts_pipeline<T, SIGN, 2> : (Kern)k_ts_pipeline<T, SIGN, 3>;
+  static int minb() {
+    static const int v = [] { if (sizeof(T) == 8) return 2; const char* e = getenv("PFFFT_B200_TS_MINB"); const int m = e ? atoi(e) : 3; return (m == 2 || m == 4) ? m : 3; }();
+    return v;
   }
-  static Kern fwd() { return kern<-1>(); }
-  static Kern bwd() { return kern<+1>(); }
+  static bool pre() {
+    static const bool v = [] { if (sizeof(T) == 8 || minb() == 4) return false; const char* e = getenv("PFFFT_B200_TS_PRE"); return !(e && atoi(e) == 0); }();
+    return v;
+  }
+  // exchange tile [+ staging buffer] + per-radix tables (entries rounded up to 128 bytes)
+  static size_t smem(int twR_entries, bool with_pre) {
+    return ((size_t)16 * 256 * (with_pre ? 2 : 1) + (size_t)((twR_entries + 15) / 16) * 16) * sizeof(cpx<T>);
+  }
+  template <int SIGN> static Kern kern(bool with_pre) {
+    if constexpr (sizeof(T) == 8) return (Kern)k_ts_pipeline<T, SIGN, 2, false>;
+    else {
+      if (minb() == 4) return (Kern)k_ts_pipeline<T, SIGN, 4, false>;
+      if (minb() == 2) return with_pre ? (Kern)k_ts_pipeline<T, SIGN, 2, true> : (Kern)k_ts_pipeline<T, SIGN, 2, false>;
+      return with_pre ? (Kern)k_ts_pipeline<T, SIGN, 3, true> : (Kern)k_ts_pipeline<T, SIGN, 3, false>;
+    }
+  }
 };
 
 template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
-  static PerDeviceInt attr_f, attr_b;
-  { const int rc = ensure_dyn_smem(attr_f, h->device, TsKernels<T>::fwd(), TsKernels<T>::smem()); if (rc) return rc; }
-  { const int rc = ensure_dyn_smem(attr_b, h->device, TsKernels<T>::bwd(), TsKernels<T>::smem()); if (rc) return rc; }
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::fwd(), kTsThreads, h->smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  if (n < 1) n = 1;
-  h->grid = n * h->sm_count;
+  static PerDeviceInt attr[4];
+  int k = 0;
+  for (int with_pre = 0; with_pre <= (TsKernels<T>::pre() ? 1 : 0); ++with_pre) {
+    const size_t smem = TsKernels<T>::smem(h->twR_entries, with_pre != 0);
+    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<-1>(with_pre != 0), smem); if (rc) return rc; }
+    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<+1>(with_pre != 0), smem); if (rc) return rc; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::template kern<-1>(with_pre != 0), kTsThreads, smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n < 1) n = 1;
+    h->grid_v[with_pre] = n * h->sm_count;
+    h->smem_v[with_pre] = smem;
+  }
+  h->pre = TsKernels<T>::pre();
+  h->grid = h->grid_v[h->pre ? 1 : 0];
+  h->smem = h->smem_v[h->pre ? 1 : 0];
   return 0;
 }
 
@@ -80,9 +105,8 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   int amax = 0; long long group = 0;
   for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
   (void)amax;
-  h->smem = dbl ? TsKernels<double>::smem() : TsKernels<float>::smem();                             // exchange tile + prefetch buffer, each one work item = 16 columns x 256 points (or G tiles of 16 x 16A)
-  bool ok = (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
-  ok = ok && (dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h));
+  bool ok = dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h);
+  ok = ok && (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
   // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
   // so its input is complete (no spinning) and still in L2; rings hold 2*lag+1 transforms so a slot's previous occupant
   // has long been consumed when it is overwritten.  Rings are capped at ~40 MB (they must stay L2 resident to pay).
@@ -127,7 +151,13 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
 
   std::lock_guard<std::mutex> lock(h->mu);
   PF_CUDA_OK(cudaStreamWaitEvent(st, h->done, 0));
-  auto kern = sign < 0 ? TsKernels<T>::fwd() : TsKernels<T>::bwd();
+  // the prefetch copies 16-byte pieces: the user's input must be aligned to them (rings and tables are)
+  const bool with_pre = h->pre && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  auto kern = sign < 0 ? TsKernels<T>::template kern<-1>(with_pre) : TsKernels<T>::template kern<+1>(with_pre);
+  // (the pipeline lag and the rings were sized for h->grid; the variant without prefetch may hold fewer or more CTAs,
+  //  never more than its own co-resident maximum)
+  const int grid_cap = h->grid_v[with_pre ? 1 : 0] < h->grid ? h->grid_v[with_pre ? 1 : 0] : h->grid;
+  const size_t smem = h->smem_v[with_pre ? 1 : 0];
   // tickets are 32-bit: very long batches go in several launches
   const long long max_groups = (long long)((0xFFFFFFFFull - 4ull * (unsigned long long)h->grid) / (unsigned long long)group);
   const long long max_batch = max_groups - (long long)(ns - 1) * h->lag;
@@ -137,8 +167,8 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
     const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
-    const long long g = total < h->grid ? total : h->grid;
-    kern<<<(int)g, kTsThreads, h->smem, st>>>(P);
+    const long long g = total < grid_cap ? total : grid_cap;
+    kern<<<(int)g, kTsThreads, smem, st>>>(P);
     count_launch();
     PF_CUDA_OK(cudaGetLastError());
   }

@@ -91,17 +91,40 @@ template <int A, bool FIRST> PF_HD int ts_tile_idx(int ka, int q, int j) {
   return FIRST ? ((q + A * j) * 16 + (ka ^ j)) : ((ka * A + q) * 16 + j);
 }
 
+// staging buffer of a work item (input prefetch, see the kernel): entry of (tile grp, sub-sequence q, radix-16 digit i,
+// column j) -- rows of 16 columns = 128 bytes, the 16 rows of one (grp, q) contiguous
+template <int A> PF_HD int ts_stage_idx(int grp, int q, int i, int j) { return ((grp * A + q) * 16 + i) * 16 + j; }
+// the r-th (r < 8) 16-byte piece thread t copies for the item: the 16 lanes that share (grp, q) copy exactly the 16 rows x
+// 128 bytes the same 16 lanes consume in phase 1, so a __syncwarp is all that separates the copy from its use.
+// Returns false when the thread has nothing to copy; *g = source element (transform-relative), *d = staging entry.
+template <int A> PF_HD bool ts_stage_piece(int t, int r, int b0, int m, long long* g, int* d) {
+  using S = TsShape<A>;
+  const int j = t & 15, qq = t >> 4, q = qq % A, grp = qq / A;
+  const int bg = b0 + 16 * grp;
+  if (grp >= S::G || bg >= m) return false;
+  const int i = (j >> 3) + 2 * r, c2 = 2 * (j & 7);
+  *g = (long long)bg + c2 + (long long)m * (q + A * i);
+  *d = ts_stage_idx<A>(grp, q, i, c2);
+  return true;
+}
+
 // ---- phase 1 (both kinds): thread t -> column j = t & 15 of tile grp = (t >> 4) / A, sub-sequence q = (t >> 4) % A
-template <int A, bool FIRST, int SIGN, typename T>
-PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base */, int m, const cpx<T>* twR, cpx<T>* tile) {
+// STAGED: the item's input already sits in the staging buffer `src` (ts_stage_idx layout) instead of global memory
+template <int A, bool FIRST, int SIGN, typename T, bool STAGED = false>
+PF_HD void ts_phase1(int t, int b0, const cpx<T>* src /* transform base, or the staging buffer */, int m, const cpx<T>* twR, cpx<T>* tile) {
   using S = TsShape<A>;
   const int j = t & 15, qq = t >> 4, q = qq % A, grp = qq / A;
   const int bg = b0 + 16 * grp;
   if (grp >= S::G || bg >= m) return;
   cpx<T> v[16];
-  const cpx<T>* c = src + bg + j + (long long)m * q;
+  if (STAGED) {
 #pragma unroll
-  for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
+    for (int p = 0; p < 16; ++p) v[p] = src[ts_stage_idx<A>(grp, q, brev4(p), j)];
+  } else {
+    const cpx<T>* c = src + bg + j + (long long)m * q;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) v[p] = ld_l2(c + (long long)m * (A * brev4(p)));
+  }
   reg_fft<16, SIGN>(v);
   cpx<T>* tl = tile + grp * (16 * S::R);
   tl[ts_tile_idx<A, FIRST>(0, q, j)] = v[0];
@@ -162,6 +185,7 @@ PF_HD void ts_item_phase(int phase, int t, int item, const TsStage& st, const cp
                          const cpx<T>* tw, const cpx<T>* twR, cpx<T>* tile) {
   const int b0 = TsShape<A>::COLS * item;
   if (phase == 0) ts_phase1<A, FIRST, SIGN, T>(t, b0, src, st.m, twR + st.tw_off, tile);
+  else if (phase == 2) ts_phase1<A, FIRST, SIGN, T, true>(t, b0, src, st.m, twR + st.tw_off, tile);   // src = staging buffer
   else if (FIRST) ts_phase2_first<A, SIGN, T>(t, b0, st.m, tw, tile, dst);
   else ts_phase2_later<A, SIGN, T>(t, b0, st.m, st.s, tw, tile, dst);
 }
@@ -256,6 +280,29 @@ PF_D void ts_red_release(unsigned* p) {                             // completio
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
+// ---- input prefetch (float): the NEXT work item's 32 KB of input are copied global/L2 -> shared by 16-byte cp.async.cg
+// (LDGSTS, L2 only like ld.cg, no registers held) while the current item runs its phase 2
+PF_D void ts_cp_async_cg16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+PF_D void ts_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int A, typename T> PF_D void ts_prefetch_item(int t, int item, int m, const cpx<T>* src, cpx<T>* stage) {
+  const int b0 = TsShape<A>::COLS * item;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    long long g; int d;
+    if (ts_stage_piece<A>(t, r, b0, m, &g, &d)) ts_cp_async_cg16(stage + d, src + g);
+  }
+}
+template <typename T> PF_D void ts_prefetch_any(int t, int item, const TsStage& st, const cpx<T>* src, cpx<T>* stage) {
+  switch (st.A) {
+#define PF_TS(a) case a: ts_prefetch_item<a, T>(t, item, st.m, src, stage); break;
+    PF_TS(1) PF_TS(2) PF_TS(3) PF_TS(4) PF_TS(5) PF_TS(6) PF_TS(8) PF_TS(9) PF_TS(10) PF_TS(12) PF_TS(15) PF_TS(16)
+#undef PF_TS
+    default: break;
+  }
+}
+
 // dependency counters of a live work item: `in_need` tiles of the producing stage, `free_need` tiles of the consuming
 // stage's previous occupant of the ring slot (nullptr pointers: no such dependency)
 struct TsDeps { const unsigned* in_ctr; unsigned in_need; const unsigned* free_ctr; unsigned free_need; unsigned* done; };
@@ -290,11 +337,16 @@ template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* S
 // Measured and dropped (slower): cp.async prefetch of the next item by all threads (0.25-0.30 of the roofline against
 // 0.35-0.40), a warp-specialised producer staging items with 1-D TMA bulk copies (0.14: 128-byte cp.async.bulk cost
 // 10-20 ns each) or with cp.async (0.19), a producer warp for the control path only (0.26-0.35).
-template <typename T, int SIGN, int MINB>
+//   * PRE (round 2b, float): the input of item i+1 is prefetched into a second shared buffer while item i runs its phase 2
+//     (ts_prefetch_item), issued once thread 0's early look has shown that item i+1's dependencies are met.  An item's
+//     timeline was [wait for 16 loads] [radix 16] [barrier] [twiddle loads, radix A, stores] with three CTAs per SM to
+//     overlap it: 30 % issue utilisation.  With the prefetch phase 1 starts from shared memory.
+template <typename T, int SIGN, int MINB, bool PRE>
 __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_constant__ TsParams<T> P) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   cpx<T>* tile = reinterpret_cast<cpx<T>*>(pf_smem_raw);
-  cpx<T>* twRs = tile + 16 * 256;                               // per-radix tables of every pass (<= 4 x 256 entries)
+  cpx<T>* stage = tile + 16 * 256;                              // PRE only
+  cpx<T>* twRs = PRE ? stage + 16 * 256 : stage;                // per-radix tables of every pass (<= 4 x 256 entries)
   __shared__ int s_cur_ready, s_next_ready;
   __shared__ TsStage ST[kTsMaxStages];                          // (dynamic indexing into the by-value parameter would
   const int t = threadIdx.x;                                    //  make the compiler copy it to local memory)
@@ -305,14 +357,15 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     s_cur_ready = 0;
   }
   __syncthreads();
+  bool staged = false;                                            // CTA-uniform: the current item's input is in `stage`
   for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
     const unsigned nxt = cur + gridDim.x;                         // (total_items + gridDim.x < 2^32: checked by the host)
     // ---- thread 0: readiness of item i (poll only if the early look failed), early look at item i+1
     unsigned li = 0, lf = 0;
     if (t == 0) {
-      int stage, item; long long tr;
-      if (!s_cur_ready && ts_decode(P, ST, cur, &stage, &tr, &item)) {
-        const TsDeps d = ts_deps(P, ST, stage, tr);
+      int stage_i, item; long long tr;
+      if (!s_cur_ready && ts_decode(P, ST, cur, &stage_i, &tr, &item)) {
+        const TsDeps d = ts_deps(P, ST, stage_i, tr);
         for (;;) {
           const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
           if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
@@ -327,9 +380,9 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       }
     }
     __syncthreads();
-    int stage, item; long long tr;
-    const bool live = ts_decode(P, ST, cur, &stage, &tr, &item);
-    const TsStage& st = ST[stage];
+    int stage_i, item; long long tr;
+    const bool live = ts_decode(P, ST, cur, &stage_i, &tr, &item);
+    const TsStage& st = ST[stage_i];
     const bool fft = live && (st.kind == TS_FIRST || st.kind == TS_LATER);
     // the thread index is made opaque per iteration: otherwise the compiler hoists the per-thread index arithmetic of ALL
     // 24 radix bodies (t % A, t / A, tile offsets ...) out of the persistent loop and spills ~150 values to local memory
@@ -337,8 +390,10 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     asm volatile("" : "+r"(tt));
     if (fft) {
       const cpx<T>* src = ts_src(P, st.src, tr);
-      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
-      else ts_item_phase_any<false, SIGN, T>(0, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
+      int ph = 0;
+      if constexpr (PRE) if (staged) { ts_cp_async_wait_all(); __syncwarp(); src = stage; ph = 2; }   // copied by the same 16 lanes that read it
+      if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(ph, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
+      else ts_item_phase_any<false, SIGN, T>(ph, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
     }
     if (t == 0) {                                                 // is item i+1 known to be ready?
       int n_ok = 0;
@@ -349,7 +404,17 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       }
       s_next_ready = n_ok;
     }
-    __syncthreads();
+    __syncthreads();                                              // tile complete; nobody reads `stage` any more
+    bool pre_next = false;
+    if constexpr (PRE) if (s_next_ready) {                        // item i+1 is live and its input complete: start fetching it
+      int nstage, nitem; long long ntr;
+      ts_decode(P, ST, nxt, &nstage, &ntr, &nitem);
+      const TsStage& nst = ST[nstage];
+      if (nst.kind == TS_FIRST || nst.kind == TS_LATER) {
+        ts_prefetch_any<T>(tt, nitem, nst, ts_src(P, nst.src, ntr), stage);
+        pre_next = true;
+      }
+    }
     if (live) {
       const cpx<T>* src = ts_src(P, st.src, tr);
       cpx<T>* dst = ts_dst(P, st.dst, tr);
@@ -360,8 +425,9 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       else ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     }
     if (t == 0) s_cur_ready = s_next_ready;
+    staged = pre_next;
     __syncthreads();                                              // every store of the item is issued; tile is free again
-    if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage, tr).done);   // another warp than thread 0's
+    if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage_i, tr).done);   // another warp than thread 0's
   }
 }
 #endif  // __CUDACC__
