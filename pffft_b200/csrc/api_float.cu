@@ -1,8 +1,9 @@
 // api_float.cu -- pffft_* : the single-precision C-ABI (ref include/pffft/pffft.h:124-250) and the
 // selection of the size-tuned kernels.
+#define PF_NO_PACKED_F32 1   // scalar fp32 arithmetic in this translation unit: the 16x16xC CTA kernels measure 1-10 % faster with scalar arithmetic (C3 backward 0.75 against 0.68) (profiles/r02b_packed.md)
 #include "../../include/pffft/pffft_b200.h"
 #include "api_impl.cuh"
-#include "fast_kernels.cuh"
+#include "fast.h"
 #include "cta_hooks.cuh"
 #include "radix.h"
 
@@ -15,110 +16,29 @@ enum { V_LDG_4x4 = 0, V_LDG_8x2 = 1, V_BULK_8 = 2, V_BULK_12 = 3, V_BULK_4x3 = 4
 static const char* kVariantName[V_COUNT] = {"c1024_warp_ldg_4w", "c1024_warp_ldg_8w", "c1024_warp_bulk_8w",
                                             "c1024_warp_bulk_12w", "c1024_warp_bulk_4w"};
 
-template <int SIGN, int WARPS, int MINB, bool ZIN, bool ZOUT>
-static int launch_ldg(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
-  auto kern = k_c1024_ldg<SIGN, WARPS, MINB, ZIN, ZOUT>;
-  const size_t smem = (1024 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
-  static PerDeviceInt attr;
-  { const int rc = ensure_dyn_smem(attr, s->device, kern, smem); if (rc) return rc; }
-  long long ctas = (batch + WARPS - 1) / WARPS;
-  const long long cap = (long long)s->sm_count * MINB;
-  if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
-  count_launch();
-  PF_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-template <int SIGN, int WARPS, int MINB, bool ZOUT>
-static int launch_bulk(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
-  auto kern = k_c1024_bulk<SIGN, WARPS, MINB, ZOUT>;
-  const size_t smem = (1024 + (size_t)WARPS * 2 * kW1024Tile) * sizeof(cf) + (size_t)WARPS * 2 * sizeof(uint64_t);
-  static PerDeviceInt attr;
-  { const int rc = ensure_dyn_smem(attr, s->device, kern, smem); if (rc) return rc; }
-  long long ctas = (batch + WARPS - 1) / WARPS;
-  const long long cap = (long long)s->sm_count * MINB;
-  if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
-  count_launch();
-  PF_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
+// ---- the warp-per-transform kernels live in fast_pk.cu (packed f32x2 arithmetic) and fast_sc.cu (scalar arithmetic);
+// `fast_packed` (fast.h) says which build serves a combination
+static FastCtx fast_ctx(const Setup<float>* s) { return FastCtx{s->device, s->sm_count, s->tw_fast, s->twr}; }
 template <int SIGN, bool ZIN, bool ZOUT>
 static int run_c1024(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
-  switch (s->fast_variant) {
-    case V_LDG_8x2: return launch_ldg<SIGN, 8, 2, ZIN, ZOUT>(s, in, out, batch, st);
-    case V_BULK_8:  if (!ZIN) return launch_bulk<SIGN, 8, 1, ZOUT>(s, in, out, batch, st); break;
-    case V_BULK_12: if (!ZIN) return launch_bulk<SIGN, 12, 1, ZOUT>(s, in, out, batch, st); break;
-    case V_BULK_4x3: if (!ZIN) return launch_bulk<SIGN, 4, 3, ZOUT>(s, in, out, batch, st); break;
-    default: break;
-  }
-  return launch_ldg<SIGN, 4, 4, ZIN, ZOUT>(s, in, out, batch, st);
-}
-
-// ---- small complex sizes on the warp machinery (N = 32..256)
-template <int R2, int SIGN, bool ZIN, bool ZOUT>
-static int launch_wsmall(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st) {
-  constexpr int WARPS = 4, MINB = 4;
-  auto kern = k_warp_small<R2, SIGN, WARPS, MINB, ZIN, ZOUT>;
-  const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
-  const long long nchunks = (batch + (32 / R2) - 1) / (32 / R2);
-  long long ctas = (nchunks + WARPS - 1) / WARPS;
-  const long long cap = (long long)s->sm_count * MINB;
-  if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast);
-  count_launch();
-  PF_CUDA_OK(cudaGetLastError());
-  return 0;
+  return fast_packed(FK_C1024, 0, ZIN, ZOUT, false) ? fast_c1024_pk(fast_ctx(s), s->fast_variant, SIGN, ZIN, ZOUT, in, out, batch, st)
+                                                    : fast_c1024_sc(fast_ctx(s), s->fast_variant, SIGN, ZIN, ZOUT, in, out, batch, st);
 }
 template <int SIGN, bool ZIN, bool ZOUT>
 static int run_wsmall(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st) {
-  switch (R2) {
-    case 1: return launch_wsmall<1, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 2: return launch_wsmall<2, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    case 4: return launch_wsmall<4, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-    default: return launch_wsmall<8, SIGN, ZIN, ZOUT>(s, in, out, batch, st);
-  }
+  return fast_packed(FK_WSMALL, R2, ZIN, ZOUT, false) ? fast_wsmall_pk(fast_ctx(s), R2, SIGN, ZIN, ZOUT, in, out, batch, st)
+                                                      : fast_wsmall_sc(fast_ctx(s), R2, SIGN, ZIN, ZOUT, in, out, batch, st);
+}
+template <int SIGN, bool ZIN, bool ZOUT, bool REAL>
+static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st, int grp = 1) {
+  return fast_packed(FK_WMIXED, R2, ZIN, ZOUT, REAL) ? fast_wmixed_pk(fast_ctx(s), R2, SIGN, ZIN, ZOUT, REAL, in, out, batch, st, grp)
+                                                     : fast_wmixed_sc(fast_ctx(s), R2, SIGN, ZIN, ZOUT, REAL, in, out, batch, st, grp);
 }
 static int wsmall_R2_for(int N, int transform) {
   if (transform != XF_COMPLEX) return 0;
   return N == 32 ? 1 : N == 64 ? 2 : N == 128 ? 4 : N == 256 ? 8 : 0;
 }
 
-// ---- non-power-of-two complex sizes on the warp machinery (N = 32*R2, R2 in {3,5,6,9,10,12,15,18,20,24,25,27,30})
-template <int R2, int SIGN, bool ZIN, bool ZOUT, bool REAL>
-static int launch_wmixed(Setup<float>* s, const float* in, float* out, long long batch, cudaStream_t st, int grp = 1) {
-  constexpr int WARPS = 4, MINB = 4;
-  auto kern = k_warp_mixed<R2, SIGN, WARPS, MINB, ZIN, ZOUT, REAL>;
-  const size_t smem = (32 * R2 + (size_t)WARPS * kW1024Tile) * sizeof(cf);
-  const long long nchunks = (batch + (32 / R2) - 1) / (32 / R2);
-  long long ctas = (nchunks + WARPS - 1) / WARPS;
-  const long long cap = (long long)s->sm_count * MINB;
-  if (ctas > cap) ctas = cap;
-  kern<<<(int)ctas, WARPS * 32, smem, st>>>(reinterpret_cast<const cf*>(in), reinterpret_cast<cf*>(out), batch, s->tw_fast, s->twr, grp);
-  count_launch();
-  PF_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-template <int SIGN, bool ZIN, bool ZOUT, bool REAL>
-static int run_wmixed(Setup<float>* s, int R2, const float* in, float* out, long long batch, cudaStream_t st, int grp = 1) {
-  switch (R2) {
-#define PF_WM(r) case r: return launch_wmixed<r, SIGN, ZIN, ZOUT, REAL>(s, in, out, batch, st, grp);
-    PF_WM(3) PF_WM(5) PF_WM(6) PF_WM(9) PF_WM(10) PF_WM(12) PF_WM(15) PF_WM(18) PF_WM(20) PF_WM(24) PF_WM(25) PF_WM(27) PF_WM(30)
-#undef PF_WM
-    default: break;
-  }
-  if constexpr (REAL) {                                     // power-of-two packed lengths only exist as real plans here
-    switch (R2) {
-      case 1: return launch_wmixed<1, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
-      case 2: return launch_wmixed<2, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
-      case 4: return launch_wmixed<4, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
-      case 8: return launch_wmixed<8, SIGN, ZIN, ZOUT, true>(s, in, out, batch, st);
-      default: break;
-    }
-  }
-  return -1;
-}
 // complex N = 32*R2 (non-pow2 R2) and real N = 64*R2 (any supported R2)
 static int wmixed_R2_for(int N, int transform) {
   const int Nc = transform == XF_REAL ? N / 2 : N;

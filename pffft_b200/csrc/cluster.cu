@@ -1,5 +1,6 @@
 // cluster.cu -- instantiations and launchers of the thread-block-cluster kernels (cluster_kernels.cuh): float complex
 // cores 8192..65536 = (CL*Q) x 4096 in one HBM round trip.  Own translation unit so the C-ABI units stay small.
+#define PF_NO_PACKED_F32 1   // scalar fp32 arithmetic in this translation unit: measured 4 % faster with scalar arithmetic (16384: 0.49 against 0.47) (profiles/r02b_packed.md)
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include "internal_api.h"

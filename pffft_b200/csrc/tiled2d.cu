@@ -1,5 +1,6 @@
 // tiled2d.cu -- instantiations and launchers of the tiled two-dimensional large-N plan (tiled2d_kernels.cuh), float.
 // Own translation unit so the C-ABI units stay small.  Default plan for 32768 and 65536 (PFFFT_B200_TILED2D=0|1 overrides).
+#define PF_NO_PACKED_F32 1   // scalar fp32 arithmetic in this translation unit: measured 4 % faster with scalar arithmetic at 16384 (cluster-fused form), equal elsewhere (profiles/r02b_packed.md)
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include "internal_api.h"

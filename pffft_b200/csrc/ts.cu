@@ -33,17 +33,19 @@ struct TsPlanHost {
   char name[48] = {0};
 };
 
-// Kernel variants.  float: 3 resident CTAs per SM (80 registers) with the input prefetch (PRE, needs the second 32 KB
-// buffer); PFFFT_B200_TS_PRE=0 switches the prefetch off, PFFFT_B200_TS_MINB=2|4 selects the two-CTA (128 registers) or
-// four-CTA (64 registers, no prefetch: shared memory) builds -- tuning knobs, read once.  double: 2 CTAs, no prefetch.
+// Kernel variants.  float: FOUR resident CTAs per SM (64 registers since the packed-arithmetic build; measured 0.42 / 0.39 /
+// 0.38 of the HBM roofline at 16384 / 32768 / 65536 against 0.38 / 0.37 / 0.35 with three and 0.29 / 0.29 / 0.28 with two:
+// the pipeline is bound by latency, i.e. by resident warps).  PFFFT_B200_TS_MINB=2|3 selects the other builds,
+// PFFFT_B200_TS_PRE=1 (with MINB 2|3) the cp.async input prefetch -- measured SLOWER (16384: 0.34 against 0.38: the
+// second 32 KB buffer leaves 12 KB of L1 for the twiddle tables).  Tuning knobs, read once.  double: 2 CTAs, no prefetch.
 template <typename T> struct TsKernels {
   using Kern = void (*)(const TsParams<T>);
   static int minb() {
-    static const int v = [] { if (sizeof(T) == 8) return 2; const char* e = getenv("PFFFT_B200_TS_MINB"); const int m = e ? atoi(e) : 3; return (m == 2 || m == 4) ? m : 3; }();
+    static const int v = [] { if (sizeof(T) == 8) return 2; const char* e = getenv("PFFFT_B200_TS_MINB"); const int m = e ? atoi(e) : 4; return (m == 2 || m == 3) ? m : 4; }();
     return v;
   }
   static bool pre() {
-    static const bool v = [] { if (sizeof(T) == 8 || minb() == 4) return false; const char* e = getenv("PFFFT_B200_TS_PRE"); return !(e && atoi(e) == 0); }();
+    static const bool v = [] { if (sizeof(T) == 8 || minb() == 4) return false; const char* e = getenv("PFFFT_B200_TS_PRE"); return e && atoi(e) == 1; }();
     return v;
   }
   // exchange tile [+ staging buffer] + per-radix tables (entries rounded up to 128 bytes)
@@ -65,8 +67,9 @@ template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
   int k = 0;
   for (int with_pre = 0; with_pre <= (TsKernels<T>::pre() ? 1 : 0); ++with_pre) {
     const size_t smem = TsKernels<T>::smem(h->twR_entries, with_pre != 0);
-    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<-1>(with_pre != 0), smem); if (rc) return rc; }
-    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<+1>(with_pre != 0), smem); if (rc) return rc; }
+    const size_t smem_max = TsKernels<T>::smem(4 * 256, with_pre != 0);     // the attribute is set once per device: largest plan
+    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<-1>(with_pre != 0), smem_max); if (rc) return rc; }
+    { const int rc = ensure_dyn_smem(attr[k++], h->device, TsKernels<T>::template kern<+1>(with_pre != 0), smem_max); if (rc) return rc; }
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TsKernels<T>::template kern<-1>(with_pre != 0), kTsThreads, smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
     if (n < 1) n = 1;

@@ -261,13 +261,17 @@ PF_HD bool ts_decode(const TsParams<T>& P, const TsStage* ST, unsigned ticket, i
   *stage = i; *tr = t; *item = r;
   return t >= 0 && t < P.batch;
 }
+// ring slot of transform tr: 32-bit arithmetic (tr < 2^31, see ts_run) -- a 64-bit modulo is a ~100-instruction subroutine,
+// and the first versions of the kernel ran five of them per thread and work item (40 % of all executed instructions, with
+// thread 0's copies on the critical path of every barrier)
+template <typename T> PF_HD unsigned ts_slot(const TsParams<T>& P, long long tr) { return (unsigned)tr % (unsigned)P.ring_slots; }
 template <typename T> PF_HD const cpx<T>* ts_src(const TsParams<T>& P, int which, long long tr) {
   if (which == 0) return reinterpret_cast<const cpx<T>*>(P.in) + tr * P.Nc;
-  return P.ring[which - 2] + (long long)(tr % P.ring_slots) * P.Nc;
+  return P.ring[which - 2] + (long long)ts_slot(P, tr) * P.Nc;
 }
 template <typename T> PF_HD cpx<T>* ts_dst(const TsParams<T>& P, int which, long long tr) {
   if (which == 1) return reinterpret_cast<cpx<T>*>(P.out) + tr * P.Nc;
-  return P.ring[which - 2] + (long long)(tr % P.ring_slots) * P.Nc;
+  return P.ring[which - 2] + (long long)ts_slot(P, tr) * P.Nc;
 }
 
 #ifdef __CUDACC__
@@ -307,8 +311,8 @@ template <typename T> PF_D void ts_prefetch_any(int t, int item, const TsStage& 
 // stage's previous occupant of the ring slot (nullptr pointers: no such dependency)
 struct TsDeps { const unsigned* in_ctr; unsigned in_need; const unsigned* free_ctr; unsigned free_need; unsigned* done; };
 template <typename T> PF_D TsDeps ts_deps(const TsParams<T>& P, const TsStage* ST, int stage, long long tr) {
-  const int slot = (int)(tr % P.ring_slots);
-  const unsigned gen = (unsigned)(tr / P.ring_slots);
+  const unsigned slot = ts_slot(P, tr);
+  const unsigned gen = (unsigned)tr / (unsigned)P.ring_slots;
   unsigned* base = P.counters + kTsCounterBase + slot;
   TsDeps d;
   d.done = base + stage * P.ring_slots;
@@ -361,7 +365,8 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
   for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
     const unsigned nxt = cur + gridDim.x;                         // (total_items + gridDim.x < 2^32: checked by the host)
     // ---- thread 0: readiness of item i (poll only if the early look failed), early look at item i+1
-    unsigned li = 0, lf = 0;
+    unsigned li = 0, lf = 0, n_in_need = 0, n_free_need = 0;      // thread 0: counters of item i+1 and what they must reach
+    bool n_live = false, n_has_in = false, n_has_free = false;
     if (t == 0) {
       int stage_i, item; long long tr;
       if (!s_cur_ready && ts_decode(P, ST, cur, &stage_i, &tr, &item)) {
@@ -375,6 +380,8 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       int nstage, nitem; long long ntr;
       if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
         const TsDeps nd = ts_deps(P, ST, nstage, ntr);
+        n_live = true; n_has_in = nd.in_ctr != nullptr; n_has_free = nd.free_ctr != nullptr;
+        n_in_need = nd.in_need; n_free_need = nd.free_need;
         if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);             // in flight during phase 1
         if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
       }
@@ -395,15 +402,8 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(ph, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
       else ts_item_phase_any<false, SIGN, T>(ph, tt, item, st, src, (cpx<T>*)nullptr, P.tw, twRs, tile);
     }
-    if (t == 0) {                                                 // is item i+1 known to be ready?
-      int n_ok = 0;
-      int nstage, nitem; long long ntr;
-      if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
-        const TsDeps nd = ts_deps(P, ST, nstage, ntr);
-        n_ok = (!nd.in_ctr || li >= nd.in_need) && (!nd.free_ctr || lf >= nd.free_need);
-      }
-      s_next_ready = n_ok;
-    }
+    if (t == 0)                                                   // is item i+1 known to be ready?
+      s_next_ready = n_live && (!n_has_in || li >= n_in_need) && (!n_has_free || lf >= n_free_need);
     __syncthreads();                                              // tile complete; nobody reads `stage` any more
     bool pre_next = false;
     if constexpr (PRE) if (s_next_ready) {                        // item i+1 is live and its input complete: start fetching it
