@@ -17,8 +17,11 @@ constexpr bool fast_packed(int kind, int R2, bool zin, bool zout, bool real) {
   return PF_FAST_FORCE != 0;
 #endif
   if (kind == FK_C1024) return zin || zout;                 // ordered: 0.98 scalar / 0.97 packed; z-domain: 0.90 / 0.96
-  if (kind == FK_WSMALL) return zin || zout;
-  return real || zin || zout || R2 >= 9;                    // 96c: 0.95 / 0.85, 480c: 0.84 / 0.90, 800c: 0.82 / 0.94, 960c: 0.72 / 0.91
+  if (kind == FK_WSMALL) return R2 == 4;                    // 128c: 0.87 / 0.97; 32c, 64c, 256c: equal (256c z-domain: 0.96 / 0.94)
+  if (real) return true;                                    // real 64 ... 1920: +3 ... +17 % packed (backward 512: equal)
+  if (zin || zout) return R2 >= 10;
+  return R2 >= 10;                                          // 96c: 0.95 / 0.84, 288c: 0.92 / 0.85, 320c: 0.86 / 0.88, 480c: 0.84 / 0.91,
+                                                            // 768c: 0.85 / 0.96, 864c: 0.81 / 0.94, 960c: 0.72 / 0.91
 }
 
 // c1024: `variant` = V_* of api_float.cu; every call returns -1 when the combination is not instantiated

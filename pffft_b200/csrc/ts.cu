@@ -25,6 +25,8 @@ struct TsPlanHost {
   size_t counter_bytes = 0;
   int grid = 0, lag = 0, ring_slots = 1;
   size_t smem = 0;
+  bool wmode = false;                  // warp-sized work items (tsw_kernels.cuh)
+  int twL_entries = 0;                 // wmode: entries of the last pass's exponent table (appended to d_twR)
   bool pre = false;                    // input prefetch variant available (float)
   int grid_v[2] = {0, 0};              // co-resident grid and shared memory of the variant without / with prefetch
   size_t smem_v[2] = {0, 0};
@@ -82,9 +84,48 @@ template <typename T> static int ts_prepare_kernels(TsPlanHost* h) {
   return 0;
 }
 
+// warp-sized work items: float only; 4 CTAs of 4 warps per SM (128 registers per thread), PFFFT_B200_TSW_MINB=2..6 overrides
+struct TswKernels {
+  using Kern = void (*)(const TsParams<float>, int);
+  static int minb() {
+    static const int v = [] { const char* e = getenv("PFFFT_B200_TSW_MINB"); const int m = e ? atoi(e) : 4; return (m >= 2 && m <= 6) ? m : 4; }();
+    return v;
+  }
+  static size_t smem(int twR_entries, int twL_entries) {
+    return ((size_t)((twR_entries + 15) & ~15) + (size_t)((twL_entries + 15) & ~15) + (size_t)kTswWarps * kTswTileMax) * sizeof(cpx<float>);
+  }
+  template <int SIGN> static Kern kern() {
+    switch (minb()) {
+      case 2: return (Kern)k_tsw_pipeline<float, SIGN, 2>;
+      case 3: return (Kern)k_tsw_pipeline<float, SIGN, 3>;
+      case 5: return (Kern)k_tsw_pipeline<float, SIGN, 5>;
+      case 6: return (Kern)k_tsw_pipeline<float, SIGN, 6>;
+      default: return (Kern)k_tsw_pipeline<float, SIGN, 4>;
+    }
+  }
+};
+static int tsw_prepare_kernels(TsPlanHost* h) {
+  static PerDeviceInt attr_f, attr_b;
+  const size_t smem = TswKernels::smem(h->twR_entries, h->twL_entries);
+  const size_t smem_max = TswKernels::smem(4 * 256, 256);
+  { const int rc = ensure_dyn_smem(attr_f, h->device, TswKernels::kern<-1>(), smem_max); if (rc) return rc; }
+  { const int rc = ensure_dyn_smem(attr_b, h->device, TswKernels::kern<+1>(), smem_max); if (rc) return rc; }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, TswKernels::kern<-1>(), kTswWarps * 32, smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (n < 1) n = 1;
+  h->grid = n * h->sm_count;
+  h->smem = smem;
+  return 0;
+}
+
 template <typename T> static bool ts_fill_radix_tables(TsPlanHost* h) {
-  const std::vector<T> host = ts_radix_tables<T>(h->P, h->A, h->tw_off);
+  std::vector<T> host = ts_radix_tables<T>(h->P, h->A, h->tw_off);
   h->twR_entries = (int)(host.size() / 2);
+  if (h->wmode) {                                                 // + exponent table of the last pass
+    const std::vector<T> last = tsw_last_table<T>(ts_radix(h->A[h->P - 1]));
+    h->twL_entries = (int)(last.size() / 2);
+    host.insert(host.end(), last.begin(), last.end());
+  }
   if (cudaMalloc(&h->d_twR, host.size() * sizeof(T)) != cudaSuccess) return false;
   return cudaMemcpy(h->d_twR, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
 }
@@ -108,18 +149,23 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   int amax = 0; long long group = 0;
   for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
   (void)amax;
+  // warp-sized work items for power-of-two float plans (PFFFT_B200_TSW=0: CTA-sized items everywhere)
+  { const char* e = getenv("PFFFT_B200_TSW"); h->wmode = !dbl && tsw_plan_ok(P, A) && !(e && atoi(e) == 0); }
+  if (h->wmode) { group = 0; for (int i = 0; i < P; ++i) group += ts_tiles(Nc, A[i], true); }
   bool ok = dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h);
-  ok = ok && (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h)) == 0;
+  ok = ok && (h->wmode ? tsw_prepare_kernels(h) : (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h))) == 0;
+  const long long flight = h->wmode ? (long long)h->grid * kTswWarps : (long long)h->grid;   // work items in flight
   // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
   // so its input is complete (no spinning) and still in L2; rings hold 2*lag+1 transforms so a slot's previous occupant
   // has long been consumed when it is overwritten.  Rings are capped at ~40 MB (they must stay L2 resident to pay).
   h->nrings = P;                                                  // P-1 between the passes + one for a pre-/post-stage
   const size_t tb = (size_t)Nc * csz;
-  long long lag = (3LL * h->grid / 2 + group - 1) / group;
+  long long lag = (3LL * flight / 2 + group - 1) / group;
   if (lag < 1) lag = 1;
-  const size_t budget = (size_t)40 << 20;
-  if ((size_t)h->nrings * (size_t)(2 * lag + 1) * tb > budget) {
-    const long long fit = ((long long)(budget / ((size_t)h->nrings * tb)) - 1) / 2;
+  const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 40) << 20;
+  const size_t hot = (size_t)(P > 2 ? P - 1 : 1);                 // rings a complex ordered call touches (the extra one serves pre/post stages)
+  if (hot * (size_t)(2 * lag + 1) * tb > budget) {
+    const long long fit = ((long long)(budget / (hot * tb)) - 1) / 2;
     if (fit >= 1) lag = fit;
     else lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
   }
@@ -131,7 +177,7 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   ok = ok && cudaMalloc((void**)&h->d_counters, h->counter_bytes) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { set_error("tiled Stockham plan: device resources", cudaGetLastError()); ts_destroy(h); return nullptr; }
-  int n = snprintf(h->name, sizeof(h->name), "ts");
+  int n = snprintf(h->name, sizeof(h->name), h->wmode ? "tsw" : "ts");
   for (int i = 0; i < P; ++i) n += snprintf(h->name + n, sizeof(h->name) - n, "%c%d", i ? 'x' : '_', ts_radix(A[i]));
   return h;
 }
@@ -148,7 +194,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   P.counters = h->d_counters;
   P.N = h->N; P.Nc = h->Nc; P.lag = h->lag; P.ring_slots = h->ring_slots;
   P.twR_entries = h->twR_entries;
-  ts_build_stages<T>(P, h->Nc, h->P, h->A, h->tw_off, lm, sm);
+  ts_build_stages<T>(P, h->Nc, h->P, h->A, h->tw_off, lm, sm, h->wmode);
   const int ns = P.nstages;
   const long long group = P.group_items;
 
@@ -162,7 +208,7 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   const int grid_cap = h->grid_v[with_pre ? 1 : 0] < h->grid ? h->grid_v[with_pre ? 1 : 0] : h->grid;
   const size_t smem = h->smem_v[with_pre ? 1 : 0];
   // tickets are 32-bit: very long batches go in several launches
-  const long long max_groups = (long long)((0xFFFFFFFFull - 4ull * (unsigned long long)h->grid) / (unsigned long long)group);
+  const long long max_groups = (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)group);
   const long long max_batch = max_groups - (long long)(ns - 1) * h->lag;
   for (long long b0 = 0; b0 < batch; b0 += max_batch) {
     const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
@@ -170,6 +216,17 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
     const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
     P.total_items = (unsigned)total;
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
+    if constexpr (sizeof(T) == 4) {
+      if (h->wmode) {
+        const long long ctas = (total + kTswWarps - 1) / kTswWarps;
+        const long long g = ctas < h->grid ? ctas : h->grid;
+        auto wk = sign < 0 ? TswKernels::kern<-1>() : TswKernels::kern<+1>();
+        wk<<<(int)g, kTswWarps * 32, h->smem, st>>>(P, h->twL_entries);
+        count_launch();
+        PF_CUDA_OK(cudaGetLastError());
+        continue;
+      }
+    }
     const long long g = total < grid_cap ? total : grid_cap;
     kern<<<(int)g, kTsThreads, smem, st>>>(P);
     count_launch();

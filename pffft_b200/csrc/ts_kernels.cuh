@@ -364,19 +364,27 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
   bool staged = false;                                            // CTA-uniform: the current item's input is in `stage`
   for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
     const unsigned nxt = cur + gridDim.x;                         // (total_items + gridDim.x < 2^32: checked by the host)
-    // ---- thread 0: readiness of item i (poll only if the early look failed), early look at item i+1
-    unsigned li = 0, lf = 0, n_in_need = 0, n_free_need = 0;      // thread 0: counters of item i+1 and what they must reach
-    bool n_live = false, n_has_in = false, n_has_free = false;
-    if (t == 0) {
-      int stage_i, item; long long tr;
-      if (!s_cur_ready && ts_decode(P, ST, cur, &stage_i, &tr, &item)) {
-        const TsDeps d = ts_deps(P, ST, stage_i, tr);
-        for (;;) {
-          const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
-          if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
-          __nanosleep(100);
+    // ---- readiness of item i: known from the early look of the previous iteration (s_cur_ready, CTA-uniform after the
+    // closing barrier) in all but a few per cent of the items -- only then does thread 0 poll, behind a barrier of its own
+    if (!s_cur_ready) {
+      if (t == 0) {
+        int stage_p, item_p; long long tr_p;
+        if (ts_decode(P, ST, cur, &stage_p, &tr_p, &item_p)) {
+          const TsDeps d = ts_deps(P, ST, stage_p, tr_p);
+          for (;;) {
+            const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
+            if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
+            __nanosleep(100);
+          }
         }
       }
+      __syncthreads();
+    }
+    // ---- thread 0: early look at item i+1 -- its counters are read now (off everybody else's critical path) and looked at
+    // after phase 1
+    unsigned li = 0, lf = 0, n_in_need = 0, n_free_need = 0;
+    bool n_live = false, n_has_in = false, n_has_free = false;
+    if (t == 0) {
       int nstage, nitem; long long ntr;
       if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
         const TsDeps nd = ts_deps(P, ST, nstage, ntr);
@@ -386,7 +394,6 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
         if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
       }
     }
-    __syncthreads();
     int stage_i, item; long long tr;
     const bool live = ts_decode(P, ST, cur, &stage_i, &tr, &item);
     const TsStage& st = ST[stage_i];

@@ -6,14 +6,15 @@
 #include <string.h>
 #include <vector>
 #include "plan.h"
-#include "ts_kernels.cuh"
+#include "tsw_kernels.cuh"
 
 namespace pf {
 
 // work items per pass
-inline int ts_tiles(int Nc, int A) {
+// (wmode: the warp-sized work items of tsw_kernels.cuh)
+inline int ts_tiles(int Nc, int A, bool wmode = false) {
   if (A >= kTsSmallFlag) return (Nc / (A - kTsSmallFlag) + 255) / 256;
-  const int m = Nc / (16 * A), cols = ts_cols_for(A);
+  const int m = Nc / (16 * A), cols = wmode ? tsw_cols_for(A) : ts_cols_for(A);
   return (m + cols - 1) / cols;
 }
 inline int ts_radix(int A) { return A >= kTsSmallFlag ? A - kTsSmallFlag : 16 * A; }
@@ -101,8 +102,25 @@ template <typename T> inline std::vector<T> ts_radix_tables(int P, const int* A,
   return host;
 }
 
+// warp-sized work items (tsw_kernels.cuh): every pass a power-of-two radix 32 ... 256, no closing small pass
+inline bool tsw_plan_ok(int P, const int* A) {
+  for (int i = 0; i < P; ++i) if (!tsw_radix_ok(A[i])) return false;
+  return P >= 2;
+}
+// exponent-indexed table of the last pass: exp(-2 pi i e / R), e < R
+template <typename T> inline std::vector<T> tsw_last_table(int R) {
+  std::vector<T> host(2 * (size_t)R);
+  for (int e = 0; e < R; ++e) {
+    long double c, s;
+    pfplan::unit_root(e, R, &c, &s);
+    host[2 * e] = (T)c; host[2 * e + 1] = (T)s;
+  }
+  return host;
+}
+
 // stage list of one call: [pre-rotation / z gather] + P passes + [post-rotation / z scatter]; sets nstages, group_items
-template <typename T> inline void ts_build_stages(TsParams<T>& Q, int Nc, int P, const int* A, const int* tw_off, int lm, int sm) {
+template <typename T> inline void ts_build_stages(TsParams<T>& Q, int Nc, int P, const int* A, const int* tw_off, int lm, int sm,
+                                                  bool wmode = false) {
   const bool pre = lm == L_C_Z || lm == L_R_ORD || lm == L_R_Z;
   const bool post = sm == S_C_Z || sm == S_R_ORD || sm == S_R_Z;
   const int chunks = (Nc + kTsChunk - 1) / kTsChunk;
@@ -113,7 +131,7 @@ template <typename T> inline void ts_build_stages(TsParams<T>& Q, int Nc, int P,
     const int R = ts_radix(A[i]);
     const bool last = (i == P - 1), small = A[i] >= kTsSmallFlag;
     const int dst = (last && !post) ? 1 : 2 + ring_next++;
-    Q.st[ns++] = TsStage{small ? TS_SMALL : (i == 0 ? TS_FIRST : TS_LATER), small ? A[i] - kTsSmallFlag : A[i], 0, ts_tiles(Nc, A[i]),
+    Q.st[ns++] = TsStage{small ? TS_SMALL : (i == 0 ? TS_FIRST : TS_LATER), small ? A[i] - kTsSmallFlag : A[i], 0, ts_tiles(Nc, A[i], wmode),
                          cur_src, dst, Nc / R, prod, tw_off[i]};
     cur_src = dst; prod *= R;
   }

@@ -161,8 +161,53 @@ static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
   }
   return 0;
 }
+// ---- warp-sized work items (tsw_kernels.cuh): same protocol, 32 lanes per item, two phases around a __syncwarp
+template <typename T, int SIGN>
+static int tsw_emulate(TsParams<T>& P, const cpx<T>* twL, int window, unsigned seed) {
+  std::vector<unsigned> counters(kTsCounterBase + (size_t)kTsMaxStages * P.ring_slots, 0u);
+  std::vector<cpx<T>> tile(kTswTileMax);
+  std::vector<unsigned> flight;
+  unsigned next = 0;
+  uint32_t rs = seed * 2654435761u + 12345u;
+  auto ready = [&](unsigned ticket) {
+    int stage, item; long long tr;
+    if (!ts_decode(P, P.st, ticket, &stage, &tr, &item)) return true;
+    const int slot = (int)(tr % P.ring_slots); const unsigned gen = (unsigned)(tr / P.ring_slots);
+    const unsigned* base = counters.data() + kTsCounterBase + slot;
+    if (stage > 0 && base[(stage - 1) * P.ring_slots] < (gen + 1u) * (unsigned)P.st[stage - 1].tiles) return false;
+    if (stage + 1 < P.nstages && gen > 0 && base[(stage + 1) * P.ring_slots] < gen * (unsigned)P.st[stage + 1].tiles) return false;
+    return true;
+  };
+  while (next < P.total_items || !flight.empty()) {
+    while ((int)flight.size() < window && next < P.total_items) flight.push_back(next++);
+    std::vector<int> cand;
+    for (int i = 0; i < (int)flight.size(); ++i) if (ready(flight[i])) cand.push_back(i);
+    if (cand.empty()) return -10;                                  // deadlock
+    rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+    const int pick = cand[rs % cand.size()];
+    const unsigned cur = flight[pick];
+    flight.erase(flight.begin() + pick);
+    int stage, item; long long tr;
+    if (!ts_decode(P, P.st, cur, &stage, &tr, &item)) continue;
+    const TsStage& st = P.st[stage];
+    const cpx<T>* src = ts_src(P, st.src, tr);
+    cpx<T>* dst = ts_dst(P, st.dst, tr);
+    if (st.kind == TS_FIRST || st.kind == TS_LATER) {
+      for (auto& e : tile) { e.x = (T)NAN; e.y = (T)NAN; }
+      for (int phase = 0; phase < 2; ++phase)
+        for (int lane = 0; lane < 32; ++lane) tsw_item_phase_any<SIGN, T>(phase, lane, item, st, P.Nc, src, dst, P.tw, P.twR, twL, tile.data());
+    } else if (st.kind == TS_PRE) {
+      for (int lane = 0; lane < 32; ++lane) ts_pre_item<T>(lane, 32, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+    } else if (st.kind == TS_POST) {
+      for (int lane = 0; lane < 32; ++lane) ts_post_item<T>(lane, 32, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
+    } else return -11;
+    counters[kTsCounterBase + stage * P.ring_slots + (int)(tr % P.ring_slots)] += 1;
+  }
+  return 0;
+}
 template <typename T>
-static int emu_ts_t(int N, int transform, int dir, int ordered, const T* in, T* out, long long batch, int lag, int window, unsigned seed) {
+static int emu_ts_t(int N, int transform, int dir, int ordered, const T* in, T* out, long long batch, int lag, int window, unsigned seed,
+                    bool wmode = false) {
   const int Nc = transform == 0 ? N / 2 : N;
   int Pn = 0, A[4], tw_off[4];
   if (!ts_factorize(Nc, &Pn, A)) return -1;
@@ -183,8 +228,14 @@ static int emu_ts_t(int N, int transform, int dir, int ordered, const T* in, T* 
   if (transform == 1) { lm = (fwd || ordered) ? L_C_ORD : L_C_Z; sm = (fwd && !ordered) ? S_C_Z : S_C_ORD; }
   else if (fwd) { lm = L_R_TIME; sm = ordered ? S_R_ORD : S_R_Z; }
   else { lm = ordered ? L_R_ORD : L_R_Z; sm = S_R_TIME; }
-  ts_build_stages<T>(P, Nc, Pn, A, tw_off, lm, sm);
+  if (wmode && !tsw_plan_ok(Pn, A)) return -2;
+  ts_build_stages<T>(P, Nc, Pn, A, tw_off, lm, sm, wmode);
   P.total_items = (unsigned)((batch + (long long)(P.nstages - 1) * lag) * P.group_items);
+  if (wmode) {
+    const std::vector<T> last = tsw_last_table<T>(ts_radix(A[Pn - 1]));
+    const cpx<T>* twL = reinterpret_cast<const cpx<T>*>(last.data());
+    return fwd ? tsw_emulate<T, -1>(P, twL, window, seed) : tsw_emulate<T, +1>(P, twL, window, seed);
+  }
   return fwd ? ts_emulate<T, -1>(P, window, seed) : ts_emulate<T, +1>(P, window, seed);
 }
 // radices come from PFFFT_B200_TS_RADICES when set (ts_factorize reads it), else the default factorisation
@@ -192,6 +243,10 @@ extern "C" int emu_ts(int prec, int N, int transform, int dir, int ordered, cons
                       int lag, int window, unsigned seed) {
   if (prec == 0) return emu_ts_t<float>(N, transform, dir, ordered, (const float*)in, (float*)out, batch, lag, window, seed);
   return emu_ts_t<double>(N, transform, dir, ordered, (const double*)in, (double*)out, batch, lag, window, seed);
+}
+extern "C" int emu_tsw(int N, int transform, int dir, int ordered, const void* in, void* out, long long batch,
+                       int lag, int window, unsigned seed) {
+  return emu_ts_t<float>(N, transform, dir, ordered, (const float*)in, (float*)out, batch, lag, window, seed, true);
 }
 extern "C" int emu_ts_factorize(int Nc, int* P, int* A) { return ts_factorize(Nc, P, A) ? 1 : 0; }
 

@@ -147,3 +147,62 @@ def _run_inplace(emu, Nc, x, batch, lag, window):
     rc = emu.emu_ts(0, Nc, 1, 0, 1, x.ctypes.data, x.ctypes.data, batch, lag, window, 9)
     assert rc == 0
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# warp-sized work items (pffft_b200/csrc/tsw_kernels.cuh): one warp = one tile, two phases around a __syncwarp
+# ---------------------------------------------------------------------------------------------------------------
+def _run_w(emu, N, tr, d, ordered, x, batch, lag, window, seed=1):
+    emu.emu_tsw.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_uint]
+    x = np.ascontiguousarray(x, np.float32)
+    o = np.full_like(x, np.nan)
+    rc = emu.emu_tsw(N, tr, d, ordered, x.ctypes.data, o.ctypes.data, batch, lag, window, seed)
+    assert rc == 0, "emulated warp pipeline failed: rc=%d (-10 = deadlock, -2 = no warp plan)" % rc
+    return o
+
+
+# every radix (32, 64, 128, 256) as first, middle and last pass
+TSW_CASES = [("256,256", 65536), ("128,128", 16384), ("256,128", 32768), ("128,256", 32768), ("64,32", 2048), ("32,64", 2048),
+             ("64,64,32", 131072), ("32,64,128", 262144), ("256,32,64", 524288), ("32,32,32,32", 1 << 20)]
+
+
+@pytest.mark.parametrize("radices,Nc", TSW_CASES)
+def test_warp_items_every_radix_and_position(emu, R, monkeypatch, radices, Nc):
+    monkeypatch.setenv("PFFFT_B200_TS_RADICES", radices)
+    rng = np.random.default_rng(Nc + 7)
+    batch = 2 if Nc <= 65536 else 1
+    x = uniform(rng, batch * 2 * Nc).reshape(batch, 2 * Nc)
+    got = _run_w(emu, Nc, 1, 0, 1, x, batch, 1, 24)
+    for b in range(batch):
+        assert R.relmax(got[b], _numpy_forward(x[b], Nc, 1)) <= 1e-5, (radices, b)
+    back = _run_w(emu, Nc, 1, 1, 1, got, batch, 1, 24)
+    assert R.relmax(back, x * Nc) <= 1e-5
+
+
+@pytest.mark.parametrize("tr", [1, 0])
+def test_warp_items_all_layouts_match_the_reference(emu, ref, R, monkeypatch, tr):
+    monkeypatch.delenv("PFFFT_B200_TS_RADICES", raising=False)
+    core = 16384
+    N = core if tr == 1 else 2 * core
+    rng = np.random.default_rng(core + tr + 100)
+    x = uniform(rng, 2 * core)
+    fo = _run_w(emu, N, tr, 0, 1, x, 1, 2, 64)
+    fz = _run_w(emu, N, tr, 0, 0, x, 1, 2, 64)
+    assert R.relmax(fo, ref.transform(N, tr, x, 0, True)) <= 1e-5
+    assert R.relmax(fz, ref.transform(N, tr, x, 0, False)) <= 1e-5
+    assert np.array_equal(ref.zreorder(N, tr, fz, 0), fo)
+    bo = _run_w(emu, N, tr, 1, 1, fo, 1, 2, 64)
+    bz = _run_w(emu, N, tr, 1, 0, fz, 1, 2, 64)
+    assert R.relmax(bo, x * N) <= 1e-5 and R.relmax(bz, x * N) <= 1e-5
+
+
+@pytest.mark.parametrize("lag,window", [(0, 1), (0, 90), (1, 7), (2, 300), (5, 64)])
+def test_warp_items_protocol_under_random_interleavings(emu, R, monkeypatch, lag, window):
+    monkeypatch.setenv("PFFFT_B200_TS_RADICES", "32,32,32")
+    Nc, batch = 32768, 9
+    rng = np.random.default_rng(lag * 100 + window + 3)
+    x = uniform(rng, batch * 2 * Nc).reshape(batch, 2 * Nc)
+    want = np.stack([_numpy_forward(x[b], Nc, 1) for b in range(batch)])
+    for seed in (1, 2):
+        got = _run_w(emu, Nc, 1, 0, 1, x, batch, lag, window, seed)
+        assert max(R.relmax(got[b], want[b]) for b in range(batch)) <= 1e-5
