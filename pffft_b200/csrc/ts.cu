@@ -154,21 +154,16 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   if (h->wmode) { group = 0; for (int i = 0; i < P; ++i) group += ts_tiles(Nc, A[i], true); }
   bool ok = dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h);
   ok = ok && (h->wmode ? tsw_prepare_kernels(h) : (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h))) == 0;
-  const long long flight = h->wmode ? (long long)h->grid * kTswWarps : (long long)h->grid;   // work items in flight
-  // pipeline depth: pass i+1 of a transform is handed out `lag` groups after pass i -- about 1.5 grid-fulls of tiles later,
-  // so its input is complete (no spinning) and still in L2; rings hold 2*lag+1 transforms so a slot's previous occupant
-  // has long been consumed when it is overwritten.  Rings are capped at ~40 MB (they must stay L2 resident to pay).
+  // ring depth: the producers of a stage may run 2*lag+1 transforms ahead of its consumers (stage-specialised workers,
+  // ts_worker); the rings must stay L2 resident to pay, so they are sized by bytes: ~24 MB over the rings a complex ordered
+  // call touches, at most 49 slots (PFFFT_B200_TS_RING_MB / PFFFT_B200_TS_LAG override).
   h->nrings = P;                                                  // P-1 between the passes + one for a pre-/post-stage
   const size_t tb = (size_t)Nc * csz;
-  long long lag = (3LL * flight / 2 + group - 1) / group;
-  if (lag < 1) lag = 1;
-  const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 40) << 20;
-  const size_t hot = (size_t)(P > 2 ? P - 1 : 1);                 // rings a complex ordered call touches (the extra one serves pre/post stages)
-  if (hot * (size_t)(2 * lag + 1) * tb > budget) {
-    const long long fit = ((long long)(budget / (hot * tb)) - 1) / 2;
-    if (fit >= 1) lag = fit;
-    else lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
-  }
+  const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 24) << 20;
+  const size_t hot = (size_t)(P > 2 ? P - 1 : 1);                 // (the extra ring serves pre/post stages)
+  long long lag = ((long long)(budget / (hot * tb)) - 1) / 2;
+  if (lag > 24) lag = 24;
+  if (lag < 1) lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
   if (const char* e = getenv("PFFFT_B200_TS_LAG")) { const long long v = atoll(e); if (v >= 0 && v < 4096) lag = v; }
   h->lag = (int)lag;
   h->ring_slots = lag > 0 ? 2 * (int)lag + 1 : 1;
@@ -207,19 +202,22 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   //  never more than its own co-resident maximum)
   const int grid_cap = h->grid_v[with_pre ? 1 : 0] < h->grid ? h->grid_v[with_pre ? 1 : 0] : h->grid;
   const size_t smem = h->smem_v[with_pre ? 1 : 0];
-  // tickets are 32-bit: very long batches go in several launches
-  const long long max_groups = (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)group);
-  const long long max_batch = max_groups - (long long)(ns - 1) * h->lag;
+  // work-item numbers are 32-bit (batch * tiles of a stage + the worker count < 2^32): very long batches go in several launches
+  long long max_tiles = 1;
+  for (int i = 0; i < ns; ++i) if (P.st[i].tiles > max_tiles) max_tiles = P.st[i].tiles;
+  const long long max_batch = (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)max_tiles);
   for (long long b0 = 0; b0 < batch; b0 += max_batch) {
     const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
     P.in = in + b0 * 2LL * h->Nc; P.out = out + b0 * 2LL * h->Nc; P.batch = nb;
-    const long long total = (nb + (long long)(ns - 1) * h->lag) * group;
-    P.total_items = (unsigned)total;
+    const long long total = nb * group;                           // work items of this launch
+    P.total_items = (unsigned)(total > 0xFFFFFFFFll ? 0xFFFFFFFFll : total);   // (informational)
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
+    // every stage needs at least one worker (ts_worker: worker g serves stage g mod nstages)
     if constexpr (sizeof(T) == 4) {
       if (h->wmode) {
-        const long long ctas = (total + kTswWarps - 1) / kTswWarps;
-        const long long g = ctas < h->grid ? ctas : h->grid;
+        long long g = (total + kTswWarps - 1) / kTswWarps;
+        if (g > h->grid) g = h->grid;
+        if (g * kTswWarps < ns) g = (ns + kTswWarps - 1) / kTswWarps;
         auto wk = sign < 0 ? TswKernels::kern<-1>() : TswKernels::kern<+1>();
         wk<<<(int)g, kTswWarps * 32, h->smem, st>>>(P, h->twL_entries);
         count_launch();
@@ -227,7 +225,8 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
         continue;
       }
     }
-    const long long g = total < grid_cap ? total : grid_cap;
+    long long g = total < grid_cap ? total : grid_cap;
+    if (g < ns) g = ns;
     kern<<<(int)g, kTsThreads, smem, st>>>(P);
     count_launch();
     PF_CUDA_OK(cudaGetLastError());

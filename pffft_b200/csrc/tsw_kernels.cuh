@@ -143,20 +143,25 @@ __global__ void __launch_bounds__(kTswWarps * 32, MINB) k_tsw_pipeline(const __g
     for (int i = 0; i < kTsMaxStages; ++i) ST[i] = P.st[i];
   }
   __syncthreads();
-  const unsigned nwarps = gridDim.x * kTswWarps;
+  // stage-specialised workers (ts_worker): this warp serves one stage for the whole launch
+  const TsWorker wk = ts_worker(P, ST, blockIdx.x * kTswWarps + warp, gridDim.x * kTswWarps);
+  const int stage_i = wk.stage;
+  const TsStage& st = ST[stage_i];
+  const unsigned tiles = (unsigned)st.tiles;
   int cur_ready = 0;                                              // warp-uniform
-  for (unsigned cur = blockIdx.x * kTswWarps + warp; cur < P.total_items; cur += nwarps) {
-    const unsigned nxt = cur + nwarps;
-    int stage_i, item; long long tr;
-    const bool live = ts_decode(P, ST, cur, &stage_i, &tr, &item);
+  unsigned* pending = nullptr;                                    // completion signal of the previous item, not yet sent
+  for (unsigned cur = wk.q0; cur < wk.count; cur += wk.step) {
+    const unsigned nxt = cur + wk.step;
+    const long long tr = (long long)(cur / tiles);
+    const int item = (int)(cur - (unsigned)tr * tiles);
     // ---- readiness of item i (poll only if the early look did not already show it), early look at item i+1.  EVERY lane
     // runs this control code (same addresses: one request per warp instruction): the first version gave it to lane 0 alone,
     // and the warps ran the whole loop split in two halves of 16 lanes (ncu: 16 threads per executed instruction, every
     // __syncwarp on its divergent slow path, twice the instructions)
-    TsDeps d;
-    d.in_ctr = nullptr; d.free_ctr = nullptr; d.done = nullptr; d.in_need = 0; d.free_need = 0;
-    if (live) d = ts_deps(P, ST, stage_i, tr);
-    if (!cur_ready && live) {
+    const TsDeps d = ts_deps(P, ST, stage_i, tr);
+    if (!cur_ready) {
+      // nothing may be owed while this warp waits: others may be waiting for exactly that signal
+      if (pending) { if (lane == 0) ts_red_release(pending); pending = nullptr; }
       for (;;) {
         const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
         if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
@@ -165,34 +170,33 @@ __global__ void __launch_bounds__(kTswWarps * 32, MINB) k_tsw_pipeline(const __g
     }
     unsigned li = 0, lf = 0, n_in_need = 0, n_free_need = 0;
     bool n_live = false, n_has_in = false, n_has_free = false;
-    {
-      int nstage, nitem; long long ntr;
-      if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
-        const TsDeps nd = ts_deps(P, ST, nstage, ntr);
-        n_live = true; n_has_in = nd.in_ctr != nullptr; n_has_free = nd.free_ctr != nullptr;
-        n_in_need = nd.in_need; n_free_need = nd.free_need;
-        if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);
-        if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
-      }
+    if (nxt < wk.count) {
+      const TsDeps nd = ts_deps(P, ST, stage_i, (long long)(nxt / tiles));
+      n_live = true; n_has_in = nd.in_ctr != nullptr; n_has_free = nd.free_ctr != nullptr;
+      n_in_need = nd.in_need; n_free_need = nd.free_need;
+      if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);
+      if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
     }
     __syncwarp();                                                 // item i is ready: its input may be read
-    const TsStage& st = ST[stage_i];
     int ll = lane;
     asm volatile("" : "+r"(ll));                                  // opaque per iteration (see ts_kernels.cuh: loop-invariant hoisting)
-    if (live) {
-      const cpx<T>* src = ts_src(P, st.src, tr);
-      cpx<T>* dst = ts_dst(P, st.dst, tr);
-      if (st.kind == TS_FIRST || st.kind == TS_LATER) {
-        tsw_item_phase_any<SIGN, T>(0, ll, item, st, P.Nc, src, dst, P.tw, twRs, twLs, tile);
-        __syncwarp();
-        tsw_item_phase_any<SIGN, T>(1, ll, item, st, P.Nc, src, dst, P.tw, twRs, twLs, tile);
-      } else if (st.kind == TS_PRE) ts_pre_item<T>(lane, 32, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
-      else if (st.kind == TS_POST) ts_post_item<T>(lane, 32, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
-    }
+    const cpx<T>* src = ts_src(P, st.src, tr);
+    cpx<T>* dst = ts_dst(P, st.dst, tr);
+    if (st.kind == TS_FIRST || st.kind == TS_LATER) {
+      tsw_item_phase_any<SIGN, T>(0, ll, item, st, P.Nc, src, dst, P.tw, twRs, twLs, tile);
+      // the previous item's completion signal goes out HERE: its release fence waits for stores issued a whole phase ago
+      // instead of stalling the warp right behind them (ncu of the first version: 2.0 warps per issue stalled on `membar`)
+      if (pending) { if (lane == 0) ts_red_release(pending); pending = nullptr; }
+      __syncwarp();
+      tsw_item_phase_any<SIGN, T>(1, ll, item, st, P.Nc, src, dst, P.tw, twRs, twLs, tile);
+    } else if (st.kind == TS_PRE) ts_pre_item<T>(lane, 32, item, st.mode, P.in + tr * 2LL * P.Nc, dst, P.N, P.Nc, P.twr);
+    else if (st.kind == TS_POST) ts_post_item<T>(lane, 32, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     __syncwarp();                                                 // every store of the item is issued; the tile is free again
-    if (live && lane == 0) ts_red_release(d.done);
+    if (pending) { if (lane == 0) ts_red_release(pending); }      // (element-wise stages: still owed)
+    pending = d.done;
     cur_ready = n_live && (!n_has_in || li >= n_in_need) && (!n_has_free || lf >= n_free_need);
   }
+  if (pending && lane == 0) ts_red_release(pending);
 }
 #endif  // __CUDACC__
 
