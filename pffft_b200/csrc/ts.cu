@@ -149,20 +149,25 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   int amax = 0; long long group = 0;
   for (int i = 0; i < P; ++i) { if (A[i] > amax) amax = A[i]; group += ts_tiles(Nc, A[i]); }
   (void)amax;
-  // warp-sized work items for power-of-two float plans (PFFFT_B200_TSW=0: CTA-sized items everywhere)
-  { const char* e = getenv("PFFFT_B200_TSW"); h->wmode = !dbl && tsw_plan_ok(P, A) && !(e && atoi(e) == 0); }
+  // warp-sized work items (tsw_kernels.cuh) for power-of-two float plans: opt-in, PFFFT_B200_TSW=1 -- correct on hardware,
+  // but measured at 0.30-0.32 of the roofline at 16384 ... 65536 against 0.41-0.45 for the CTA-sized items
+  { const char* e = getenv("PFFFT_B200_TSW"); h->wmode = !dbl && tsw_plan_ok(P, A) && e && atoi(e) == 1; }
   if (h->wmode) { group = 0; for (int i = 0; i < P; ++i) group += ts_tiles(Nc, A[i], true); }
   bool ok = dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h);
   ok = ok && (h->wmode ? tsw_prepare_kernels(h) : (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h))) == 0;
-  // ring depth: the producers of a stage may run 2*lag+1 transforms ahead of its consumers (stage-specialised workers,
-  // ts_worker); the rings must stay L2 resident to pay, so they are sized by bytes: ~24 MB over the rings a complex ordered
-  // call touches, at most 49 slots (PFFFT_B200_TS_RING_MB / PFFFT_B200_TS_LAG override).
+  // ring depth.  With stage-specialised workers (ts_worker) the W/nstages workers of a pass hold W / (nstages * tiles)
+  // transforms in flight, and the pass behind it as many: a ring needs about twice that many slots or the producers wait for
+  // free slots (measured, profiles/r02b_large_n.md: 16384 with 49 slots 0.20 of the roofline, with 151 slots 0.44).  The
+  // rings must also stay L2 resident to pay: at most ~48 MB over the rings a complex ordered call touches.
   h->nrings = P;                                                  // P-1 between the passes + one for a pre-/post-stage
   const size_t tb = (size_t)Nc * csz;
-  const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 24) << 20;
+  const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 48) << 20;
   const size_t hot = (size_t)(P > 2 ? P - 1 : 1);                 // (the extra ring serves pre/post stages)
-  long long lag = ((long long)(budget / (hot * tb)) - 1) / 2;
-  if (lag > 24) lag = 24;
+  const long long workers = h->wmode ? (long long)h->grid * kTswWarps : (long long)h->grid;
+  const long long tiles0 = ts_tiles(Nc, A[0], h->wmode);
+  long long lag = (workers / P + tiles0 - 1) / tiles0 + 1;        // transforms in flight per stage (+1)
+  const long long fit = ((long long)(budget / (hot * tb)) - 1) / 2;
+  if (lag > fit) lag = fit;
   if (lag < 1) lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
   if (const char* e = getenv("PFFFT_B200_TS_LAG")) { const long long v = atoll(e); if (v >= 0 && v < 4096) lag = v; }
   h->lag = (int)lag;

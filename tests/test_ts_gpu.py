@@ -42,7 +42,7 @@ def test_every_mode_vs_reference(pf, ref, R, ts_on, core, tr, dtype):
     pow2 = (N & (N - 1)) == 0
     tol_ref = TOL[dtype] if (pow2 or dtype == np.float32) else 5e-7      # reference double path: float radix-3/5 constants
     with pf.Setup(N, tr, dtype) as s:
-        assert s.kernel.startswith("ts_"), s.kernel
+        assert s.kernel.startswith(("ts_", "tsw_")), s.kernel
         xd = torch.from_numpy(x).cuda()
         fo = s.transform_batch(xd, 0, True)
         fz = s.transform_batch(xd, 0, False)
