@@ -194,6 +194,88 @@ PF_HD void k2_store_pairs(int t, const cpx<T> (&u)[16], T* base, int N, const cp
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// BACKWARD REAL (ordered spectrum in, time samples out) for C <= 8 as the MIRROR IMAGE of the forward passes -- decimation
+// in frequency (round 2b).  The element-wise form (k2_pass1<L_R_ORD>) rebuilds every packed input Z[n] from X[n] and X[Nc-n]
+// with two mirrored global reads and a rotation per element: 2x the load instructions and LSU wavefronts of the forward
+// kernel (C3 backward 0.75 of the roofline against 0.83 forward).  Mirrored, the thread that owns row (k_a, k_b) also owns
+// the row with the mirror bins (the forward kernel's k2_store_pairs, read backwards): every spectrum element is loaded ONCE
+// and a pair (k, Nc-k) shares its sum, difference and twiddle:
+//     a = X[k], b = conj X[Nc-k], s = a + b, u = (a - b) * conj(w_k):   Z[k] = s + i u,   Z[Nc-k] = conj(s) + i conj(u)
+//   pass B1: thread (k_a, k_b) [+ mirror row]: pre-rotation in registers, radix-C DFT over k_c -> n_c, * conj W_{16C}^{n_c k_b}
+//   pass B2: thread (k_a, n_c): radix 16 over k_b -> n_b, * conj W_Nc^{(n_c + C n_b) k_a}            (in place)
+//   pass B3: thread m = (n_b, n_c): radix 16 over k_a -> n_a, stores x[m + 16C n_a]                  (coalesced)
+// Same tile, same swizzle: B1 writes what forward pass 3 reads, B3 reads what forward pass 1 writes.
+// ---------------------------------------------------------------------------------------------------------------
+// Z[k], Z[Nc-k] from a = X[k], xm = X[Nc-k]
+template <typename T> PF_HD void real_pre_regs(cpx<T> a, cpx<T> xm, cpx<T> w, cpx<T>* zk, cpx<T>* zm) {
+  const cpx<T> b = conj(xm);
+  const cpx<T> s = a + b, d = a - b;
+  const cpx<T> u = cmul_dir<+1>(d, w);                       // d * conj(w)
+  *zk = s + mul_pi(u);                                        // s + i u
+  *zm = conj(s) + mul_pi(conj(u));                            // conj(s) + i conj(u)
+}
+template <int C, typename T>
+PF_HD void k2b_pass1_pairs(int t, const T* base, int N, const cpx<T>* twr, const cpx<T>* tw2, cpx<T>* tile) {
+  using K = K2<C>;
+  const cpx<T>* X = reinterpret_cast<const cpx<T>*>(base);
+  const int ka = t & 15, kb0 = t >> 4;
+#pragma unroll
+  for (int r = 0; r < 8 / C; ++r) {
+    const int kb = kb0 + C * r;
+    int ka2, kb2;
+    k2_mirror_row<C>(ka, kb, ka2, kb2);
+    cpx<T> xa[C], xb[C], za[C], zb[C];
+#pragma unroll
+    for (int kc = 0; kc < C; ++kc) { xa[kc] = X[ka + 16 * kb + 256 * kc]; xb[kc] = X[ka2 + 16 * kb2 + 256 * kc]; }
+    if (ka == 0 && kb == 0) {
+      // row (0,0): k = 256 kc pairs with 256 (C - kc) inside the row; row (0,8): k = 128 + 256 kc with 128 + 256 (C-1-kc)
+      za[0] = mk<T>(xa[0].x + xa[0].y, xa[0].x - xa[0].y);                          // slot 0 = (DC, Nyquist)
+      if (C >= 2) za[C / 2] = scale(conj(xa[C / 2]), T(2));                          // Z[Nc/2] = 2 conj X[Nc/2]
+#pragma unroll
+      for (int kc = 1; kc < C / 2; ++kc) real_pre_regs<T>(xa[kc], xa[C - kc], ldtab(twr + 256 * kc), &za[kc], &za[C - kc]);
+#pragma unroll
+      for (int kc = 0; kc < C / 2; ++kc) real_pre_regs<T>(xb[kc], xb[C - 1 - kc], ldtab(twr + 128 + 256 * kc), &zb[kc], &zb[C - 1 - kc]);
+    } else {
+#pragma unroll
+      for (int kc = 0; kc < C; ++kc) real_pre_regs<T>(xa[kc], xb[C - 1 - kc], ldtab(twr + ka + 16 * kb + 256 * kc), &za[kc], &zb[C - 1 - kc]);
+    }
+    dft_small<C, +1>(za);
+    dft_small<C, +1>(zb);
+    tile[K::idx(ka, kb, 0)] = za[0];
+    tile[K::idx(ka2, kb2, 0)] = zb[0];
+#pragma unroll
+    for (int nc = 1; nc < C; ++nc) {
+      tile[K::idx(ka, kb, nc)] = cmul_dir<+1>(za[nc], ldtab(tw2 + kb * C + nc));
+      tile[K::idx(ka2, kb2, nc)] = cmul_dir<+1>(zb[nc], ldtab(tw2 + kb2 * C + nc));
+    }
+  }
+}
+template <int C, typename T>
+PF_HD void k2b_pass2(int t, const cpx<T>* tw1, cpx<T>* tile) {
+  using K = K2<C>;
+  const int ka = t / C, nc = t % C;
+  cpx<T> v[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = tile[K::idx(ka, brev4(p), nc)];
+  reg_fft<16, +1>(v);
+  if (ka == 0) {
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) tile[K::idx(ka, nb, nc)] = v[nb];
+  } else {
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) tile[K::idx(ka, nb, nc)] = cmul_dir<+1>(v[nb], ldtab(tw1 + ka * K::BC + nb * C + nc));
+  }
+}
+template <int C, typename T>
+PF_HD void k2b_pass3(int m, const cpx<T>* tile, cpx<T> (&v)[16]) {
+  using K = K2<C>;
+  const int jb = m / C, jc = m % C;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) v[p] = tile[K::idx(brev4(p), jb, jc)];
+  reg_fft<16, +1>(v);                                         // v[n_a] = x[m + 16C n_a] (complex pair of real samples)
+}
+
 // natural index of u[r*C + kc] held by thread t after pass 3
 template <int C> PF_HD int k2_out_index(int t, int r, int kc) { return (t & 15) + 16 * ((t >> 4) + C * r) + 256 * kc; }
 
@@ -238,6 +320,7 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
   constexpr bool kNeedsPartner = (SM == S_R_ORD || SM == S_R_Z);  // forward real: X[k] needs Z[k] and Z[Nc-k]
   // (staging the ORDERED backward-real input was measured slower than its direct mirrored loads: 0.58 vs 0.75)
   constexpr bool kGatherIn = (LM == L_C_Z || LM == L_R_Z);
+  constexpr bool kMirrorBwd = (LM == L_R_ORD && SM == S_R_TIME && SIGN > 0 && C <= 8 && !STAGED);
   // the API length is fixed by the kernel: a compile-time N turns the z-domain index maps into shifts and masks
   constexpr int kN = (LM == L_C_ORD || LM == L_C_Z) ? K::NC : 2 * K::NC;
   constexpr bool kZIn = (LM == L_C_Z || LM == L_R_Z);
@@ -269,6 +352,24 @@ k_cta_fft(const XformParams<T> p, const cpx<T>* tw1, const cpx<T>* tw2) {
         mbar_expect_tx(bar, kStageBytes);
         bulk_g2s(stage, p.in + nxt * p.in_stride, kStageBytes, bar);
       }
+    } else if (kMirrorBwd && p.in_estride == 1 && p.in_limit < 0 && vec_aligned<T>(ibase) && vec_aligned<T>(obase)) {
+      // backward real, ordered spectrum: decimation in frequency with in-register pair pre-rotation (see k2b_pass1_pairs)
+      k2b_pass1_pairs<C, T>(t, ibase, kN, twr, tw2, tile);
+      __syncthreads();
+      k2b_pass2<C, T>(t, tw1, tile);
+      __syncthreads();
+      cpx<T> v[16];
+      k2b_pass3<C, T>(t, tile, v);
+      if (p.out_count >= 2 * K::NC) {
+        cpx<T>* dst = reinterpret_cast<cpx<T>*>(obase);
+#pragma unroll
+        for (int na = 0; na < 16; ++na) dst[t + K::BC * na] = v[na];
+      } else {
+#pragma unroll
+        for (int na = 0; na < 16; ++na) store_elem<SM, T>(obase, t + K::BC * na, v[na], kN, p.out_count, true);
+      }
+      __syncthreads();                          // tile is rewritten by the next transform
+      continue;
     } else if (kGatherIn && aligned16(ibase)) {
       // whole spectrum -> shared (coalesced), then every thread gathers its 16 points (and their mirrors) from there
       stage_in16<T, 16 * C, kZIn>(ibase, reinterpret_cast<T*>(stage), 2 * K::NC, t);

@@ -53,6 +53,17 @@ static void emu_k2_run(const float* in, float* out, int N, long long in_limit, i
   const cf* ptw2 = reinterpret_cast<const cf*>(tw2.data());
   const cf* ptwr = reinterpret_cast<const cf*>(twr.data());
   std::vector<cf> tile(Nc), nat(Nc);
+  if constexpr (LM == L_R_ORD && SM == S_R_TIME && SIGN > 0 && C <= 8) {      // mirrored (decimation in frequency) backward real
+    for (auto& e : tile) { e.x = NAN; e.y = NAN; }
+    for (int t = 0; t < K::T; ++t) k2b_pass1_pairs<C, float>(t, in, N, ptwr, ptw2, tile.data());
+    for (int t = 0; t < K::T; ++t) k2b_pass2<C, float>(t, ptw1, tile.data());
+    for (int t = 0; t < K::T; ++t) {
+      cf v[16];
+      k2b_pass3<C, float>(t, tile.data(), v);
+      for (int na = 0; na < 16; ++na) store_elem<SM, float>(out, t + K::BC * na, v[na], N, out_count, vec_aligned<float>(out));
+    }
+    return;
+  }
   for (int t = 0; t < K::T; ++t) k2_pass1<C, LM, SIGN, false, float>(t, in, N, ptwr, in_limit, vec_aligned<float>(in), ptw1, tile.data());
   for (int t = 0; t < K::T; ++t) k2_pass2<C, SIGN, float>(t, ptw2, tile.data());
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
