@@ -155,20 +155,25 @@ TsPlanHost* ts_create(int N, int Nc, bool dbl, int device, int sm_count) {
   if (h->wmode) { group = 0; for (int i = 0; i < P; ++i) group += ts_tiles(Nc, A[i], true); }
   bool ok = dbl ? ts_fill_radix_tables<double>(h) : ts_fill_radix_tables<float>(h);
   ok = ok && (h->wmode ? tsw_prepare_kernels(h) : (dbl ? ts_prepare_kernels<double>(h) : ts_prepare_kernels<float>(h))) == 0;
-  // ring depth.  With stage-specialised workers (ts_worker) the W/nstages workers of a pass hold W / (nstages * tiles)
-  // transforms in flight, and the pass behind it as many: a ring needs about twice that many slots or the producers wait for
-  // free slots (measured, profiles/r02b_large_n.md: 16384 with 49 slots 0.20 of the roofline, with 151 slots 0.44).  The
-  // rings must also stay L2 resident to pay: at most ~48 MB over the rings a complex ordered call touches.
+  // pipeline depth.  CTA kernel (interleaved order): pass i+1 of a transform is handed out `lag` groups after pass i -- about
+  // 1.5 grid-fulls of work items later, so its input is complete (no spinning) and still in L2; rings hold 2*lag+1
+  // transforms so a slot's previous occupant has long been consumed when it is overwritten.  Warp kernel (stage-specialised
+  // workers): a pass holds workers / (P * tiles) transforms in flight and its ring needs about twice that.  Either way the
+  // rings must stay L2 resident to pay: at most ~48 MB over the rings a complex ordered call touches.
   h->nrings = P;                                                  // P-1 between the passes + one for a pre-/post-stage
   const size_t tb = (size_t)Nc * csz;
   const size_t budget = (size_t)(getenv("PFFFT_B200_TS_RING_MB") ? atoi(getenv("PFFFT_B200_TS_RING_MB")) : 48) << 20;
   const size_t hot = (size_t)(P > 2 ? P - 1 : 1);                 // (the extra ring serves pre/post stages)
-  const long long workers = h->wmode ? (long long)h->grid * kTswWarps : (long long)h->grid;
-  const long long tiles0 = ts_tiles(Nc, A[0], h->wmode);
-  long long lag = (workers / P + tiles0 - 1) / tiles0 + 1;        // transforms in flight per stage (+1)
+  long long lag;
+  if (h->wmode) {
+    const long long tiles0 = ts_tiles(Nc, A[0], true);
+    lag = ((long long)h->grid * kTswWarps / P + tiles0 - 1) / tiles0 + 1;
+  } else {
+    lag = (3LL * h->grid / 2 + group - 1) / group;
+    if (lag < 1) lag = 1;
+  }
   const long long fit = ((long long)(budget / (hot * tb)) - 1) / 2;
-  if (lag > fit) lag = fit;
-  if (lag < 1) lag = ((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0;
+  if (lag > fit) lag = fit >= 1 ? fit : (((size_t)h->nrings * 3 * tb <= ((size_t)512 << 20)) ? 1 : 0);
   if (const char* e = getenv("PFFFT_B200_TS_LAG")) { const long long v = atoll(e); if (v >= 0 && v < 4096) lag = v; }
   h->lag = (int)lag;
   h->ring_slots = lag > 0 ? 2 * (int)lag + 1 : 1;
@@ -207,19 +212,20 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
   //  never more than its own co-resident maximum)
   const int grid_cap = h->grid_v[with_pre ? 1 : 0] < h->grid ? h->grid_v[with_pre ? 1 : 0] : h->grid;
   const size_t smem = h->smem_v[with_pre ? 1 : 0];
-  // work-item numbers are 32-bit (batch * tiles of a stage + the worker count < 2^32): very long batches go in several launches
+  // work-item numbers are 32-bit: very long batches go in several launches
   long long max_tiles = 1;
   for (int i = 0; i < ns; ++i) if (P.st[i].tiles > max_tiles) max_tiles = P.st[i].tiles;
-  const long long max_batch = (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)max_tiles);
+  const long long max_batch = h->wmode
+      ? (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)max_tiles)      // batch * tiles + workers < 2^32
+      : (long long)((0xFFFFFFFFull - 8ull * (unsigned long long)h->grid) / (unsigned long long)group) - (long long)(ns - 1) * h->lag;
   for (long long b0 = 0; b0 < batch; b0 += max_batch) {
     const long long nb = batch - b0 < max_batch ? batch - b0 : max_batch;
     P.in = in + b0 * 2LL * h->Nc; P.out = out + b0 * 2LL * h->Nc; P.batch = nb;
-    const long long total = nb * group;                           // work items of this launch
-    P.total_items = (unsigned)(total > 0xFFFFFFFFll ? 0xFFFFFFFFll : total);   // (informational)
     PF_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, h->counter_bytes, st));
-    // every stage needs at least one worker (ts_worker: worker g serves stage g mod nstages)
     if constexpr (sizeof(T) == 4) {
-      if (h->wmode) {
+      if (h->wmode) {                                             // stage-specialised warps: every stage needs a worker
+        const long long total = nb * group;
+        P.total_items = (unsigned)(total > 0xFFFFFFFFll ? 0xFFFFFFFFll : total);   // (informational)
         long long g = (total + kTswWarps - 1) / kTswWarps;
         if (g > h->grid) g = h->grid;
         if (g * kTswWarps < ns) g = (ns + kTswWarps - 1) / kTswWarps;
@@ -230,8 +236,9 @@ int ts_run(TsPlanHost* h, const T* in, T* out, long long batch, int sign, int lm
         continue;
       }
     }
-    long long g = total < grid_cap ? total : grid_cap;
-    if (g < ns) g = ns;
+    const long long total = (nb + (long long)(ns - 1) * h->lag) * group;      // interleaved order incl. pipeline fill / drain slots
+    P.total_items = (unsigned)total;
+    const long long g = total < grid_cap ? total : grid_cap;
     kern<<<(int)g, kTsThreads, smem, st>>>(P);
     count_launch();
     PF_CUDA_OK(cudaGetLastError());

@@ -264,7 +264,8 @@ PF_HD bool ts_decode(const TsParams<T>& P, const TsStage* ST, unsigned ticket, i
 // ring slot of transform tr: 32-bit arithmetic (tr < 2^31, see ts_run) -- a 64-bit modulo is a ~100-instruction subroutine,
 // and the first versions of the kernel ran five of them per thread and work item (40 % of all executed instructions, with
 // thread 0's copies on the critical path of every barrier)
-// STAGE-SPECIALISED WORK DISTRIBUTION (round 2b).  Worker g of W (a CTA of k_ts_pipeline, a warp of k_tsw_pipeline) serves
+// STAGE-SPECIALISED WORK DISTRIBUTION (round 2b; used by k_tsw_pipeline -- measured on k_ts_pipeline too and taken out again,
+// see the note at the end of this comment).  Worker g of W (a warp of k_tsw_pipeline) serves
 // ONE stage, s = g mod nstages, as the (g div nstages)-th of the n_s workers there, and takes that stage's work items
 // q = j, j + n_s, ... in order (q = transform * tiles + tile).  The first versions dealt all stages out to all workers in one
 // interleaved order ("pass 2 of transform g - L behind pass 1 of transform g"): a worker whose pass-2 item had to wait for
@@ -272,6 +273,10 @@ PF_HD bool ts_decode(const TsParams<T>& P, const TsStage* ST, unsigned ticket, i
 // 36 polls per work item in the CTA kernel and 139 in the warp kernel.  Now the producers of a stage never wait for its
 // consumers (only for a free ring slot, 2L+1 transforms ahead), every worker waits only for work of an EARLIER transform or
 // stage, and all workers are co-resident: no deadlock.
+// On the CTA kernel the polls disappeared and the time did not change (the waits had been hidden behind the other CTAs of
+// the SM): 16384 / 65536 / 2^17 / 2^20 / 2^24 / 2^26: 0.45 / 0.40 / 0.28 / 0.25 / 0.13 / 0.07 of the roofline against 0.45 / 0.44 /
+// 0.26 / 0.27 / 0.23 / 0.16 interleaved -- a stage's producers need ring slots for every transform they hold in flight, which
+// transforms of 128 MB do not have.  k_ts_pipeline went back to the interleaved order (profiles/r02b_large_n.md).
 struct TsWorker { int stage; unsigned q0, step, count; };
 template <typename T> PF_HD TsWorker ts_worker(const TsParams<T>& P, const TsStage* ST, unsigned g, unsigned W) {
   TsWorker w;
@@ -381,23 +386,20 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
   }
   __syncthreads();
   bool staged = false;                                            // CTA-uniform: the current item's input is in `stage`
-  const TsWorker wk = ts_worker(P, ST, blockIdx.x, gridDim.x);
-  const int stage_i = wk.stage;
-  const TsStage& st = ST[stage_i];
-  const unsigned tiles = (unsigned)st.tiles;
-  for (unsigned cur = wk.q0; cur < wk.count; cur += wk.step) {
-    const unsigned nxt = cur + wk.step;                           // (count + step < 2^32: checked by the host)
-    const long long tr = (long long)(cur / tiles);
-    const int item = (int)(cur - (unsigned)tr * tiles);
+  for (unsigned cur = blockIdx.x; cur < P.total_items; cur += gridDim.x) {
+    const unsigned nxt = cur + gridDim.x;                         // (total_items + gridDim.x < 2^32: checked by the host)
     // ---- readiness of item i: known from the early look of the previous iteration (s_cur_ready, CTA-uniform after the
     // closing barrier) in all but a few per cent of the items -- only then does thread 0 poll, behind a barrier of its own
     if (!s_cur_ready) {
       if (t == 0) {
-        const TsDeps d = ts_deps(P, ST, stage_i, tr);
-        for (;;) {
-          const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
-          if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
-          __nanosleep(100);
+        int stage_p, item_p; long long tr_p;
+        if (ts_decode(P, ST, cur, &stage_p, &tr_p, &item_p)) {
+          const TsDeps d = ts_deps(P, ST, stage_p, tr_p);
+          for (;;) {
+            const unsigned a = d.in_ctr ? ts_ld_relaxed(d.in_ctr) : 0u, f = d.free_ctr ? ts_ld_relaxed(d.free_ctr) : 0u;
+            if ((!d.in_ctr || a >= d.in_need) && (!d.free_ctr || f >= d.free_need)) break;
+            __nanosleep(100);
+          }
         }
       }
       __syncthreads();
@@ -406,14 +408,20 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     // after phase 1
     unsigned li = 0, lf = 0, n_in_need = 0, n_free_need = 0;
     bool n_live = false, n_has_in = false, n_has_free = false;
-    if (t == 0 && nxt < wk.count) {
-      const TsDeps nd = ts_deps(P, ST, stage_i, (long long)(nxt / tiles));
-      n_live = true; n_has_in = nd.in_ctr != nullptr; n_has_free = nd.free_ctr != nullptr;
-      n_in_need = nd.in_need; n_free_need = nd.free_need;
-      if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);               // in flight during phase 1
-      if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
+    if (t == 0) {
+      int nstage, nitem; long long ntr;
+      if (nxt < P.total_items && ts_decode(P, ST, nxt, &nstage, &ntr, &nitem)) {
+        const TsDeps nd = ts_deps(P, ST, nstage, ntr);
+        n_live = true; n_has_in = nd.in_ctr != nullptr; n_has_free = nd.free_ctr != nullptr;
+        n_in_need = nd.in_need; n_free_need = nd.free_need;
+        if (nd.in_ctr) li = ts_ld_relaxed(nd.in_ctr);             // in flight during phase 1
+        if (nd.free_ctr) lf = ts_ld_relaxed(nd.free_ctr);
+      }
     }
-    const bool fft = st.kind == TS_FIRST || st.kind == TS_LATER;
+    int stage_i, item; long long tr;
+    const bool live = ts_decode(P, ST, cur, &stage_i, &tr, &item);
+    const TsStage& st = ST[stage_i];
+    const bool fft = live && (st.kind == TS_FIRST || st.kind == TS_LATER);
     // the thread index is made opaque per iteration: otherwise the compiler hoists the per-thread index arithmetic of ALL
     // 24 radix bodies (t % A, t / A, tile offsets ...) out of the persistent loop and spills ~150 values to local memory
     int tt = t;
@@ -429,12 +437,16 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
       s_next_ready = n_live && (!n_has_in || li >= n_in_need) && (!n_has_free || lf >= n_free_need);
     __syncthreads();                                              // tile complete; nobody reads `stage` any more
     bool pre_next = false;
-    if constexpr (PRE) if (s_next_ready && fft) {                 // item i+1 is live and its input complete: start fetching it
-      const long long ntr = (long long)(nxt / tiles);
-      ts_prefetch_any<T>(tt, (int)(nxt - (unsigned)ntr * tiles), st, ts_src(P, st.src, ntr), stage);
-      pre_next = true;
+    if constexpr (PRE) if (s_next_ready) {                        // item i+1 is live and its input complete: start fetching it
+      int nstage, nitem; long long ntr;
+      ts_decode(P, ST, nxt, &nstage, &ntr, &nitem);
+      const TsStage& nst = ST[nstage];
+      if (nst.kind == TS_FIRST || nst.kind == TS_LATER) {
+        ts_prefetch_any<T>(tt, nitem, nst, ts_src(P, nst.src, ntr), stage);
+        pre_next = true;
+      }
     }
-    {
+    if (live) {
       const cpx<T>* src = ts_src(P, st.src, tr);
       cpx<T>* dst = ts_dst(P, st.dst, tr);
       if (st.kind == TS_FIRST) ts_item_phase_any<true, SIGN, T>(1, tt, item, st, src, dst, P.tw, twRs, tile);
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(kTsThreads, MINB) k_ts_pipeline(const __grid_c
     if (t == 0) s_cur_ready = s_next_ready;
     staged = pre_next;
     __syncthreads();                                              // every store of the item is issued; tile is free again
-    if (t == kTsThreads - 32) ts_red_release(ts_deps(P, ST, stage_i, tr).done);   // another warp than thread 0's
+    if (t == kTsThreads - 32 && live) ts_red_release(ts_deps(P, ST, stage_i, tr).done);   // another warp than thread 0's
   }
 }
 #endif  // __CUDACC__

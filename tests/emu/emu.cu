@@ -145,14 +145,38 @@ static int ts_schedule(TsParams<T>& P, int window, unsigned seed, Run run) {
 template <typename T, int SIGN>
 static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
   std::vector<cpx<T>> stagebuf(16 * 256);
+  std::vector<unsigned> counters(kTsCounterBase + (size_t)kTsMaxStages * P.ring_slots, 0u);
   std::vector<cpx<T>> tile(16 * 256);
-  return ts_schedule<T>(P, window, seed, [&](int stage, long long tr, int item, uint32_t rs) {
+  std::vector<unsigned> flight;
+  unsigned next = 0;
+  uint32_t rs = seed * 2654435761u + 12345u;
+  auto ready = [&](unsigned ticket) {
+    int stage, item; long long tr;
+    if (!ts_decode(P, P.st, ticket, &stage, &tr, &item)) return true;
+    const int slot = (int)(tr % P.ring_slots); const unsigned gen = (unsigned)(tr / P.ring_slots);
+    const unsigned* base = counters.data() + kTsCounterBase + slot;
+    if (stage > 0 && base[(stage - 1) * P.ring_slots] < (gen + 1u) * (unsigned)P.st[stage - 1].tiles) return false;
+    if (stage + 1 < P.nstages && gen > 0 && base[(stage + 1) * P.ring_slots] < gen * (unsigned)P.st[stage + 1].tiles) return false;
+    return true;
+  };
+  while (next < P.total_items || !flight.empty()) {
+    while ((int)flight.size() < window && next < P.total_items) flight.push_back(next++);
+    std::vector<int> cand;
+    for (int i = 0; i < (int)flight.size(); ++i) if (ready(flight[i])) cand.push_back(i);
+    if (cand.empty()) return -10;                                  // deadlock
+    rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+    const int pick = cand[rs % cand.size()];
+    const unsigned cur = flight[pick];
+    flight.erase(flight.begin() + pick);
+    int stage, item; long long tr;
+    if (!ts_decode(P, P.st, cur, &stage, &tr, &item)) continue;
     const TsStage& st = P.st[stage];
     const cpx<T>* src = ts_src(P, st.src, tr);
     cpx<T>* dst = ts_dst(P, st.dst, tr);
     if (st.kind == TS_FIRST || st.kind == TS_LATER) {
       // every other item (float) takes the prefetched path: phase 1 reads the staging buffer instead of global memory
-      const bool staged = sizeof(T) == 4 && (rs & 16u);
+      rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+      const bool staged = sizeof(T) == 4 && (rs & 1u);
       if (staged) {
         for (auto& e : stagebuf) { e.x = (T)NAN; e.y = (T)NAN; }
         ts_emu_stage<T>(item, st, src, stagebuf.data());
@@ -171,7 +195,9 @@ static int ts_emulate(TsParams<T>& P, int window, unsigned seed) {
     } else {
       for (int t = 0; t < kTsThreads; ++t) ts_post_item<T>(t, kTsThreads, item, st.mode, src, P.out + tr * 2LL * P.Nc, P.N, P.Nc, P.twr);
     }
-  });
+    counters[kTsCounterBase + stage * P.ring_slots + (int)(tr % P.ring_slots)] += 1;
+  }
+  return 0;
 }
 // ---- warp-sized work items (tsw_kernels.cuh): same protocol, 32 lanes per item, two phases around a __syncwarp
 template <typename T, int SIGN>
@@ -220,6 +246,7 @@ static int emu_ts_t(int N, int transform, int dir, int ordered, const T* in, T* 
   if (wmode && !tsw_plan_ok(Pn, A)) return -2;
   ts_build_stages<T>(P, Nc, Pn, A, tw_off, lm, sm, wmode);
   P.total_items = (unsigned)(batch * P.group_items);
+  if (!wmode) P.total_items = (unsigned)((batch + (long long)(P.nstages - 1) * lag) * P.group_items);   // interleaved order
   if (wmode) {
     const std::vector<T> last = tsw_last_table<T>(ts_radix(A[Pn - 1]));
     const cpx<T>* twL = reinterpret_cast<const cpx<T>*>(last.data());

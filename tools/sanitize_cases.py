@@ -42,6 +42,13 @@ os.environ["PFFFT_B200_TS"] = "1"
 for N, tr, batch in [(16384, 1, 300), (8192, 0, 50), (65536, 1, 8)]:
     run(N, tr, np.float32, batch)
 run(16384, 1, np.float64, 20)
+os.environ["PFFFT_B200_TSW"] = "1"                      # warp-sized work items (tsw_kernels.cuh), stage-specialised warps
+for N, tr, batch in [(16384, 1, 200), (8192, 0, 30), (65536, 1, 6), (131072, 1, 3)]:
+    run(N, tr, np.float32, batch)
+del os.environ["PFFFT_B200_TSW"]
+os.environ["PFFFT_B200_TS_MINB"] = "3"; os.environ["PFFFT_B200_TS_PRE"] = "1"     # cp.async input prefetch variant
+run(16384, 1, np.float32, 100)
+del os.environ["PFFFT_B200_TS_MINB"]; del os.environ["PFFFT_B200_TS_PRE"]
 del os.environ["PFFFT_B200_TS"]
 # streaming push / flush and partitioned convolution (C-ABI entry points of round 2)
 n, taps = 30000, 301
