@@ -105,3 +105,31 @@ def test_two_streams_share_one_plan(pf, ref, R, ts_on):
         w = ref.transform_batch(N, 1, x[[0, 63]].cpu().numpy(), 0, True)
         g = y[[0, 63]].cpu().numpy()
         assert max(R.relmax(g[i], w[i]) for i in range(2)) <= 1e-5
+
+
+# ---- opt-in variants of the pipeline (round 2b): warp-sized work items (tsw_kernels.cuh) and the cp.async input prefetch
+@pytest.mark.parametrize("variant", ["tsw", "prefetch"])
+@pytest.mark.parametrize("tr,core,batch", [(1, 16384, 300), (1, 65536, 40), (0, 16384, 60), (1, 131072, 6), (1, 8192, 500)])
+def test_opt_in_pipeline_variants(pf, ref, R, ts_on, monkeypatch, variant, tr, core, batch):
+    """same plans, other kernels: results against the reference on sampled transforms, every transform by round trip"""
+    import torch
+    if variant == "tsw":
+        monkeypatch.setenv("PFFFT_B200_TSW", "1")
+    else:
+        monkeypatch.setenv("PFFFT_B200_TS_MINB", "3"); monkeypatch.setenv("PFFFT_B200_TS_PRE", "1")
+    N = core if tr == 1 else 2 * core
+    per = 2 * core
+    g = torch.Generator(device="cuda"); g.manual_seed(core + tr + 11)
+    x = torch.rand((batch, per), generator=g, device="cuda") * 2 - 1
+    with pf.Setup(N, tr) as s:
+        assert s.kernel.startswith("tsw_" if variant == "tsw" else "ts_"), s.kernel
+        y = s.transform_batch(x, 0, True)
+        yz = s.transform_batch(x, 0, False)
+        z = s.transform_batch(y, 1, True)
+        zz = s.transform_batch(yz, 1, False)
+        torch.cuda.synchronize()
+        assert float((z / N - x).abs().max()) <= N * 1e-7 and float((zz / N - x).abs().max()) <= N * 1e-7
+        for b in (0, batch // 2, batch - 1):
+            xb = x[b].cpu().numpy()
+            assert R.relmax(y[b].cpu().numpy(), ref.transform(N, tr, xb, 0, True)) <= 1e-5, (s.kernel, b)
+            assert R.relmax(yz[b].cpu().numpy(), ref.transform(N, tr, xb, 0, False)) <= 1e-5, (s.kernel, b)

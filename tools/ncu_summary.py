@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""ncu_summary.py <file.ncu-rep> [out.txt] -- condenses an `ncu --set full` capture to the metrics the
+"""ncu_summary.py <file.ncu-rep | raw.csv> [out.txt] -- condenses an `ncu --set full` capture to the metrics the
 roofline discussion uses (per launch).  Run in the build container: ncu reads reports without a GPU."""
 import csv
 import subprocess
@@ -29,7 +29,10 @@ WANT = [
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):                                  # `ncu -i x.ncu-rep --page raw --csv` written on the GPU box (the reports
+        raw = open(rep).read()                                #  themselves are too large to bring back more than one per call)
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     rows = [r for r in rows if len(r) > 20]
     hdr, units = rows[0], rows[1]
