@@ -1,7 +1,10 @@
 // radix_b.cu -- compile-time-radix CTA kernels, larger cores (radix_kernels.cuh): 1296 .. 12000
+#include <stdlib.h>
 #include "radix_impl.cuh"
 namespace pf {
 int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
+                         int device, int sm_count, cudaStream_t st);
+int radix_launch_float_c(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st);
 bool radix_core_supported(int Nc, const char** name) {
   static const struct { int nc; const char* name; } k[] = {
@@ -13,6 +16,9 @@ bool radix_core_supported(int Nc, const char** name) {
 }
 int radix_launch_float(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                        int device, int sm_count, cudaStream_t st) {
+  static const bool one_cta = getenv("PFFFT_B200_RADIX_MINB1") && atoi(getenv("PFFFT_B200_RADIX_MINB1")) == 1;
+  if (one_cta && (Nc == 2000 || Nc == 2592 || Nc == 4000 || Nc == 6000))
+    return radix_launch_float_c(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   switch (Nc) {
     case 1296:  return radix_launch_modes<12, 12, 9,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 2000:  return radix_launch_modes<20, 10, 10, 2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
