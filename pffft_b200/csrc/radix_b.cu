@@ -16,9 +16,15 @@ bool radix_core_supported(int Nc, const char** name) {
 }
 int radix_launch_float(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                        int device, int sm_count, cudaStream_t st) {
-  static const bool one_cta = getenv("PFFFT_B200_RADIX_MINB1") && atoi(getenv("PFFFT_B200_RADIX_MINB1")) == 1;
-  if (one_cta && (Nc == 2000 || Nc == 2592 || Nc == 4000 || Nc == 6000))
-    return radix_launch_float_c(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+  // The radix-18/20 register DFTs of these cores need ~120 registers; at two resident CTAs (72 registers) they spill
+  // 200-500 bytes per thread, at one (128 registers, radix_c.cu) they do not.  Measured (profiles/r02b_radix.md): the forward
+  // REAL transforms, which add the pair rotation on top, are 14-20 % faster without the spills (real 5184 / 8000 / 12000:
+  // 0.35 / 0.29 / 0.29 -> 0.40 / 0.34 / 0.35), the complex ones 5-15 % slower (2000c: 0.50 -> 0.42).
+  // PFFFT_B200_RADIX_MINB1=1 / =0 forces one / two CTAs for every mode.
+  static const int force = getenv("PFFFT_B200_RADIX_MINB1") ? atoi(getenv("PFFFT_B200_RADIX_MINB1")) : -1;
+  const bool big = Nc == 2000 || Nc == 2592 || Nc == 4000 || Nc == 6000;
+  const bool one_cta = force == 1 || (force < 0 && lm == L_R_TIME && Nc != 2000);
+  if (big && one_cta) return radix_launch_float_c(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   switch (Nc) {
     case 1296:  return radix_launch_modes<12, 12, 9,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 2000:  return radix_launch_modes<20, 10, 10, 2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
