@@ -1,8 +1,24 @@
 // radix_a.cu -- compile-time-radix CTA kernels, small cores (radix_kernels.cuh): 16 .. 432
+#include <stdlib.h>
 #include "radix_impl.cuh"
 namespace pf {
 int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st) {
+  // Resident CTAs per SM, measured (profiles/r02b_radix.md; PFFFT_B200_RADIX_VAR=0 forces the round-2 shapes, =2 the
+  // one-more-CTA shapes everywhere): the small cores 48 / 80 / 144 gain 2-5 % from a fourth CTA (64 registers), the backward
+  // real transforms of the core 400 27 % from a third (0.33 -> 0.42); 240 and the forward transforms of 400 lose 8-18 %.
+  static const int var = getenv("PFFFT_B200_RADIX_VAR") ? atoi(getenv("PFFFT_B200_RADIX_VAR")) : -1;
+  const bool bwd_real = lm == L_R_ORD || lm == L_R_Z;
+  const bool more = var == 2 || (var < 0 && (Nc == 48 || Nc == 80 || Nc == 144 || (Nc == 400 && bwd_real)));
+  if (more) switch (Nc) {
+    case 48:  return radix_launch_modes<16, 3,  1,  16, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 80:  return radix_launch_modes<16, 5,  1,  16, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 144: return radix_launch_modes<12, 12, 1,  20, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 240: if (var == 2) return radix_launch_modes<16, 15, 1,  16, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st); break;
+    case 400: return radix_launch_modes<20, 20, 1,  12, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 432: if (var == 2) return radix_launch_modes<12, 12, 3,  2,  4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st); break;
+    default: break;
+  }
   switch (Nc) {
     //                                  R1  R2  R3  TPC MINB
     case 16:  return radix_launch_modes<4,  4,  1,  64, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
