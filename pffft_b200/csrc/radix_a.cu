@@ -27,7 +27,10 @@ int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, floa
     case 144: return radix_launch_modes<12, 12, 1,  20, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 240: return radix_launch_modes<16, 15, 1,  16, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 400: return radix_launch_modes<20, 20, 1,  12, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 432: return radix_launch_modes<12, 12, 3,  2,  3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 432:                                                    // two stages (24 x 18) since round 2b; PFFFT_B200_RADIX_432=3: the three-stage 12 x 12 x 3
+      if (getenv("PFFFT_B200_RADIX_432") && atoi(getenv("PFFFT_B200_RADIX_432")) == 3)
+        return radix_launch_modes<12, 12, 3,  2,  3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+      return radix_launch_modes<24, 18, 1,  10, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return -1;
   }
 }
