@@ -10,6 +10,11 @@ int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, floa
   static const int var = getenv("PFFFT_B200_RADIX_VAR") ? atoi(getenv("PFFFT_B200_RADIX_VAR")) : -1;
   const bool bwd_real = lm == L_R_ORD || lm == L_R_Z;
   const bool more = var == 2 || (var < 0 && (Nc == 48 || Nc == 80 || Nc == 144 || (Nc == 400 && bwd_real)));
+  // cores 48 and 80 with BALANCED radices (8 x 6, 10 x 8: both stages keep 6-10 of the transform's 8-10 threads busy; 16 x 3 and
+  // 16 x 5 left 3 resp. 5 of 16 threads working in the first stage).  PFFFT_B200_RADIX_BAL=0: the round-2 shapes.
+  static const bool balanced = !(getenv("PFFFT_B200_RADIX_BAL") && atoi(getenv("PFFFT_B200_RADIX_BAL")) == 0);
+  if (balanced && Nc == 48) return radix_launch_modes<8,  6, 1, 32, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+  if (balanced && Nc == 80) return radix_launch_modes<10, 8, 1, 24, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   if (more) switch (Nc) {
     case 48:  return radix_launch_modes<16, 3,  1,  16, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 80:  return radix_launch_modes<16, 5,  1,  16, 4>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
@@ -31,6 +36,7 @@ int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, floa
       if (getenv("PFFFT_B200_RADIX_432") && atoi(getenv("PFFFT_B200_RADIX_432")) == 3)
         return radix_launch_modes<12, 12, 3,  2,  3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
       return radix_launch_modes<24, 18, 1,  10, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 720: return radix_launch_modes<30, 24, 1,  8,  2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);   // round 2b (was on the generic kernel: 0.36)
     default: return -1;
   }
 }

@@ -8,8 +8,8 @@ int radix_launch_float_c(int Nc, int lm, int sm, int sign, const float* in, floa
                          int device, int sm_count, cudaStream_t st);
 bool radix_core_supported(int Nc, const char** name) {
   static const struct { int nc; const char* name; } k[] = {
-      {16, "radix_4x4"}, {48, "radix_16x3"}, {80, "radix_16x5"}, {144, "radix_12x12"}, {240, "radix_16x15"}, {400, "radix_20x20"},
-      {432, "radix_24x18"}, {1296, "radix_12x12x9"}, {2000, "radix_20x10x10"}, {2592, "radix_18x12x12"}, {4000, "radix_20x20x10"},
+      {16, "radix_4x4"}, {48, "radix_8x6"}, {80, "radix_10x8"}, {144, "radix_12x12"}, {240, "radix_16x15"}, {400, "radix_20x20"},
+      {432, "radix_24x18"}, {720, "radix_30x24"}, {1296, "radix_12x12x9"}, {2000, "radix_20x10x10"}, {2592, "radix_18x12x12"}, {4000, "radix_20x20x10"},
       {6000, "radix_20x20x15"}, {12000, "radix_25x24x20"}};
   for (const auto& e : k) if (e.nc == Nc) { if (name) *name = e.name; return true; }
   return false;

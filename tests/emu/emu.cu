@@ -325,12 +325,13 @@ extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float
   const int sign = fwd ? -1 : +1;
   switch (Nc) {
     case 16: return radix_emu_modes<4, 4, 1>(N, lm, sm, sign, in, out, t1, t2);
-    case 48: return radix_emu_modes<16, 3, 1>(N, lm, sm, sign, in, out, t1, t2);
-    case 80: return radix_emu_modes<16, 5, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 48: return radix_emu_modes<8, 6, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 80: return radix_emu_modes<10, 8, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 144: return radix_emu_modes<12, 12, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 240: return radix_emu_modes<16, 15, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 400: return radix_emu_modes<20, 20, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 432: return radix_emu_modes<24, 18, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 720: return radix_emu_modes<30, 24, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
     case 2000: return radix_emu_modes<20, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
     case 2592: return radix_emu_modes<18, 12, 12>(N, lm, sm, sign, in, out, t1, t2);

@@ -367,6 +367,8 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(144, 1) as s:
         assert s.kernel == "radix_12x12"
     with pf.Setup(720, 1) as s:
+        assert s.kernel == "radix_30x24"
+    with pf.Setup(96, 1, np.float64) as s:                      # doubles outside the tuned sizes: the generic kernel
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "tiled2dg_256x256"

@@ -6,7 +6,7 @@ import pytest
 from conftest import uniform
 
 pytestmark = pytest.mark.gpu
-CORES = [16, 48, 80, 144, 240, 400, 432, 1296, 2000, 2592, 4000, 6000, 12000]
+CORES = [16, 48, 80, 144, 240, 400, 432, 720, 1296, 2000, 2592, 4000, 6000, 12000]
 
 
 @pytest.fixture()
