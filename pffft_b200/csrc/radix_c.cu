@@ -12,4 +12,25 @@ int radix_launch_float_c(int Nc, int lm, int sm, int sign, const float* in, floa
     default: return -1;
   }
 }
+// Cores 1152 ... 3840 that had no tuned plan (two-launch split plans at 0.30-0.33 of the roofline or the generic shared-memory
+// kernel): three stages of radices <= 16, no spills at three resident CTAs (round 2b, profiles/r02b_radix.md)
+int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
+                         int device, int sm_count, cudaStream_t st) {
+  switch (Nc) {
+    //                                  R1  R2  R3  TPC MINB
+    case 1152: return radix_launch_modes<12, 12, 8,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1200: return radix_launch_modes<12, 10, 10, 2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1280: return radix_launch_modes<16, 10, 8,  2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1440: return radix_launch_modes<12, 12, 10, 2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1600: return radix_launch_modes<16, 10, 10, 2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1728: return radix_launch_modes<12, 12, 12, 2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1920: return radix_launch_modes<16, 12, 10, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2304: return radix_launch_modes<16, 12, 12, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3200: return radix_launch_modes<20, 16, 10, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3456: return radix_launch_modes<16, 18, 12, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3600: return radix_launch_modes<16, 15, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3840: return radix_launch_modes<16, 16, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    default: return -1;
+  }
+}
 }  // namespace pf

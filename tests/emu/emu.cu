@@ -332,6 +332,18 @@ extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float
     case 400: return radix_emu_modes<20, 20, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 432: return radix_emu_modes<24, 18, 1>(N, lm, sm, sign, in, out, t1, t2);
     case 720: return radix_emu_modes<30, 24, 1>(N, lm, sm, sign, in, out, t1, t2);
+    case 1152: return radix_emu_modes<12, 12, 8>(N, lm, sm, sign, in, out, t1, t2);
+    case 1200: return radix_emu_modes<12, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 1280: return radix_emu_modes<16, 10, 8>(N, lm, sm, sign, in, out, t1, t2);
+    case 1440: return radix_emu_modes<12, 12, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 1600: return radix_emu_modes<16, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 1728: return radix_emu_modes<12, 12, 12>(N, lm, sm, sign, in, out, t1, t2);
+    case 1920: return radix_emu_modes<16, 12, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 2304: return radix_emu_modes<16, 12, 12>(N, lm, sm, sign, in, out, t1, t2);
+    case 3200: return radix_emu_modes<20, 16, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 3456: return radix_emu_modes<16, 18, 12>(N, lm, sm, sign, in, out, t1, t2);
+    case 3600: return radix_emu_modes<16, 15, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 3840: return radix_emu_modes<16, 16, 15>(N, lm, sm, sign, in, out, t1, t2);
     case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
     case 2000: return radix_emu_modes<20, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
     case 2592: return radix_emu_modes<18, 12, 12>(N, lm, sm, sign, in, out, t1, t2);
