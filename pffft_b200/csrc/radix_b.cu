@@ -4,8 +4,6 @@
 namespace pf {
 int radix_launch_float_a(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st);
-int radix_launch_float_c(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
-                         int device, int sm_count, cudaStream_t st);
 int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st);
 int radix_launch_float_x(int alt, int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
@@ -13,11 +11,13 @@ int radix_launch_float_x(int alt, int Nc, int lm, int sm, int sign, const float*
 bool radix_core_supported(int Nc, const char** name) {
   static const struct { int nc; const char* name; } k[] = {
       {16, "radix_4x4"}, {48, "radix_8x6"}, {80, "radix_10x8"}, {144, "radix_12x12"}, {240, "radix_16x15"}, {400, "radix_20x20"},
-      {432, "radix_24x18"}, {720, "radix_30x24"}, {1296, "radix_12x12x9"}, {2000, "radix_20x10x10"}, {2592, "radix_18x12x12"}, {4000, "radix_20x20x10"},
-      {6000, "radix_20x20x15"}, {12000, "radix_25x24x20"},
+      {432, "radix_24x18"}, {720, "radix_30x24"}, {1296, "radix_12x12x9"}, {2000, "radix_25x10x8"}, {2592, "radix_9x16x18"}, {4000, "radix_25x16x10"},
+      {6000, "radix_15x20x20"}, {12000, "radix_25x24x20"},
       {1152, "radix_12x12x8"}, {1200, "radix_12x10x10"}, {1280, "radix_16x10x8"}, {1440, "radix_12x12x10"}, {1600, "radix_16x10x10"},
       {1728, "radix_12x12x12"}, {1920, "radix_16x12x10"}, {2304, "radix_16x12x12"}, {3200, "radix_20x16x10"}, {3456, "radix_16x18x12"},
-      {3600, "radix_16x15x15"}, {3840, "radix_16x16x15"}};
+      {3600, "radix_16x15x15"}, {3840, "radix_16x16x15"}, {2160, "radix_12x12x15"}, {2400, "radix_16x15x10"}, {2880, "radix_16x15x12"},
+      {4320, "radix_16x18x15"}, {4608, "radix_16x16x18"}, {4800, "radix_16x20x15"}, {5184, "radix_16x18x18"}, {5760, "radix_16x18x20"},
+      {6400, "radix_16x20x20"}, {6912, "radix_16x18x24"}, {7200, "radix_15x20x24"}, {8000, "radix_20x20x20"}};
   for (const auto& e : k) if (e.nc == Nc) { if (name) *name = e.name; return true; }
   return false;
 }
@@ -25,23 +25,17 @@ int radix_launch_float(int Nc, int lm, int sm, int sign, const float* in, float*
                        int device, int sm_count, cudaStream_t st) {
   static const int alt = getenv("PFFFT_B200_RADIX_ALT") ? atoi(getenv("PFFFT_B200_RADIX_ALT")) : 0;      // A/B shapes (radix_x.cu)
   if (alt > 0) { const int rc = radix_launch_float_x(alt, Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st); if (rc != -2 && rc != -1) return rc; }
-  // The radix-18/20 register DFTs of these cores need ~120 registers; at two resident CTAs (72 registers) they spill
-  // 200-500 bytes per thread, at one (128 registers, radix_c.cu) they do not.  Measured (profiles/r02b_radix.md): the forward
-  // REAL transforms, which add the pair rotation on top, are 14-20 % faster without the spills (real 5184 / 8000 / 12000:
-  // 0.35 / 0.29 / 0.29 -> 0.40 / 0.34 / 0.35), the complex ones 5-15 % slower (2000c: 0.50 -> 0.42).
-  // PFFFT_B200_RADIX_MINB1=1 / =0 forces one / two CTAs for every mode.
-  static const int force = getenv("PFFFT_B200_RADIX_MINB1") ? atoi(getenv("PFFFT_B200_RADIX_MINB1")) : -1;
-  const bool big = Nc == 2000 || Nc == 2592 || Nc == 4000 || Nc == 6000;
-  const bool one_cta = force == 1 || (force < 0 && lm == L_R_TIME && Nc != 2000);
-  if (big && one_cta) return radix_launch_float_c(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+  // Stage shapes of the cores 2000 ... 6000: measured against three alternatives each (radix_x.cu, profiles/r02b_radix.md):
+  // radices and their ORDER decide how many threads a transform gets (Nc / smallest radix) and with it the register budget.
   switch (Nc) {
     case 1152: case 1200: case 1280: case 1440: case 1600: case 1728: case 1920: case 2304: case 3200: case 3456: case 3600: case 3840:
+    case 2160: case 2400: case 2880: case 4320: case 4608: case 4800: case 5184: case 5760: case 6400: case 6912: case 7200: case 8000:
       return radix_launch_float_d(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 1296:  return radix_launch_modes<12, 12, 9,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 2000:  return radix_launch_modes<20, 10, 10, 2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 2592:  return radix_launch_modes<18, 12, 12, 2, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 4000:  return radix_launch_modes<20, 20, 10, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 6000:  return radix_launch_modes<20, 20, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2000:  return radix_launch_modes<25, 10, 8,  1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2592:  return radix_launch_modes<9,  16, 18, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 4000:  return radix_launch_modes<25, 16, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 6000:  return radix_launch_modes<15, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 12000: return radix_launch_modes<25, 24, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return radix_launch_float_a(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   }

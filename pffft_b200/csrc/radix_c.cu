@@ -1,18 +1,7 @@
-// radix_c.cu -- compile-time-radix CTA kernels, the larger cores built for ONE resident CTA per SM (more registers, no spills):
-// A/B against the two-CTA builds of radix_b.cu (PFFFT_B200_RADIX_MINB1=1 selects these), see profiles/r02b_radix.md
+// radix_c.cu -- compile-time-radix CTA kernels, third translation unit: the three-stage cores 1152 ... 3840 added in round 2b
 #include "radix_impl.cuh"
 namespace pf {
-int radix_launch_float_c(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
-                         int device, int sm_count, cudaStream_t st) {
-  switch (Nc) {
-    case 2000:  return radix_launch_modes<20, 10, 10, 2, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 2592:  return radix_launch_modes<18, 12, 12, 2, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 4000:  return radix_launch_modes<20, 20, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 6000:  return radix_launch_modes<20, 20, 15, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    default: return -1;
-  }
-}
-// Cores 1152 ... 3840 that had no tuned plan (two-launch split plans at 0.30-0.33 of the roofline or the generic shared-memory
+// Cores 1152 ... 8000 that had no tuned plan (two-launch split plans at 0.30-0.33 of the roofline or the generic shared-memory
 // kernel): three stages of radices <= 16, no spills at three resident CTAs (round 2b, profiles/r02b_radix.md)
 int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st) {
@@ -30,6 +19,19 @@ int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, floa
     case 3456: return radix_launch_modes<16, 18, 12, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 3600: return radix_launch_modes<16, 15, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 3840: return radix_launch_modes<16, 16, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2160: return radix_launch_modes<12, 12, 15, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2400: return radix_launch_modes<16, 15, 10, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2880: return radix_launch_modes<16, 15, 12, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    // 4320 ... 8000: radices up to 20 / 24 (two-launch split plans before)
+    case 4320: return radix_launch_modes<16, 18, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 4608: return radix_launch_modes<16, 16, 18, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 4800: return radix_launch_modes<16, 20, 15, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 5184: return radix_launch_modes<16, 18, 18, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 5760: return radix_launch_modes<16, 18, 20, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 6400: return radix_launch_modes<16, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 6912: return radix_launch_modes<16, 18, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 7200: return radix_launch_modes<15, 20, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 8000: return radix_launch_modes<20, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return -1;
   }
 }

@@ -344,11 +344,23 @@ extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float
     case 3456: return radix_emu_modes<16, 18, 12>(N, lm, sm, sign, in, out, t1, t2);
     case 3600: return radix_emu_modes<16, 15, 15>(N, lm, sm, sign, in, out, t1, t2);
     case 3840: return radix_emu_modes<16, 16, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 2160: return radix_emu_modes<12, 12, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 2400: return radix_emu_modes<16, 15, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 2880: return radix_emu_modes<16, 15, 12>(N, lm, sm, sign, in, out, t1, t2);
+    case 4320: return radix_emu_modes<16, 18, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 4608: return radix_emu_modes<16, 16, 18>(N, lm, sm, sign, in, out, t1, t2);
+    case 4800: return radix_emu_modes<16, 20, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 5184: return radix_emu_modes<16, 18, 18>(N, lm, sm, sign, in, out, t1, t2);
+    case 5760: return radix_emu_modes<16, 18, 20>(N, lm, sm, sign, in, out, t1, t2);
+    case 6400: return radix_emu_modes<16, 20, 20>(N, lm, sm, sign, in, out, t1, t2);
+    case 6912: return radix_emu_modes<16, 18, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 7200: return radix_emu_modes<15, 20, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 8000: return radix_emu_modes<20, 20, 20>(N, lm, sm, sign, in, out, t1, t2);
     case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
-    case 2000: return radix_emu_modes<20, 10, 10>(N, lm, sm, sign, in, out, t1, t2);
-    case 2592: return radix_emu_modes<18, 12, 12>(N, lm, sm, sign, in, out, t1, t2);
-    case 4000: return radix_emu_modes<20, 20, 10>(N, lm, sm, sign, in, out, t1, t2);
-    case 6000: return radix_emu_modes<20, 20, 15>(N, lm, sm, sign, in, out, t1, t2);
+    case 2000: return radix_emu_modes<25, 10, 8>(N, lm, sm, sign, in, out, t1, t2);
+    case 2592: return radix_emu_modes<9, 16, 18>(N, lm, sm, sign, in, out, t1, t2);
+    case 4000: return radix_emu_modes<25, 16, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 6000: return radix_emu_modes<15, 20, 20>(N, lm, sm, sign, in, out, t1, t2);
     case 12000: return radix_emu_modes<25, 24, 20>(N, lm, sm, sign, in, out, t1, t2);
   }
   return -1;

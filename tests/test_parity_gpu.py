@@ -355,9 +355,11 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(800, 1) as s:
         assert s.kernel == "warp_32x25"
     with pf.Setup(4000, 1) as s:
-        assert s.kernel == "radix_20x20x10"
+        assert s.kernel == "radix_25x16x10"
     with pf.Setup(2400, 1) as s:
-        assert s.kernel == "split_3x800"
+        assert s.kernel == "radix_16x15x10"
+    with pf.Setup(9600, 1) as s:                                # no tuned one-kernel plan: decimated rows + combine
+        assert s.kernel.startswith("split_"), s.kernel
     with pf.Setup(36864, 1) as s:
         assert s.kernel == "tiled2dg_192x192"
     with pf.Setup(8192, 1) as s:
