@@ -32,6 +32,11 @@ int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, floa
     case 6912: return radix_launch_modes<16, 18, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 7200: return radix_launch_modes<15, 20, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 8000: return radix_launch_modes<20, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    // 7680 / 9216: against the one-CTA split kernels (0.31 / 0.43) and the general-radix tiled plan (0.34 / 0.36); PFFFT_B200_RADIX_BIG=0 keeps those
+    case 7680: return radix_launch_modes<16, 20, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 9216: return radix_launch_modes<16, 24, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2560: return radix_launch_modes<16, 16, 10, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 5120: return radix_launch_modes<16, 16, 20, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return -1;
   }
 }

@@ -356,6 +356,10 @@ extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float
     case 6912: return radix_emu_modes<16, 18, 24>(N, lm, sm, sign, in, out, t1, t2);
     case 7200: return radix_emu_modes<15, 20, 24>(N, lm, sm, sign, in, out, t1, t2);
     case 8000: return radix_emu_modes<20, 20, 20>(N, lm, sm, sign, in, out, t1, t2);
+    case 7680: return radix_emu_modes<16, 20, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 9216: return radix_emu_modes<16, 24, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 2560: return radix_emu_modes<16, 16, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 5120: return radix_emu_modes<16, 16, 20>(N, lm, sm, sign, in, out, t1, t2);
     case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
     case 2000: return radix_emu_modes<25, 10, 8>(N, lm, sm, sign, in, out, t1, t2);
     case 2592: return radix_emu_modes<9, 16, 18>(N, lm, sm, sign, in, out, t1, t2);

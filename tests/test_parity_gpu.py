@@ -365,7 +365,9 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(8192, 1) as s:
         assert s.kernel == "cta_split_2x4096"
     with pf.Setup(9216, 1) as s:
-        assert s.kernel == "cta_split_9x1024"
+        assert s.kernel == "radix_16x24x24"
+    with pf.Setup(6144, 1) as s:
+        assert s.kernel == "cta_split_3x2048"
     with pf.Setup(144, 1) as s:
         assert s.kernel == "radix_12x12"
     with pf.Setup(720, 1) as s:

@@ -9,8 +9,8 @@ import pytest
 from conftest import ROOT, uniform
 
 EMU = os.path.join(ROOT, "tests", "emu", "libemu.so")
-CORES = [16, 48, 80, 144, 240, 400, 432, 720, 1152, 1200, 1280, 1296, 1440, 1600, 1728, 1920, 2000, 2160, 2304, 2400, 2592, 2880, 3200,
-         3456, 3600, 3840, 4000, 4320, 4608, 4800, 5184, 5760, 6000, 6400, 6912, 7200, 8000, 12000]
+CORES = [16, 48, 80, 144, 240, 400, 432, 720, 1152, 1200, 1280, 1296, 1440, 1600, 1728, 1920, 2000, 2160, 2304, 2400, 2560, 2592, 2880, 3200,
+         3456, 3600, 3840, 4000, 4320, 4608, 4800, 5120, 5184, 5760, 6000, 6400, 6912, 7200, 7680, 8000, 9216, 12000]
 
 
 @pytest.fixture(scope="module")
