@@ -2,6 +2,7 @@
 #pragma once
 #include "engine.cuh"
 #include "cta_kernels.cuh"
+#include "radix.h"
 
 namespace pf {
 
@@ -444,20 +445,26 @@ template <typename T> struct CtaOnlyHooks {
     int R = 0, N2 = 0; bool fused = false;
     return decompose(transform == XF_REAL ? N / 2 : N, &R, &N2, &fused) ? N2 : 0;
   }
+  // double: compile-time-radix CTA kernels for the small and mixed-radix cores (radix_d.cu, round 2b)
+  static bool radix_d(int Nc) { if constexpr (sizeof(T) == 8) return radix_core_supported_double(Nc, nullptr); else return false; }
   static size_t extra_table_cpx(int N, int transform) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    if (ts_wanted_for<T>(Nc)) return 0;
+    if (ts_wanted_for<T>(Nc) || radix_d(Nc)) return 0;
     const int n2 = rows_size(N, transform);
     return n2 ? split_table_cpx(Nc, n2) : cta_table_cpx(Nc);
   }
   static void fill_extra_table(int N, int transform, T* dst) {
     const int Nc = transform == XF_REAL ? N / 2 : N;
-    if (ts_wanted_for<T>(Nc)) return;
+    if (ts_wanted_for<T>(Nc) || radix_d(Nc)) return;
     const int n2 = rows_size(N, transform);
     if (n2) split_fill_tables<T>(Nc, n2, dst); else cta_fill_tables<T>(Nc, dst);
   }
   static bool plan(Setup<T>* s) {
     if (ts_wanted_for<T>(s->Nc)) return ts_plan<T>(s);
+    if constexpr (sizeof(T) == 8) {
+      const char* nm = "";
+      if (radix_core_supported_double(s->Nc, &nm)) { s->fast_variant = 600; s->kernel_name = nm; return true; }
+    }
     int R = 0, N2 = 0; bool fused = false;
     if (decompose(s->Nc, &R, &N2, &fused)) {
       if (getenv("PFFFT_B200_NO_SPLIT")) return false;
@@ -482,6 +489,15 @@ template <typename T> struct CtaOnlyHooks {
   }
   static int run(Setup<T>* s, const T* in, T* out, long long batch, int direction, int ordered, cudaStream_t st, const XformOpts& o) {
     if (s->fast_variant == 500) return ts_dispatch<T>(s, in, out, batch, direction, ordered, st, o);
+    if constexpr (sizeof(T) == 8) {
+      if (s->fast_variant == 600) {                               // compile-time-radix CTA kernels: dense aligned batches
+        const bool plain = o.in_stride < 0 && o.out_stride < 0 && o.in_limit < 0 && o.out_count < 0;
+        if (!plain || !vec_aligned<T>(in) || !vec_aligned<T>(out)) return -1;
+        int lm = 0, sm = 0;
+        ts_modes(s->transform, direction, ordered, &lm, &sm);
+        return radix_launch_double(s->Nc, lm, sm, direction == DIR_FORWARD ? -1 : +1, in, out, batch, s->tw, s->twr, s->device, s->sm_count, st);
+      }
+    }
     const XformParams<T> p = make_params(s, in, out, batch, o);
     if (s->fast_variant >= 300)
       return run_split<T>(s, split_rows_cta<T, -1>, split_rows_cta<T, +1>, p, direction, ordered, st);

@@ -10,4 +10,8 @@ bool radix_core_supported(int Nc, const char** name);
 // tw = exp(-2 pi i k/Nc), twr = exp(-2 pi i k/(2 Nc)) for real plans.  Returns -1 when (Nc, lm, sm) is not instantiated.
 int radix_launch_float(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cpx<float>* tw,
                        const cpx<float>* twr, int device, int sm_count, cudaStream_t st);
+// double precision (radix_d.cu): the cores below 512 that the double CTA kernels (512 ... 4096) do not cover
+bool radix_core_supported_double(int Nc, const char** name);
+int radix_launch_double(int Nc, int lm, int sm, int sign, const double* in, double* out, long long batch, const cpx<double>* tw,
+                        const cpx<double>* twr, int device, int sm_count, cudaStream_t st);
 }  // namespace pf

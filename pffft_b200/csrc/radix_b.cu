@@ -33,12 +33,12 @@ int radix_launch_float(int Nc, int lm, int sm, int sign, const float* in, float*
     case 1152: case 1200: case 1280: case 1440: case 1600: case 1728: case 1920: case 2304: case 3200: case 3456: case 3600: case 3840:
     case 2160: case 2400: case 2880: case 4320: case 4608: case 4800: case 5184: case 5760: case 6400: case 6912: case 7200: case 8000: case 7680: case 9216: case 2560: case 5120:
       return radix_launch_float_d(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 1296:  return radix_launch_modes<12, 12, 9,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 2000:  return radix_launch_modes<25, 10, 8,  1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 2592:  return radix_launch_modes<9,  16, 18, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 4000:  return radix_launch_modes<25, 16, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 6000:  return radix_launch_modes<15, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    case 12000: return radix_launch_modes<25, 24, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 1296:  return radix_launch_modes<float, 12, 12, 9,  2, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2000:  return radix_launch_modes<float, 25, 10, 8,  1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2592:  return radix_launch_modes<float, 9,  16, 18, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 4000:  return radix_launch_modes<float, 25, 16, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 6000:  return radix_launch_modes<float, 15, 20, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 12000: return radix_launch_modes<float, 25, 24, 20, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return radix_launch_float_a(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   }
 }

@@ -8,11 +8,11 @@
 
 namespace pf {
 
-template <int R1, int R2, int R3, int LM, int SM, int SIGN, int TPC, int MINB>
-int radix_launch_one(const float* in, float* out, long long batch, const cf* tw, const cf* twr, int device, int sm_count, cudaStream_t st) {
+template <typename T, int R1, int R2, int R3, int LM, int SM, int SIGN, int TPC, int MINB>
+int radix_launch_one(const T* in, T* out, long long batch, const cpx<T>* tw, const cpx<T>* twr, int device, int sm_count, cudaStream_t st) {
   using S = RadixShape<R1, R2, R3>;
-  auto kern = k_cta_radix<float, R1, R2, R3, LM, SM, SIGN, TPC, MINB>;
-  constexpr size_t smem = (size_t)TPC * S::NCP * sizeof(cf);
+  auto kern = k_cta_radix<T, R1, R2, R3, LM, SM, SIGN, TPC, MINB>;
+  constexpr size_t smem = (size_t)TPC * S::NCP * sizeof(cpx<T>);
   static PerDeviceInt occ;
   int arc = 0;
   const int per_sm = occ.get(device, [&]() -> int {
@@ -33,10 +33,10 @@ int radix_launch_one(const float* in, float* out, long long batch, const cf* tw,
 }
 
 // the eight (load, store, direction) combinations of the API for one core
-template <int R1, int R2, int R3, int TPC, int MINB>
-int radix_launch_modes(int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
+template <typename T, int R1, int R2, int R3, int TPC, int MINB>
+int radix_launch_modes(int lm, int sm, int sign, const T* in, T* out, long long batch, const cpx<T>* tw, const cpx<T>* twr,
                        int device, int sm_count, cudaStream_t st) {
-#define PF_RX(L, S_, SG) if (lm == L && sm == S_ && sign == SG) return radix_launch_one<R1, R2, R3, L, S_, SG, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
+#define PF_RX(L, S_, SG) if (lm == L && sm == S_ && sign == SG) return radix_launch_one<T, R1, R2, R3, L, S_, SG, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
   PF_RX(L_C_ORD, S_C_ORD, -1) PF_RX(L_C_ORD, S_C_ORD, +1) PF_RX(L_C_ORD, S_C_Z, -1) PF_RX(L_C_Z, S_C_ORD, +1)
   PF_RX(L_R_TIME, S_R_ORD, -1) PF_RX(L_R_TIME, S_R_Z, -1) PF_RX(L_R_ORD, S_R_TIME, +1) PF_RX(L_R_Z, S_R_TIME, +1)
 #undef PF_RX

@@ -5,8 +5,8 @@
 namespace pf {
 template <int R1, int R2, int R3, int TPC, int MINB>
 static int alt2(int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr, int device, int sm_count, cudaStream_t st) {
-  if (lm == L_C_ORD && sm == S_C_ORD && sign < 0) return radix_launch_one<R1, R2, R3, L_C_ORD, S_C_ORD, -1, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
-  if (lm == L_R_TIME && sm == S_R_ORD && sign < 0) return radix_launch_one<R1, R2, R3, L_R_TIME, S_R_ORD, -1, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
+  if (lm == L_C_ORD && sm == S_C_ORD && sign < 0) return radix_launch_one<float, R1, R2, R3, L_C_ORD, S_C_ORD, -1, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
+  if (lm == L_R_TIME && sm == S_R_ORD && sign < 0) return radix_launch_one<float, R1, R2, R3, L_R_TIME, S_R_ORD, -1, TPC, MINB>(in, out, batch, tw, twr, device, sm_count, st);
   return -1;
 }
 int radix_launch_float_x(int alt, int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,

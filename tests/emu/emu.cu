@@ -312,6 +312,35 @@ static int radix_emu_modes(int N, int lm, int sm, int sign, const float* in, flo
 #undef PF_RX
   return -2;
 }
+// double-precision cores (radix_d.cu)
+template <int R1, int R2, int R3>
+static int radix_emu_modes_d(int N, int lm, int sm, int sign, const double* in, double* out, const cd* tw, const cd* twr) {
+#define PF_RX(L, S_, SG) if (lm == L && sm == S_ && sign == SG) { radix_emulate<double, R1, R2, R3, L, S_, SG>(in, out, N, tw, twr); return 0; }
+  PF_RX(L_C_ORD, S_C_ORD, -1) PF_RX(L_C_ORD, S_C_ORD, +1) PF_RX(L_C_ORD, S_C_Z, -1) PF_RX(L_C_Z, S_C_ORD, +1)
+  PF_RX(L_R_TIME, S_R_ORD, -1) PF_RX(L_R_TIME, S_R_Z, -1) PF_RX(L_R_ORD, S_R_TIME, +1) PF_RX(L_R_Z, S_R_TIME, +1)
+#undef PF_RX
+  return -2;
+}
+extern "C" int emu_radix_d(int N, int transform, int dir, int ordered, const double* in, double* out) {
+  const int Nc = transform == 0 ? N / 2 : N;
+  std::vector<double> tw(2 * (size_t)Nc), twr(2 * (size_t)(N / 2));
+  pfplan::fill_roots<double>(tw.data(), Nc, Nc);
+  pfplan::fill_roots<double>(twr.data(), N / 2, N);
+  const cd* t1 = reinterpret_cast<const cd*>(tw.data()); const cd* t2 = reinterpret_cast<const cd*>(twr.data());
+  int lm, sm; const bool fwd = dir == 0;
+  if (transform == 1) { lm = (fwd || ordered) ? L_C_ORD : L_C_Z; sm = (fwd && !ordered) ? S_C_Z : S_C_ORD; }
+  else if (fwd) { lm = L_R_TIME; sm = ordered ? S_R_ORD : S_R_Z; }
+  else { lm = ordered ? L_R_ORD : L_R_Z; sm = S_R_TIME; }
+  const int sign = fwd ? -1 : +1;
+  switch (Nc) {
+#define D(nc, r1, r2, r3) case nc: return radix_emu_modes_d<r1, r2, r3>(N, lm, sm, sign, in, out, t1, t2);
+    D(16, 4, 4, 1) D(32, 8, 4, 1) D(48, 8, 6, 1) D(64, 8, 8, 1) D(80, 10, 8, 1) D(96, 12, 8, 1) D(128, 8, 4, 4) D(144, 12, 12, 1)
+    D(160, 8, 5, 4) D(192, 8, 6, 4) D(240, 8, 6, 5) D(256, 8, 8, 4) D(288, 8, 6, 6) D(320, 8, 8, 5) D(384, 8, 8, 6) D(400, 10, 10, 4)
+    D(432, 9, 8, 6) D(480, 10, 8, 6) D(1296, 12, 12, 9) D(2000, 10, 20, 10)
+#undef D
+  }
+  return -1;
+}
 extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float* in, float* out) {
   const int Nc = transform == 0 ? N / 2 : N;
   std::vector<float> tw(2 * (size_t)Nc), twr(2 * (size_t)(N / 2));
