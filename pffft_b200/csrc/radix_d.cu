@@ -10,8 +10,13 @@ const struct { int nc; const char* name; } kCoresD[] = {
     {16, "radix_4x4"}, {32, "radix_8x4"}, {48, "radix_8x6"}, {64, "radix_8x8"}, {80, "radix_10x8"}, {96, "radix_12x8"},
     {128, "radix_8x4x4"}, {144, "radix_12x12"}, {160, "radix_8x5x4"}, {192, "radix_8x6x4"}, {240, "radix_8x6x5"},
     {256, "radix_8x8x4"}, {288, "radix_8x6x6"}, {320, "radix_8x8x5"}, {384, "radix_8x8x6"}, {400, "radix_10x10x4"},
-    {432, "radix_9x8x6"}, {480, "radix_10x8x6"}, {1296, "radix_12x12x9"}, {2000, "radix_10x20x10"}};
+    {432, "radix_9x8x6"}, {480, "radix_10x8x6"}, {1296, "radix_12x12x9"}, {2000, "radix_10x20x10"},
+    {576, "radix_9x8x8"}, {640, "radix_10x8x8"}, {720, "radix_10x9x8"}, {768, "radix_12x8x8"}, {800, "radix_10x10x8"}, {864, "radix_12x9x8"},
+    {960, "radix_12x10x8"}, {1152, "radix_12x12x8"}, {1200, "radix_12x10x10"}, {1280, "radix_16x10x8"}, {1440, "radix_12x12x10"},
+    {1600, "radix_16x10x10"}, {1728, "radix_12x12x12"}, {1920, "radix_16x12x10"}};
 }
+int radix_launch_double_e(int Nc, int lm, int sm, int sign, const double* in, double* out, long long batch, const cd* tw, const cd* twr,
+                          int device, int sm_count, cudaStream_t st);
 bool radix_core_supported_double(int Nc, const char** name) {
   static const bool on = !(getenv("PFFFT_B200_RADIX_D") && atoi(getenv("PFFFT_B200_RADIX_D")) == 0);
   if (!on) return false;
@@ -42,7 +47,7 @@ int radix_launch_double(int Nc, int lm, int sm, int sign, const double* in, doub
     case 480:  return radix_launch_modes<double, 10, 8,  6, 3,  2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 1296: return radix_launch_modes<double, 12, 12, 9, 1,  3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 2000: return radix_launch_modes<double, 10, 20, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
-    default: return -1;
+    default: return radix_launch_double_e(Nc, lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
   }
 }
 }  // namespace pf

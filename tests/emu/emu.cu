@@ -337,6 +337,8 @@ extern "C" int emu_radix_d(int N, int transform, int dir, int ordered, const dou
     D(16, 4, 4, 1) D(32, 8, 4, 1) D(48, 8, 6, 1) D(64, 8, 8, 1) D(80, 10, 8, 1) D(96, 12, 8, 1) D(128, 8, 4, 4) D(144, 12, 12, 1)
     D(160, 8, 5, 4) D(192, 8, 6, 4) D(240, 8, 6, 5) D(256, 8, 8, 4) D(288, 8, 6, 6) D(320, 8, 8, 5) D(384, 8, 8, 6) D(400, 10, 10, 4)
     D(432, 9, 8, 6) D(480, 10, 8, 6) D(1296, 12, 12, 9) D(2000, 10, 20, 10)
+    D(576, 9, 8, 8) D(640, 10, 8, 8) D(720, 10, 9, 8) D(768, 12, 8, 8) D(800, 10, 10, 8) D(864, 12, 9, 8) D(960, 12, 10, 8)
+    D(1152, 12, 12, 8) D(1200, 12, 10, 10) D(1280, 16, 10, 8) D(1440, 12, 12, 10) D(1600, 16, 10, 10) D(1728, 12, 12, 12) D(1920, 16, 12, 10)
 #undef D
   }
   return -1;

@@ -372,7 +372,9 @@ def test_kernel_selection_reports_tuned_kernel(pf):
         assert s.kernel == "radix_12x12"
     with pf.Setup(720, 1) as s:
         assert s.kernel == "radix_30x24"
-    with pf.Setup(96, 1, np.float64) as s:                      # doubles outside the tuned sizes: the generic kernel
+    with pf.Setup(96, 1, np.float64) as s:                      # double-precision radix cores (round 2b)
+        assert s.kernel == "radix_12x8"
+    with pf.Setup(4800, 1, np.float64) as s:                    # doubles outside the tuned sizes: the generic kernel
         assert s.kernel == "smem_stockham"
     with pf.Setup(65536, 1) as s:
         assert s.kernel == "tiled2dg_256x256"

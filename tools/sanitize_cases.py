@@ -22,7 +22,9 @@ for N, tr in [(1024, 1), (64, 1), (256, 1), (32, 1), (512, 1), (2048, 1), (4096,
               (16, 1), (96, 1), (160, 0), (480, 1), (8192, 1), (16384, 0), (12000, 1),
               (64, 0), (192, 0), (512, 0), (960, 0), (1920, 0), (800, 1), (128, 1), (48, 1), (4000, 1)]:
     run(N, tr)
-for N, tr in [(1024, 1), (4096, 0), (96, 1), (8192, 1)]:
+for N, tr in [(720, 1), (1440, 0), (2400, 1), (4608, 1), (7680, 1), (9216, 0), (2592, 1), (8000, 0), (432, 1), (160, 0)]:   # radix family, round 2b
+    run(N, tr)
+for N, tr in [(1024, 1), (4096, 0), (96, 1), (8192, 1), (48, 1), (384, 1), (800, 0), (2592, 0), (2000, 1)]:
     run(N, tr, np.float64, 3)
 # overlap-save: fused (Nfft 1024, 8192) and three-launch (Nfft 256, 16384) paths, tail block, complex modes
 for taps, bl, n in [(100, 1024, 5000), (4097, 0, 40000), (31, 0, 3000), (200, 16384, 70000)]:
