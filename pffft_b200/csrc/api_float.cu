@@ -67,6 +67,8 @@ static bool float_split_for(int N, int transform, int* R, int* N2) {
 // ---- compile-time-radix CTA kernels (radix_kernels.cuh): cores that are neither 32*R2 nor 256*C.  PFFFT_B200_RADIX=0 off.
 static bool radix_wanted(int Nc) {
   static const int mode = getenv("PFFFT_B200_RADIX") ? atoi(getenv("PFFFT_B200_RADIX")) : 1;   // default on (profiles/r02_radix.md)
+  // an explicit request for another plan of the same core wins over the default (7680, 9216 have a tiled plan and a one-CTA split plan)
+  if (const char* e = getenv("PFFFT_B200_TILED2D_GENERAL")) { int a1, a2; if (atoi(e) != 0 && t2dg_shape_for(Nc, &a1, &a2)) return false; }
   return mode != 0 && radix_core_supported(Nc, nullptr);
 }
 
