@@ -16,6 +16,9 @@
 // Replaces, for these sizes, passf2/3/4/5_ps + cplx_finalize (complex) and radf*/radb* + real_finalize/preprocess (real)
 // of the reference (src/pffft_priv_impl.h:122-807, :1195-1462).
 #pragma once
+#ifndef RADIX_NO_PAIRS
+#define RADIX_NO_PAIRS 0                                          // 1: forward real through the natural-order copy + pairing pass (round 2)
+#endif
 #include "butterfly.cuh"
 #include "generic_kernels.cuh"
 #include "cta_kernels.cuh"   // store_elem, ldtab
@@ -120,6 +123,38 @@ PF_HD void radix_emit(int b, const cpx<T> (&v)[RL], T* obase, int N, cpx<T>* nat
   }
 }
 
+// ---- forward real, last stage on PAIRS of butterflies (round 2b).  Thread p <= M/2 runs the butterflies b = p and M - p: the
+// outputs of the second one, X[(M-p) + M k], are exactly the mirror bins Nc - (p + M k') of the first (k' = R-1-k), so the real
+// post-rotation happens in registers and both halves of every pair go straight to global memory -- no natural-order copy in
+// shared memory, no pairing pass, two barriers less.  p = 0 and p = M/2 pair inside their own butterfly.  Used when the last
+// radix is <= 16 (two butterflies = 4 R registers of data).  PADDED: the stage-1 layout (two-stage plans read it).
+template <typename T, int R, int M, int NC, int SM, bool PADDED, int R1>
+PF_HD void radix_last_pairs(int p, const cpx<T>* buf, T* obase, int N, const cpx<T>* twr) {
+  if (2 * p > M) return;
+  const int b2 = (p == 0) ? 0 : M - p;
+  auto rd = [&](int n) { return PADDED ? buf[n + n / R1] : buf[n]; };
+  cpx<T> v1[R], v2[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) { v1[j] = rd(p + j * M); v2[j] = rd(b2 + j * M); }
+  dft_small<R, -1>(v1);
+  if (p == 0) {                                                  // n = M k  <->  M (R - k)
+    spec_put<SM == S_R_Z, true>(obase, 0, N, mk<T>(v1[0].x + v1[0].y, v1[0].x - v1[0].y));          // (DC, Nyquist)
+    if (R % 2 == 0) spec_put<SM == S_R_Z, true>(obase, NC / 2, N, mk<T>(v1[R / 2].x, -v1[R / 2].y));   // X[Nc/2] = conj Z[Nc/2]
+#pragma unroll
+    for (int k = 1; 2 * k < R; ++k) real_post_regs<SM, T>(obase, M * k, NC, N, v1[k], v1[R - k], twr);
+    return;
+  }
+  if (2 * p == M) {                                              // n = M/2 + M k  <->  M/2 + M (R-1-k)
+#pragma unroll
+    for (int k = 0; 2 * k < R - 1; ++k) real_post_regs<SM, T>(obase, p + M * k, NC, N, v1[k], v1[R - 1 - k], twr);
+    if (R % 2 == 1) { const int k = (R - 1) / 2; spec_put<SM == S_R_Z, true>(obase, p + M * k, N, mk<T>(v1[k].x, -v1[k].y)); }   // self-paired: n = Nc/2
+    return;
+  }
+  dft_small<R, -1>(v2);
+#pragma unroll
+  for (int k = 0; k < R; ++k) real_post_regs<SM, T>(obase, p + M * k, NC, N, v1[k], v2[R - 1 - k], twr);
+}
+
 #ifdef __CUDACC__
 // TPC transforms per CTA iteration, TT threads each (blockDim.x = TPC * TT)
 template <typename T, int R1, int R2, int R3, int LM, int SM, int SIGN, int TPC, int MINB>
@@ -130,6 +165,9 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
   constexpr bool kReal = (LM == L_R_TIME || LM == L_R_ORD || LM == L_R_Z);
   constexpr int N = kReal ? 2 * S::NC : S::NC;
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
+  // forward real with a last radix <= 16: the pair rotation runs in registers (radix_last_pairs)
+  constexpr int kRL = S::STAGES == 3 ? R3 : R2;
+  constexpr bool kPairs = partner && S::STAGES >= 2 && kRL <= 16 && SIGN < 0 && !RADIX_NO_PAIRS;
   const int tid = threadIdx.x;
   const int tl = tid / S::TT;
   int li = tid - tl * S::TT;
@@ -152,6 +190,9 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
     if (live) radix_stage1_store<T, R1, R2, R3, SIGN>(li, v1, tw, buf);
     if (S::STAGES == 1) {
       if (live) radix_emit<T, R1, S::M1, SM>(li, v1, obase, N, buf);
+    } else if (S::STAGES == 2 && kPairs) {
+      __syncthreads();
+      if (live) radix_last_pairs<T, R2, S::M2, S::NC, SM, true, R1>(li, buf, obase, N, twr);
     } else if (S::STAGES == 2) {
       __syncthreads();
       cpx<T> a[R2];
@@ -167,12 +208,16 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
         if (live) radix_stage2_write<T, R1, R2, R3, SIGN>(li, a, tw, buf);
       }
       __syncthreads();
-      cpx<T> c[R3];
-      if (live) radix_stage3_read<T, R1, R2, R3>(li, buf, c);
-      if (partner) __syncthreads();
-      if (live && li < S::M3) { dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, obase, N, buf); }
+      if (kPairs) {
+        if (live) radix_last_pairs<T, R3, S::M3, S::NC, SM, false, R1>(li, buf, obase, N, twr);
+      } else {
+        cpx<T> c[R3];
+        if (live) radix_stage3_read<T, R1, R2, R3>(li, buf, c);
+        if (partner) __syncthreads();
+        if (live && li < S::M3) { dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, obase, N, buf); }
+      }
     }
-    if (partner) {
+    if (partner && !kPairs) {
       __syncthreads();
       // bins k and Nc-k share their sum, difference and twiddle: one pass over half the spectrum (k = 0 also emits Nc/2)
       if (live) for (int k = li; k < S::NC / 2; k += S::TT) real_post_pair<SM, T>(obase, buf, k, N, S::NC, twr);

@@ -289,7 +289,13 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
     radix_stage1_store<T, R1, R2, R3, SIGN>(li, a, tw, buf.data());
     if (S::STAGES == 1) radix_emit<T, R1, S::M1, SM>(li, a, o.data(), N, buf.data());
   }
-  if (S::STAGES == 2) {
+  // forward real with a last radix <= 16: pair rotation in registers (radix_last_pairs), as in the kernel
+  constexpr int kRL = S::STAGES == 3 ? R3 : R2;
+  constexpr bool kPairs = partner && S::STAGES >= 2 && kRL <= 16 && SIGN < 0;
+  if (kPairs) for (auto& e : o) e = (T)NAN;
+  if (S::STAGES == 2 && kPairs) {
+    for (int li = 0; li < S::TT; ++li) radix_last_pairs<T, R2, S::M2, S::NC, SM, true, R1>(li, buf.data(), o.data(), N, twr);
+  } else if (S::STAGES == 2) {
     std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
     for (int li = 0; li < S::M2; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; dft_small<R2, SIGN>(a); radix_emit<T, R2, S::M2, SM>(li, a, o.data(), N, buf.data()); }
@@ -297,11 +303,15 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
     std::vector<std::vector<cpx<T>>> regs(S::TT, std::vector<cpx<T>>(R2));
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; radix_stage2_read<T, R1, R2, R3>(li, buf.data(), a); for (int j = 0; j < R2; ++j) regs[li][j] = a[j]; }
     for (int li = 0; li < S::TT; ++li) { cpx<T> a[R2]; for (int j = 0; j < R2; ++j) a[j] = regs[li][j]; radix_stage2_write<T, R1, R2, R3, SIGN>(li, a, tw, buf.data()); }
+    if (kPairs) {
+      for (int li = 0; li < S::TT; ++li) radix_last_pairs<T, R3, S::M3, S::NC, SM, false, R1>(li, buf.data(), o.data(), N, twr);
+    } else {
     std::vector<std::vector<cpx<T>>> r3(S::TT, std::vector<cpx<T>>(R3));
     for (int li = 0; li < S::TT; ++li) { cpx<T> c[R3]; radix_stage3_read<T, R1, R2, R3>(li, buf.data(), c); for (int j = 0; j < R3; ++j) r3[li][j] = c[j]; }
     for (int li = 0; li < S::M3; ++li) { cpx<T> c[R3]; for (int j = 0; j < R3; ++j) c[j] = r3[li][j]; dft_small<R3, SIGN>(c); radix_emit<T, R3, S::M3, SM>(li, c, o.data(), N, buf.data()); }
+    }
   }
-  if (partner) for (int k = 0; k < S::NC / 2; ++k) real_post_pair<SM, T>(o.data(), buf.data(), k, N, S::NC, twr);
+  if (partner && !kPairs) for (int k = 0; k < S::NC / 2; ++k) real_post_pair<SM, T>(o.data(), buf.data(), k, N, S::NC, twr);
   memcpy(out, o.data(), sizeof(T) * 2 * (size_t)S::NC);
 }
 template <int R1, int R2, int R3>
