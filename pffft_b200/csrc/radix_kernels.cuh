@@ -155,6 +155,12 @@ PF_HD void radix_last_pairs(int p, const cpx<T>* buf, T* obase, int N, const cpx
   for (int k = 0; k < R; ++k) real_post_regs<SM, T>(obase, p + M * k, NC, N, v1[k], v2[R - 1 - k], twr);
 }
 
+// which (core, mode) takes the pair form (kernel and CPU stepping harness agree through this one function)
+template <typename T, int R1, int R2, int R3, int SM, int SIGN> PF_HD constexpr bool radix_pairs_wanted() {
+  return (SM == S_R_ORD || SM == S_R_Z) && SIGN < 0 && R3 > 1 && R3 <= 16 && !RADIX_NO_PAIRS &&
+         R1 * R2 * R3 >= (sizeof(T) == 8 ? 256 : 1024);
+}
+
 #ifdef __CUDACC__
 // TPC transforms per CTA iteration, TT threads each (blockDim.x = TPC * TT)
 template <typename T, int R1, int R2, int R3, int LM, int SM, int SIGN, int TPC, int MINB>
@@ -165,9 +171,10 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
   constexpr bool kReal = (LM == L_R_TIME || LM == L_R_ORD || LM == L_R_Z);
   constexpr int N = kReal ? 2 * S::NC : S::NC;
   constexpr bool partner = (SM == S_R_ORD || SM == S_R_Z);
-  // forward real with a last radix <= 16: the pair rotation runs in registers (radix_last_pairs)
-  constexpr int kRL = S::STAGES == 3 ? R3 : R2;
-  constexpr bool kPairs = partner && S::STAGES >= 2 && kRL <= 16 && SIGN < 0 && !RADIX_NO_PAIRS;
+  // forward real, three-stage cores with a last radix <= 16: the pair rotation runs in registers (radix_last_pairs).
+  // Measured (profiles/r02b_radix.md): real 4608 ... 20480: +3 ... +30 % (5120: 0.42 -> 0.53, 9600: 0.36 -> 0.47); the small
+  // two-stage cores LOSE 17-20 % (real 96: 0.54 -> 0.43: half of very few threads idle in the last stage) and keep the pairing pass.
+  constexpr bool kPairs = radix_pairs_wanted<T, R1, R2, R3, SM, SIGN>();
   const int tid = threadIdx.x;
   const int tl = tid / S::TT;
   int li = tid - tl * S::TT;

@@ -290,8 +290,7 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
     if (S::STAGES == 1) radix_emit<T, R1, S::M1, SM>(li, a, o.data(), N, buf.data());
   }
   // forward real with a last radix <= 16: pair rotation in registers (radix_last_pairs), as in the kernel
-  constexpr int kRL = S::STAGES == 3 ? R3 : R2;
-  constexpr bool kPairs = partner && S::STAGES >= 2 && kRL <= 16 && SIGN < 0;
+  constexpr bool kPairs = radix_pairs_wanted<T, R1, R2, R3, SM, SIGN>();
   if (kPairs) for (auto& e : o) e = (T)NAN;
   if (S::STAGES == 2 && kPairs) {
     for (int li = 0; li < S::TT; ++li) radix_last_pairs<T, R2, S::M2, S::NC, SM, true, R1>(li, buf.data(), o.data(), N, twr);
