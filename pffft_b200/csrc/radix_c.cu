@@ -1,7 +1,7 @@
 // radix_c.cu -- compile-time-radix CTA kernels, third translation unit: the three-stage cores 1152 ... 3840 added in round 2b
 #include "radix_impl.cuh"
 namespace pf {
-// Cores 1152 ... 8000 that had no tuned plan (two-launch split plans at 0.30-0.33 of the roofline or the generic shared-memory
+// Cores 1152 ... 14400 that had no tuned plan (two-launch split plans at 0.30-0.33 of the roofline or the generic shared-memory
 // kernel): three stages of radices <= 16, no spills at three resident CTAs (round 2b, profiles/r02b_radix.md)
 int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, float* out, long long batch, const cf* tw, const cf* twr,
                          int device, int sm_count, cudaStream_t st) {
@@ -35,6 +35,13 @@ int radix_launch_float_d(int Nc, int lm, int sm, int sign, const float* in, floa
     // 7680 / 9216: against the one-CTA split kernels (0.31 / 0.43) and the general-radix tiled plan (0.34 / 0.36); PFFFT_B200_RADIX_BIG=0 keeps those
     case 7680: return radix_launch_modes<float, 16, 20, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 9216: return radix_launch_modes<float, 16, 24, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    // 9600 ... 14400 (one CTA per SM, radices up to 30; two-launch split plans before)
+    case 9600:  return radix_launch_modes<float, 20, 20, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 10800: return radix_launch_modes<float, 18, 20, 30, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 11520: return radix_launch_modes<float, 20, 24, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 12960: return radix_launch_modes<float, 18, 24, 30, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 13824: return radix_launch_modes<float, 24, 24, 24, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 14400: return radix_launch_modes<float, 24, 24, 25, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 2560: return radix_launch_modes<float, 16, 16, 10, 1, 3>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 5120: return radix_launch_modes<float, 16, 16, 20, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return -1;

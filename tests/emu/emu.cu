@@ -399,6 +399,12 @@ extern "C" int emu_radix(int N, int transform, int dir, int ordered, const float
     case 7680: return radix_emu_modes<16, 20, 24>(N, lm, sm, sign, in, out, t1, t2);
     case 9216: return radix_emu_modes<16, 24, 24>(N, lm, sm, sign, in, out, t1, t2);
     case 2560: return radix_emu_modes<16, 16, 10>(N, lm, sm, sign, in, out, t1, t2);
+    case 9600: return radix_emu_modes<20, 20, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 10800: return radix_emu_modes<18, 20, 30>(N, lm, sm, sign, in, out, t1, t2);
+    case 11520: return radix_emu_modes<20, 24, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 12960: return radix_emu_modes<18, 24, 30>(N, lm, sm, sign, in, out, t1, t2);
+    case 13824: return radix_emu_modes<24, 24, 24>(N, lm, sm, sign, in, out, t1, t2);
+    case 14400: return radix_emu_modes<24, 24, 25>(N, lm, sm, sign, in, out, t1, t2);
     case 5120: return radix_emu_modes<16, 16, 20>(N, lm, sm, sign, in, out, t1, t2);
     case 1296: return radix_emu_modes<12, 12, 9>(N, lm, sm, sign, in, out, t1, t2);
     case 2000: return radix_emu_modes<25, 10, 8>(N, lm, sm, sign, in, out, t1, t2);

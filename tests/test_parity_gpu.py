@@ -358,7 +358,7 @@ def test_kernel_selection_reports_tuned_kernel(pf):
         assert s.kernel == "radix_25x16x10"
     with pf.Setup(2400, 1) as s:
         assert s.kernel == "radix_16x15x10"
-    with pf.Setup(9600, 1) as s:                                # no tuned one-kernel plan: decimated rows + combine
+    with pf.Setup(15360, 1) as s:                               # no tuned one-kernel plan: decimated rows + combine
         assert s.kernel.startswith("split_"), s.kernel
     with pf.Setup(36864, 1) as s:
         assert s.kernel == "tiled2dg_192x192"

@@ -7,7 +7,7 @@ from conftest import uniform
 
 pytestmark = pytest.mark.gpu
 CORES = [16, 48, 80, 144, 240, 400, 432, 720, 1152, 1200, 1280, 1296, 1440, 1600, 1728, 1920, 2000, 2160, 2304, 2400, 2560, 2592, 2880, 3200,
-         3456, 3600, 3840, 4000, 4320, 4608, 4800, 5120, 5184, 5760, 6000, 6400, 6912, 7200, 7680, 8000, 9216, 12000]
+         3456, 3600, 3840, 4000, 4320, 4608, 4800, 5120, 5184, 5760, 6000, 6400, 6912, 7200, 7680, 8000, 9216, 9600, 10800, 11520, 12000, 12960, 13824, 14400]
 
 
 @pytest.fixture()
