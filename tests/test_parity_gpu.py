@@ -17,7 +17,8 @@ TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 # bench_pffft.c:445 validation sizes + the power-of-two ladder of tests/test_pffft.c:333
 POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144]
 NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864,
-           1536, 2560, 3072, 5120, 6144, 7680, 9216, 10240, 12288]     # two-level plans that run as one kernel
+           1536, 2560, 3072, 5120, 6144, 7680, 9216, 10240, 12288,     # two-level plans that run as one kernel
+           15360, 18432, 23040, 30720, 57600]                           # pipeline instead of two launches (round 2b)
 
 
 def torch_mod():
@@ -358,8 +359,10 @@ def test_kernel_selection_reports_tuned_kernel(pf):
         assert s.kernel == "radix_25x16x10"
     with pf.Setup(2400, 1) as s:
         assert s.kernel == "radix_16x15x10"
-    with pf.Setup(15360, 1) as s:                               # no tuned one-kernel plan: decimated rows + combine
-        assert s.kernel.startswith("split_"), s.kernel
+    with pf.Setup(15360, 1) as s:                               # no tiled plan of its own: the pipeline (round 2b; was split_15x1024)
+        assert s.kernel == "ts_240x64", s.kernel
+    with pf.Setup(17280, 1) as s:                               # not factorisable into radices 16*A either
+        assert s.kernel.startswith("split_") or s.kernel == "global_stockham", s.kernel
     with pf.Setup(36864, 1) as s:
         assert s.kernel == "tiled2dg_192x192"
     with pf.Setup(8192, 1) as s:
