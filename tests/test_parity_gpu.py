@@ -360,7 +360,7 @@ def test_kernel_selection_reports_tuned_kernel(pf):
     with pf.Setup(2400, 1) as s:
         assert s.kernel == "radix_16x15x10"
     with pf.Setup(15360, 1) as s:                               # no tiled plan of its own: the pipeline (round 2b; was split_15x1024)
-        assert s.kernel == "ts_240x64", s.kernel
+        assert s.kernel == "ts_160x96", s.kernel
     with pf.Setup(17280, 1) as s:                               # not factorisable into radices 16*A either
         assert s.kernel.startswith("split_") or s.kernel == "global_stockham", s.kernel
     with pf.Setup(36864, 1) as s:
