@@ -155,6 +155,49 @@ PF_HD void radix_last_pairs(int p, const cpx<T>* buf, T* obase, int N, const cpx
   for (int k = 0; k < R; ++k) real_post_regs<SM, T>(obase, p + M * k, NC, N, v1[k], v2[R - 1 - k], twr);
 }
 
+// ---- backward real, FIRST stage on pairs of butterflies: the mirror image of radix_last_pairs.  Thread p <= M1/2 loads the inputs
+// of the butterflies b = p and M1 - p straight from the spectrum: element j of the second is the mirror bin of element
+// R1-1-j of the first, so the pre-rotation (real_pre_regs, cta_kernels.cuh) runs in registers -- no natural-order copy of the
+// rebuilt half-length spectrum in shared memory, two barriers less.  Then both butterflies take the ordinary stage-1 path.
+template <typename T, int R1, int R2, int R3, int LM>
+PF_HD void radix_first_pairs(int p, const T* ibase, int N, const cpx<T>* twr, const cpx<T>* tw, cpx<T>* buf) {
+  using S = RadixShape<R1, R2, R3>;
+  constexpr int M = S::M1, NC = S::NC;
+  constexpr bool Z = (LM == L_R_Z);
+  if (2 * p > M) return;
+  const int b2 = (p == 0) ? 0 : M - p;
+  cpx<T> x1[R1], z1[R1];
+#pragma unroll
+  for (int j = 0; j < R1; ++j) x1[j] = spec_get<Z, true>(ibase, p + j * M, N);
+  if (p == 0) {                                                  // k = M j  <->  M (R1 - j)
+    z1[0] = mk<T>(x1[0].x + x1[0].y, x1[0].x - x1[0].y);        // slot 0 = (DC, Nyquist)
+    if (R1 % 2 == 0) z1[R1 / 2] = scale(conj(x1[R1 / 2]), T(2));   // Z'[Nc/2] = 2 conj X[Nc/2]
+#pragma unroll
+    for (int j = 1; 2 * j < R1; ++j) real_pre_regs<T>(x1[j], x1[R1 - j], ldtab(twr + M * j), &z1[j], &z1[R1 - j]);
+    radix_stage1_store<T, R1, R2, R3, +1>(0, z1, tw, buf);
+    return;
+  }
+  if (2 * p == M) {                                              // k = M/2 + M j  <->  M/2 + M (R1-1-j)
+#pragma unroll
+    for (int j = 0; 2 * j < R1 - 1; ++j) real_pre_regs<T>(x1[j], x1[R1 - 1 - j], ldtab(twr + p + M * j), &z1[j], &z1[R1 - 1 - j]);
+    if (R1 % 2 == 1) z1[(R1 - 1) / 2] = scale(conj(x1[(R1 - 1) / 2]), T(2));     // self-paired: k = Nc/2
+    radix_stage1_store<T, R1, R2, R3, +1>(p, z1, tw, buf);
+    return;
+  }
+  cpx<T> x2[R1], z2[R1];
+#pragma unroll
+  for (int j = 0; j < R1; ++j) x2[j] = spec_get<Z, true>(ibase, b2 + j * M, N);
+#pragma unroll
+  for (int j = 0; j < R1; ++j) real_pre_regs<T>(x1[j], x2[R1 - 1 - j], ldtab(twr + p + M * j), &z1[j], &z2[R1 - 1 - j]);
+  radix_stage1_store<T, R1, R2, R3, +1>(p, z1, tw, buf);
+  radix_stage1_store<T, R1, R2, R3, +1>(b2, z2, tw, buf);
+  (void)NC;
+}
+template <typename T, int R1, int R2, int R3, int LM, int SIGN> PF_HD constexpr bool radix_pairs_in_wanted() {
+  return (LM == L_R_ORD || LM == L_R_Z) && SIGN > 0 && R3 > 1 && R1 <= 16 && !RADIX_NO_PAIRS &&
+         R1 * R2 * R3 >= (sizeof(T) == 8 ? 256 : 1024);
+}
+
 // which (core, mode) takes the pair form (kernel and CPU stepping harness agree through this one function)
 template <typename T, int R1, int R2, int R3, int SM, int SIGN> PF_HD constexpr bool radix_pairs_wanted() {
   return (SM == S_R_ORD || SM == S_R_Z) && SIGN < 0 && R3 > 1 && R3 <= 16 && !RADIX_NO_PAIRS &&
@@ -186,7 +229,10 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
     T* obase = out + (t0 + tl) * (2LL * S::NC);
     constexpr bool prerot = (LM == L_R_ORD || LM == L_R_Z);       // backward real: pair-wise pre-rotation through `buf`
     cpx<T> v1[R1];
-    if (prerot) {
+    constexpr bool kPairsIn = radix_pairs_in_wanted<T, R1, R2, R3, LM, SIGN>();
+    if (kPairsIn) {                                               // backward real, large three-stage cores: pre-rotation in registers
+      if (live) radix_first_pairs<T, R1, R2, R3, LM>(li, ibase, N, twr, tw, buf);
+    } else if (prerot) {
       if (live) radix_prerotate<T, LM>(li, S::TT, ibase, N, S::NC, twr, buf);
       __syncthreads();
       if (live) radix_stage1_load<T, R1, R2, R3, LM, true>(li, ibase, N, twr, buf, v1);
@@ -194,7 +240,7 @@ k_cta_radix(const T* __restrict__ in, T* __restrict__ out, long long batch, cons
     } else if (live) {
       radix_stage1_load<T, R1, R2, R3, LM, false>(li, ibase, N, twr, buf, v1);
     }
-    if (live) radix_stage1_store<T, R1, R2, R3, SIGN>(li, v1, tw, buf);
+    if (live && !kPairsIn) radix_stage1_store<T, R1, R2, R3, SIGN>(li, v1, tw, buf);
     if (S::STAGES == 1) {
       if (live) radix_emit<T, R1, S::M1, SM>(li, v1, obase, N, buf);
     } else if (S::STAGES == 2 && kPairs) {

@@ -275,6 +275,11 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
   std::vector<cpx<T>> buf(S::NCP);
   std::vector<T> o(2 * (size_t)S::NC);
   constexpr bool prerot = (LM == L_R_ORD || LM == L_R_Z);
+  constexpr bool kPairsIn = radix_pairs_in_wanted<T, R1, R2, R3, LM, SIGN>();
+  if (kPairsIn) {                                                // backward real: pre-rotation in registers, as in the kernel
+    for (auto& e : buf) { e.x = (T)NAN; e.y = (T)NAN; }
+    for (int li = 0; li < S::TT; ++li) radix_first_pairs<T, R1, R2, R3, LM>(li, in, N, twr, tw, buf.data());
+  } else {
   if (prerot) for (int li = 0; li < S::TT; ++li) radix_prerotate<T, LM>(li, S::TT, in, N, S::NC, twr, buf.data());
   std::vector<std::vector<cpx<T>>> r1(S::TT, std::vector<cpx<T>>(R1));
   for (int li = 0; li < S::TT; ++li) {
@@ -288,6 +293,7 @@ static void radix_emulate(const T* in, T* out, int N, const cpx<T>* tw, const cp
     for (int j = 0; j < R1; ++j) a[j] = r1[li][j];
     radix_stage1_store<T, R1, R2, R3, SIGN>(li, a, tw, buf.data());
     if (S::STAGES == 1) radix_emit<T, R1, S::M1, SM>(li, a, o.data(), N, buf.data());
+  }
   }
   // forward real with a last radix <= 16: pair rotation in registers (radix_last_pairs), as in the kernel
   constexpr bool kPairs = radix_pairs_wanted<T, R1, R2, R3, SM, SIGN>();
