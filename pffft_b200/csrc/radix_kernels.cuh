@@ -193,9 +193,13 @@ PF_HD void radix_first_pairs(int p, const T* ibase, int N, const cpx<T>* twr, co
   radix_stage1_store<T, R1, R2, R3, +1>(b2, z2, tw, buf);
   (void)NC;
 }
+// Measured against a -DRADIX_NO_PAIRS=1 build (profiles/r02b_radix.md): +7 ... +17 % for a first radix <= 10 (real 5184: 0.35 ->
+// 0.41) and for the float cores from 3840 points (real 7680 / 9600 / 10240: 0.33 / 0.30 / 0.34 -> 0.38 / 0.32 / 0.37); with a
+// radix-16 first stage on the smaller cores (two butterflies = 64 registers of data, half the threads loading) and in double
+// precision it LOSES 10-30 % -- those keep the pre-rotation pass through shared memory.
 template <typename T, int R1, int R2, int R3, int LM, int SIGN> PF_HD constexpr bool radix_pairs_in_wanted() {
-  return (LM == L_R_ORD || LM == L_R_Z) && SIGN > 0 && R3 > 1 && R1 <= 16 && !RADIX_NO_PAIRS &&
-         R1 * R2 * R3 >= (sizeof(T) == 8 ? 256 : 1024);
+  return (LM == L_R_ORD || LM == L_R_Z) && SIGN > 0 && R3 > 1 && !RADIX_NO_PAIRS && sizeof(T) == 4 && R1 * R2 * R3 >= 1024 &&
+         (R1 <= 10 || (R1 <= 16 && R1 * R2 * R3 >= 3840));
 }
 
 // which (core, mode) takes the pair form (kernel and CPU stepping harness agree through this one function)
