@@ -172,7 +172,7 @@ inline bool ts_wanted(int Nc, bool dbl) {
   // round 2b: float cores 15360 ... 131071 WITHOUT a tuned plan of their own (tiled 2-D: 16384, 32768, 65536; general-radix
   // tiled: 20480 ... 61440) ran as two launches through HBM (decimated rows + combine: 0.23-0.35 of the roofline) or on the
   // multi-launch global path (0.08); the pipeline measured 0.35-0.45 at the two-pass sizes (profiles/r02b_large_n.md)
-  if (!other_choice && Nc >= 15360 && Nc < 131072) {
+  if (!other_choice && (Nc >= 15360 || Nc == 12800) && Nc < 131072) {          // (12800 = 160 x 80: split_16x800 0.27 -> 0.41)
     if (dbl) want = want || (Nc != 32768 && Nc != 65536);          // double: the general-radix tiled plan keeps those two
     else switch (Nc) {
       case 16384: case 20480: case 24576: case 32768: case 36864: case 40960: case 49152: case 61440: case 65536: break;

@@ -18,7 +18,7 @@ TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 POW2 = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144]
 NONPOW2 = [96, 160, 192, 288, 384, 480, 576, 640, 800, 864, 2592, 4000, 12000, 36864,
            1536, 2560, 3072, 5120, 6144, 7680, 9216, 10240, 12288,     # two-level plans that run as one kernel
-           15360, 18432, 23040, 30720, 57600]                           # pipeline instead of two launches (round 2b)
+           12800, 15360, 18432, 23040, 30720, 57600]                           # pipeline instead of two launches (round 2b)
 
 
 def torch_mod():
