@@ -13,7 +13,9 @@ const struct { int nc; const char* name; } kCoresD[] = {
     {432, "radix_9x8x6"}, {480, "radix_10x8x6"}, {1296, "radix_12x12x9"}, {2000, "radix_10x20x10"},
     {576, "radix_9x8x8"}, {640, "radix_10x8x8"}, {720, "radix_10x9x8"}, {768, "radix_12x8x8"}, {800, "radix_10x10x8"}, {864, "radix_12x9x8"},
     {960, "radix_12x10x8"}, {1152, "radix_12x12x8"}, {1200, "radix_12x10x10"}, {1280, "radix_16x10x8"}, {1440, "radix_12x12x10"},
-    {1600, "radix_16x10x10"}, {1728, "radix_12x12x12"}, {1920, "radix_16x12x10"}};
+    {1600, "radix_16x10x10"}, {1728, "radix_12x12x12"}, {1920, "radix_16x12x10"},
+    {2160, "radix_12x12x15"}, {2304, "radix_16x12x12"}, {2400, "radix_16x15x10"}, {2560, "radix_16x16x10"}, {2592, "radix_9x16x18"},
+    {2880, "radix_16x15x12"}, {3456, "radix_16x18x12"}, {3600, "radix_16x15x15"}, {3840, "radix_16x16x15"}};
 }
 int radix_launch_double_e(int Nc, int lm, int sm, int sign, const double* in, double* out, long long batch, const cd* tw, const cd* twr,
                           int device, int sm_count, cudaStream_t st);

@@ -1,4 +1,4 @@
-// radix_e.cu -- double-precision compile-time-radix CTA kernels, second translation unit: three-stage cores 576 ... 1920
+// radix_e.cu -- double-precision compile-time-radix CTA kernels, second translation unit: three-stage cores 576 ... 3840
 #include "radix_impl.cuh"
 namespace pf {
 int radix_launch_double_e(int Nc, int lm, int sm, int sign, const double* in, double* out, long long batch, const cd* tw, const cd* twr,
@@ -19,6 +19,16 @@ int radix_launch_double_e(int Nc, int lm, int sm, int sign, const double* in, do
     case 1600: return radix_launch_modes<double, 16, 10, 10, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 1728: return radix_launch_modes<double, 12, 12, 12, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     case 1920: return radix_launch_modes<double, 16, 12, 10, 1, 2>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    // 2160 ... 3840: radices up to 16 / 18 (a double radix-16 DFT holds 64 registers of data: one CTA per SM)
+    case 2160: return radix_launch_modes<double, 12, 12, 15, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2304: return radix_launch_modes<double, 16, 12, 12, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2400: return radix_launch_modes<double, 16, 15, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2560: return radix_launch_modes<double, 16, 16, 10, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2592: return radix_launch_modes<double, 9,  16, 18, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 2880: return radix_launch_modes<double, 16, 15, 12, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3456: return radix_launch_modes<double, 16, 18, 12, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3600: return radix_launch_modes<double, 16, 15, 15, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
+    case 3840: return radix_launch_modes<double, 16, 16, 15, 1, 1>(lm, sm, sign, in, out, batch, tw, twr, device, sm_count, st);
     default: return -1;
   }
 }

@@ -354,6 +354,8 @@ extern "C" int emu_radix_d(int N, int transform, int dir, int ordered, const dou
     D(432, 9, 8, 6) D(480, 10, 8, 6) D(1296, 12, 12, 9) D(2000, 10, 20, 10)
     D(576, 9, 8, 8) D(640, 10, 8, 8) D(720, 10, 9, 8) D(768, 12, 8, 8) D(800, 10, 10, 8) D(864, 12, 9, 8) D(960, 12, 10, 8)
     D(1152, 12, 12, 8) D(1200, 12, 10, 10) D(1280, 16, 10, 8) D(1440, 12, 12, 10) D(1600, 16, 10, 10) D(1728, 12, 12, 12) D(1920, 16, 12, 10)
+    D(2160, 12, 12, 15) D(2304, 16, 12, 12) D(2400, 16, 15, 10) D(2560, 16, 16, 10) D(2592, 9, 16, 18) D(2880, 16, 15, 12)
+    D(3456, 16, 18, 12) D(3600, 16, 15, 15) D(3840, 16, 16, 15)
 #undef D
   }
   return -1;

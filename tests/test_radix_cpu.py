@@ -47,7 +47,7 @@ def test_every_core_and_mode_vs_reference(emu, ref, R, core, tr):
 # double-precision cores (pffft_b200/csrc/radix_d.cu): against numpy float64 at 1e-12 (the reference's own double path carries
 # float-precision radix-3/5 constants)
 CORES_D = [16, 32, 48, 64, 80, 96, 128, 144, 160, 192, 240, 256, 288, 320, 384, 400, 432, 480, 576, 640, 720, 768, 800, 864, 960, 1152, 1200,
-           1280, 1296, 1440, 1600, 1728, 1920, 2000]
+           1280, 1296, 1440, 1600, 1728, 1920, 2000, 2160, 2304, 2400, 2560, 2592, 2880, 3456, 3600, 3840]
 
 
 def _numpy_forward(x, N, tr):
